@@ -1,0 +1,205 @@
+"""Pins the CPU oracle (oracle/ndi_oracle.cpp) against every golden vector the reference's own
+tests hold for the hot path and against scipy as an independent check."""
+import numpy as np
+import pytest
+
+import golden_util as G
+from oracle import oracle_py as O
+
+
+def _close(got, exp, tol):
+    got = np.asarray(got, dtype=np.float64).ravel()
+    exp = np.asarray(exp, dtype=np.float64).ravel()
+    assert got.shape == exp.shape
+    # approx::assert_relative_eq!(epsilon, max_relative): |a-b| <= eps OR |a-b| <= max(|a|,|b|)*rel
+    diff = np.abs(got - exp)
+    ok = (diff <= tol.get("abs", 0.0)) | (diff <= np.maximum(np.abs(got), np.abs(exp)) * tol.get("rel", 0.0))
+    assert ok.all(), f"max diff {diff.max()} at {diff.argmax()}: got {got[diff.argmax()]} exp {exp[diff.argmax()]}"
+
+
+@pytest.mark.parametrize("case", G.load("linear"), ids=lambda c: c["name"])
+def test_linear_golden(case):
+    dt = G.DT[case["dtype"]]
+    data = np.array(case["data"], dtype=dt)
+    x = np.array(case["x"], dtype=dt) if case["x"] is not None else G.default_axis(len(data), dt)
+    q = np.array(case["query"], dtype=dt)
+    st, out, _ = O.interp1d_linear(x, data, q, case["extrapolate"])
+    assert st == O.ST_OK
+    exp = np.array(case["expect"], dtype=dt)
+    assert out.shape == exp.shape
+    if case["tol"]["abs"] == 0.0:
+        assert np.array_equal(out, exp)          # assert_eq! in the reference
+    else:
+        _close(out, exp, case["tol"])
+
+
+@pytest.mark.parametrize("case", G.load("bilinear"), ids=lambda c: c["name"])
+def test_bilinear_golden(case):
+    dt = G.DT[case["dtype"]]
+    data = G.materialise(case["data"], dt)
+    x = np.array(case["x"], dtype=dt) if case.get("x") is not None else G.default_axis(data.shape[0], dt)
+    y = np.array(case["y"], dtype=dt) if case.get("y") is not None else G.default_axis(data.shape[1], dt)
+    qx, qy = G.materialise(case["qx"], dt), G.materialise(case["qy"], dt)
+    st, out, _, _ = O.interp2d_bilinear(x, y, data, qx, qy, case.get("extrapolate", False))
+    assert st == O.ST_OK
+    exp = np.array(case["expect"], dtype=dt).reshape(out.shape)
+    if case["name"] == "interpolate_array":
+        # the restatement reproduces all 121 values bit-exactly
+        assert np.array_equal(out, exp)
+    elif case["tol"]["abs"] == 0.0:
+        assert np.array_equal(out, exp)
+    else:
+        _close(out, exp, case["tol"])
+
+
+@pytest.mark.parametrize("case", G.load("cubic"), ids=lambda c: c["name"])
+def test_cubic_golden(case):
+    dt = G.DT[case["dtype"]]
+    data = np.array(case["data"], dtype=dt)
+    x = np.array(case["x"], dtype=dt) if case["x"] is not None else G.default_axis(len(data), dt)
+    q = G.materialise(case["query"], dt)
+    st, out = O.cubic_interp(x, data, case["bc"], case["extrapolate"], q)
+    assert st == O.ST_OK
+    exp = np.array(case["expect"], dtype=dt).reshape(out.shape)
+    if case["name"] == "doctest_wikipedia":
+        assert np.array_equal(out, exp)          # bit-exact incl. -5.551115123125783e-17
+    _close(out, exp, case["tol"])
+
+
+def test_oob_pins():
+    for case in G.load("oob1d"):
+        data = np.array(case["data"])
+        x = np.array(case["x"]) if case["x"] is not None else G.default_axis(len(data), np.float64)
+        for i, qv in enumerate(case["queries"]):
+            st, _, bad = O.interp1d_linear(x, data, np.array([0.0 + x[0], qv]), False)
+            assert (st, bad) == (O.ST_OUT_OF_BOUNDS, 1)
+    for case in G.load("oob1d_cubic"):
+        data = np.array(case["data"])
+        x = G.default_axis(len(data), np.float64)
+        st, a, b = O.spline_build(x, data, {"kind": "NotAKnot"})
+        assert st == O.ST_OK
+        for qv in case["queries"]:
+            st, _, bad = O.interp1d_cubic(x, data, a, b, np.array([qv]), 0)
+            assert (st, bad) == (O.ST_OUT_OF_BOUNDS, 0)
+    for case in G.load("oob2d"):
+        data = np.array(case["data"], dtype=np.int32)
+        x, y = G.default_axis(3, np.int32), G.default_axis(4, np.int32)
+        for qx, qy, axis in case["queries"]:
+            st, _, bad, ax = O.interp2d_bilinear(x, y, data, np.array([qx], np.int32), np.array([qy], np.int32), False)
+            assert (st, bad, ax) == (O.ST_OUT_OF_BOUNDS, 0, axis)
+
+
+@pytest.mark.parametrize("case", G.load("index"), ids=lambda c: c["name"])
+def test_lower_index_golden(case):
+    grid = G.index_grid(case["grid"])
+    exp = np.array([p[0] for p in case["pairs"]], dtype=np.int64)
+    q = np.array([G.index_query(p[1]) for p in case["pairs"]])
+    st, idx, _ = O.lower_index(grid, q)
+    assert st == O.ST_OK
+    assert np.array_equal(idx, exp)
+
+
+def test_lower_index_nan_panics():
+    st, _, bad = O.lower_index(G.index_grid("linspace"), np.array([1.0, np.nan]))
+    assert (st, bad) == (O.ST_NAN_QUERY, 1)
+
+
+@pytest.mark.parametrize("case", G.load("monotonic"), ids=lambda c: c["name"])
+def test_monotonic_golden(case):
+    x = np.array(case["x"], dtype=G.DT[case["dtype"]])
+    assert O.monotonic_prop(x, case["stride"]) == case["expect"]
+    if case["stride"] == 1:
+        assert O.monotonic_prop(x[::1], 1) == case["expect"]
+
+
+def test_monotonic_nan_semantics():
+    # vector_extensions.rs:136-170: an unordered pair is "else" in Init/NotStrict (-> Falling)
+    # and "else" in the Likely states (-> NotMonotonic)
+    nan = np.nan
+    assert O.monotonic_prop(np.array([nan, 1.0])) == "FallingStrict"
+    assert O.monotonic_prop(np.array([1.0, 1.0, nan])) == "Falling"
+    assert O.monotonic_prop(np.array([1.0, 2.0, nan])) == "NotMonotonic"
+    assert O.monotonic_prop(np.array([3.0, 2.0, nan])) == "NotMonotonic"
+
+
+# ---- independent cross-check: scipy.interpolate.CubicSpline ---------------------------------------
+@pytest.mark.parametrize("bc,scipy_bc", [("Natural", "natural"), ("NotAKnot", "not-a-knot"),
+                                         ("Clamped", "clamped"), ("Periodic", "periodic")])
+def test_cubic_vs_scipy(bc, scipy_bc):
+    from scipy.interpolate import CubicSpline
+    rng = np.random.default_rng(7)
+    n, w = 40, 3
+    # NotAKnot: uniform grid only -- on a non-uniform grid the REFERENCE deviates from scipy
+    # (see test_not_a_knot_right_boundary_quirk); the oracle follows the reference.
+    x = np.arange(n) * 0.75 + 1.0 if bc == "NotAKnot" else np.cumsum(rng.uniform(0.5, 1.5, n))
+    y = rng.normal(size=(n, w))
+    if bc == "Periodic":
+        y[-1] = y[0]
+    q = rng.uniform(x[0], x[-1], 500)
+    st, out = O.cubic_interp(x, y, {"kind": bc}, False, q)
+    assert st == O.ST_OK
+    ref = CubicSpline(x, y, axis=0, bc_type=scipy_bc)(q)
+    scale = np.abs(y).max()
+    assert np.abs(out - ref).max() <= 1e-12 * scale
+
+
+def test_cubic_deriv_bcs_vs_scipy():
+    from scipy.interpolate import CubicSpline
+    rng = np.random.default_rng(8)
+    n = 25
+    x = np.cumsum(rng.uniform(0.5, 1.5, n))
+    y = rng.normal(size=n)
+    q = rng.uniform(x[0], x[-1], 300)
+    for lk, rk, sl, sr in [("FirstDeriv", "SecondDeriv", 1, 2), ("SecondDeriv", "FirstDeriv", 2, 1),
+                           ("NotAKnot", "FirstDeriv", None, 1)]:
+        bc = {"kind": "Individual", "rows": [{"kind": "Mixed", "left": {"kind": lk, "value": 0.3},
+                                             "right": {"kind": rk, "value": -0.7}}]}
+        st, out = O.cubic_interp(x, y, bc, False, q)
+        assert st == O.ST_OK
+        left = "not-a-knot" if sl is None else (sl, 0.3)
+        ref = CubicSpline(x, y, bc_type=(left, (sr, -0.7)))(q)
+        assert np.abs(out - ref).max() <= 1e-12 * np.abs(y).max()
+
+
+def test_not_a_knot_right_boundary_quirk():
+    """cubic_spline.rs:635 sets the last diagonal entry to dx[n-2] (x[n-1]-x[n-2]) where the
+    textbook/scipy system has dx[n-3].  Identical on uniform grids (all the reference's own
+    NotAKnot tests), different otherwise.  Parity means following the reference, so the oracle
+    (and the CUDA path) reproduce the quirk; this test documents it."""
+    from scipy.interpolate import CubicSpline
+    rng = np.random.default_rng(7)
+    n = 40
+    x = np.cumsum(rng.uniform(0.5, 1.5, n))
+    y = rng.normal(size=n)
+    q = np.linspace(x[0], x[-1], 400)
+    st, out = O.cubic_interp(x, y, {"kind": "NotAKnot"}, False, q)
+    assert st == O.ST_OK
+    ref = CubicSpline(x, y, bc_type="not-a-knot")(q)
+    left = q < x[n // 2]
+    assert np.abs(out - ref)[left].max() < 1e-6       # the left end is the textbook system
+    assert np.abs(out - ref)[~left].max() > 1e-3      # the right end is not
+    # still an interpolant: exact at the knots
+    st, at_knots = O.cubic_interp(x, y, {"kind": "NotAKnot"}, False, x)
+    assert np.abs(at_knots - y).max() < 1e-12
+
+
+def test_periodic_mismatch_is_value_error():
+    x = np.array([0.0, 1.0, 2.0, 3.0])
+    st, _, _ = O.spline_build(x, np.array([[0.5, 1.0], [0.0, 1.5], [0.2, 0.1], [0.5, 1.1]]), {"kind": "Periodic"})
+    assert st == O.ST_PERIODIC_MISMATCH
+    st, _, _ = O.spline_build(x[:3], np.array([[0.5, 1.0], [0.0, 1.5], [0.5, 1.1]]), {"kind": "Periodic"})
+    assert st == O.ST_PERIODIC_MISMATCH
+
+
+def test_fma_would_break_parity():
+    """the oracle must be built without FMA contraction.  Check that calc_frac
+    equals the unfused numpy evaluation on a cancellation-heavy sample (numpy never fuses)."""
+    rng = np.random.default_rng(1)
+    n = 20000
+    x1 = rng.uniform(0, 1, n).astype(np.float32); x2 = x1 + rng.uniform(0.01, 1, n).astype(np.float32)
+    y1 = rng.uniform(-1, 1, n).astype(np.float32); y2 = rng.uniform(-1, 1, n).astype(np.float32)
+    x = (x1 + (x2 - x1) * rng.uniform(0, 1, n).astype(np.float32)).astype(np.float32)
+    ref = ((y2 - y1) / (x2 - x1)) * (x - x1) + y1
+    got = np.array([O.calc_frac(float(a), float(b), float(c), float(d), float(e), np.float32)
+                    for a, b, c, d, e in zip(x1, y1, x2, y2, x)], dtype=np.float32)
+    assert np.array_equal(got, ref)
