@@ -1,0 +1,760 @@
+// ndi_api.cu -- the C ABI (include/ndi_b200.h): handles, table upload, dtype dispatch and the
+// host-buffer pipeline around the kernels.  No interpolation arithmetic happens on the host.
+//
+// Host entry points (no _dev suffix):
+//   small batches : one fused launch (evaluation + first-error word), results staged through a
+//                   pinned buffer and copied out with a single synchronisation -- this is the
+//                   latency path of interp_scalar / interp / interp_into.
+//   large batches : (1) queries uploaded once, (2) K7 pre-pass finds the first query the reference
+//                   would fail on, (3) only the rows before it are evaluated, in chunks alternating
+//                   between two streams so the D2H copy of one chunk overlaps the kernel of the
+//                   next.  Rows at and after the failing query stay untouched, like the reference
+//                   (interp1d/mod.rs:321,336-340).
+// All per-call state lives in a thread-local workspace, so one handle can be used from many
+// threads at once (the reference's &self methods are called from rayon workers).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "../../include/ndi_b200.h"
+#include "ndi_internal.h"
+
+namespace ndi {
+
+// ---- errors ----------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static ndi_status fail(ndi_status st, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return st;
+}
+static ndi_status cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    cudaGetLastError();   // clear the sticky-free error state
+    return NDI_CUDA_ERROR + (ndi_status)e;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);      \
+    } while (0)
+
+// ---- device info / launch counter -------------------------------------------------------------------
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+const DeviceInfo& device_info() {
+    static std::mutex mu;
+    static std::map<int, DeviceInfo> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    DeviceInfo di{dev, 148, 48 * 1024};
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) di.sm_count = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && v > 0) di.smem_optin = (size_t)v;
+    return cache.emplace(dev, di).first->second;
+}
+
+struct DeviceGuard {
+    int prev = -1; bool changed = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+
+static size_t elem_size(ndi_dtype d) { return d == NDI_F64 ? 8 : 4; }
+static bool dtype_ok(ndi_dtype d) { return d == NDI_F32 || d == NDI_F64 || d == NDI_I32; }
+
+template <class F>
+static ndi_status dispatch(ndi_dtype d, F&& f) {
+    switch (d) {
+    case NDI_F32: return f(float{});
+    case NDI_F64: return f(double{});
+    case NDI_I32: return f(int32_t{});
+    default: return fail(NDI_UNSUPPORTED_DTYPE, "unsupported dtype %d", (int)d);
+    }
+}
+template <class F>
+static ndi_status dispatch_float(ndi_dtype d, F&& f) {
+    switch (d) {
+    case NDI_F32: return f(float{});
+    case NDI_F64: return f(double{});
+    default: return fail(NDI_UNSUPPORTED_DTYPE, "cubic splines need a float dtype (SplineNum), got %d", (int)d);
+    }
+}
+
+// ---- thread-local workspace --------------------------------------------------------------------------
+constexpr size_t kChunkBytes = 64ull << 20;    // output bytes per pipeline chunk
+constexpr size_t kSmallBytes = 256ull << 10;   // outputs up to this size take the single-sync path
+
+struct Workspace {
+    bool ready = false;
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t ev = nullptr;
+    void* d_q[2] = {nullptr, nullptr}; size_t d_q_cap[2] = {0, 0};
+    void* d_out[2] = {nullptr, nullptr}; size_t d_out_cap[2] = {0, 0};
+    unsigned long long* d_err = nullptr;      // 4 words
+    int32_t* d_res = nullptr;                 // 2 words (grid classify result)
+    uint32_t* d_scr = nullptr;                // grid classify scratch
+    unsigned char* h_pin = nullptr; size_t h_pin_cap = 0;   // pinned: [err words | small outputs]
+};
+
+static Workspace* workspace(int dev, ndi_status* st) {
+    static thread_local std::map<int, Workspace> per_dev;
+    Workspace& w = per_dev[dev];
+    *st = NDI_OK;
+    if (w.ready) return &w;
+    cudaError_t e;
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaStreamCreateWithFlags(&w.s[i], cudaStreamNonBlocking)) != cudaSuccess) { *st = cuda_fail(e, "cudaStreamCreate"); return nullptr; }
+    if ((e = cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming)) != cudaSuccess) { *st = cuda_fail(e, "cudaEventCreate"); return nullptr; }
+    if ((e = cudaMalloc(&w.d_err, 4 * sizeof(unsigned long long))) != cudaSuccess) { *st = cuda_fail(e, "cudaMalloc"); return nullptr; }
+    if ((e = cudaMalloc(&w.d_res, 2 * sizeof(int32_t))) != cudaSuccess) { *st = cuda_fail(e, "cudaMalloc"); return nullptr; }
+    if ((e = cudaMalloc(&w.d_scr, grid_classify_scratch_words() * sizeof(uint32_t))) != cudaSuccess) { *st = cuda_fail(e, "cudaMalloc"); return nullptr; }
+    w.h_pin_cap = 64 + kSmallBytes;
+    if ((e = cudaMallocHost(&w.h_pin, w.h_pin_cap)) != cudaSuccess) { *st = cuda_fail(e, "cudaMallocHost"); return nullptr; }
+    w.ready = true;
+    return &w;
+}
+static ndi_status grow(void** p, size_t* cap, size_t need) {
+    if (*cap >= need) return NDI_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    size_t want = need + need / 4;
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) { want = need; e = cudaMalloc(p, want); }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
+    *cap = want;
+    return NDI_OK;
+}
+
+// ---- search configuration ----------------------------------------------------------------------------
+static SearchCfg make_search(int64_t n, size_t elem, int uniform_hint, int mode, int64_t nq, size_t other_smem) {
+    SearchCfg sc{bisect_top_step(n), 0, 0};
+    const size_t bytes = (size_t)n * elem;
+    const size_t room = device_info().smem_optin > other_smem + 1024 ? device_info().smem_optin - other_smem - 1024 : 0;
+    switch (mode) {
+    case NDI_SEARCH_BINARY_GLOBAL: break;
+    case NDI_SEARCH_BINARY_SMEM: sc.smem = bytes <= room; break;
+    case NDI_SEARCH_UNIFORM_GUESS: sc.guess = 1; break;
+    default:   // AUTO: O(1) guess on grids where it always hits; else stage small grids for big batches
+        if (uniform_hint) sc.guess = 1;
+        else if (bytes <= 48 * 1024 && bytes <= room && nq >= 32768) sc.smem = 1;
+        break;
+    }
+    return sc;
+}
+
+}  // namespace ndi
+
+using namespace ndi;
+
+// ---- handles ---------------------------------------------------------------------------------------------
+struct ndi_interp1d {
+    ndi_dtype dtype; int device; int64_t n, w;
+    void* x; void* data; void* a; void* b;
+    bool owns_tables, owns_coeffs;
+    int uniform_hint; int search_mode;
+};
+struct ndi_interp2d {
+    ndi_dtype dtype; int device; int64_t n, m, w;
+    void* x; void* y; void* data;
+    bool owns_tables;
+    int hint_x, hint_y; int search_mode;
+};
+
+// upload or adopt one table
+static ndi_status take_table(const void* src, size_t bytes, uint32_t flags, cudaStream_t st, void** dst, bool* owned) {
+    if ((flags & NDI_DEVICE_POINTERS) && (flags & NDI_BORROW)) { *dst = const_cast<void*>(src); *owned = false; return NDI_OK; }
+    CK(cudaMalloc(dst, bytes ? bytes : 1));
+    *owned = true;
+    if (bytes) CK(cudaMemcpyAsync(*dst, src, bytes, (flags & NDI_DEVICE_POINTERS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    return NDI_OK;
+}
+
+// K1 on an uploaded grid: Monotonic enum and the uniform-guess flag
+static ndi_status classify_grid(ndi_dtype dtype, const void* x_dev, int64_t n, Workspace* ws, int32_t res[2]) {
+    ndi_status st = dispatch(dtype, [&](auto tag) -> ndi_status {
+        using T = decltype(tag);
+        CK(launch_grid_classify<T>((const T*)x_dev, n, ws->d_res, ws->d_scr, ws->s[0]));
+        return NDI_OK;
+    });
+    if (st != NDI_OK) return st;
+    CK(cudaMemcpyAsync(ws->h_pin, ws->d_res, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ws->s[0]));
+    CK(cudaStreamSynchronize(ws->s[0]));
+    memcpy(res, ws->h_pin, 2 * sizeof(int32_t));
+    return NDI_OK;
+}
+
+extern "C" {
+
+const char* ndi_version_string(void) { return "ndarray-interp-b200 0.1 (sm_100a)"; }
+const char* ndi_last_error_message(void) { return g_err; }
+uint64_t ndi_kernel_launch_count(void) { return g_launches.load(); }
+
+ndi_status ndi_device_count(int32_t* count) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *count = 0; return cuda_fail(e, "cudaGetDeviceCount"); }
+    *count = c;
+    return c > 0 ? NDI_OK : fail(NDI_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+}
+ndi_status ndi_set_device(int32_t device) { CK(cudaSetDevice(device)); return NDI_OK; }
+ndi_status ndi_get_device(int32_t* device) { int d = 0; CK(cudaGetDevice(&d)); *device = d; return NDI_OK; }
+
+// ---- vector_extensions --------------------------------------------------------------------------------------
+ndi_status ndi_monotonic_prop(ndi_dtype dtype, const void* x, int64_t n, int64_t stride, int32_t* prop) {
+    if (!dtype_ok(dtype)) return fail(NDI_UNSUPPORTED_DTYPE, "unsupported dtype %d", (int)dtype);
+    if (!prop || (n > 0 && !x)) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    *prop = NDI_MONO_NOT_MONOTONIC;
+    if (n <= 1) return NDI_OK;                                   // vector_extensions.rs:41-43
+    int dev = 0; CK(cudaGetDevice(&dev));
+    ndi_status st; Workspace* ws = workspace(dev, &st); if (!ws) return st;
+    const size_t es = elem_size(dtype), bytes = (size_t)n * es;
+    // a strided (possibly reversed) view is made contiguous on the way to the device
+    std::vector<unsigned char> packed;
+    const void* src = x;
+    if (stride != 1) {
+        packed.resize(bytes);
+        for (int64_t i = 0; i < n; ++i) memcpy(packed.data() + (size_t)i * es, (const unsigned char*)x + i * stride * (int64_t)es, es);
+        src = packed.data();
+    }
+    if ((st = grow(&ws->d_q[0], &ws->d_q_cap[0], bytes)) != NDI_OK) return st;
+    CK(cudaMemcpyAsync(ws->d_q[0], src, bytes, cudaMemcpyHostToDevice, ws->s[0]));
+    int32_t res[2];
+    if ((st = classify_grid(dtype, ws->d_q[0], n, ws, res)) != NDI_OK) return st;
+    *prop = res[0];
+    return NDI_OK;
+}
+
+ndi_status ndi_lower_index_dev(ndi_dtype dtype, const void* grid_dev, int64_t n, const void* q_dev, int64_t nq,
+                               int64_t* idx_dev, uint64_t* err_word_dev, int32_t search_mode, void* stream) {
+    if (n < 2) return fail(NDI_INVALID_ARGUMENT, "grid needs at least 2 points, got %lld", (long long)n);
+    if (n > 0x7fffffffll) return fail(NDI_INVALID_ARGUMENT, "grid longer than 2^31-1");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (err_word_dev) CK(cudaMemsetAsync(err_word_dev, 0xff, sizeof(uint64_t), st));
+    return dispatch(dtype, [&](auto tag) -> ndi_status {
+        using T = decltype(tag);
+        SearchCfg sc = make_search(n, sizeof(T), 0, search_mode, nq, 0);
+        CK(launch_lower_index<T>((const T*)grid_dev, n, sc, (const T*)q_dev, nq, idx_dev, (unsigned long long*)err_word_dev, st));
+        return NDI_OK;
+    });
+}
+
+ndi_status ndi_lower_index(ndi_dtype dtype, const void* grid, int64_t n, const void* q, int64_t nq, int64_t* idx,
+                           int64_t* first_bad) {
+    if (!dtype_ok(dtype)) return fail(NDI_UNSUPPORTED_DTYPE, "unsupported dtype %d", (int)dtype);
+    if (first_bad) *first_bad = -1;
+    if (nq <= 0) return NDI_OK;
+    if (!grid || !q || !idx) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    int dev = 0; CK(cudaGetDevice(&dev));
+    ndi_status st; Workspace* ws = workspace(dev, &st); if (!ws) return st;
+    const size_t es = elem_size(dtype);
+    if ((st = grow(&ws->d_q[0], &ws->d_q_cap[0], (size_t)nq * es)) != NDI_OK) return st;
+    if ((st = grow(&ws->d_q[1], &ws->d_q_cap[1], (size_t)n * es)) != NDI_OK) return st;
+    if ((st = grow(&ws->d_out[0], &ws->d_out_cap[0], (size_t)nq * sizeof(int64_t))) != NDI_OK) return st;
+    CK(cudaMemcpyAsync(ws->d_q[1], grid, (size_t)n * es, cudaMemcpyHostToDevice, ws->s[0]));
+    CK(cudaMemcpyAsync(ws->d_q[0], q, (size_t)nq * es, cudaMemcpyHostToDevice, ws->s[0]));
+    st = ndi_lower_index_dev(dtype, ws->d_q[1], n, ws->d_q[0], nq, (int64_t*)ws->d_out[0], (uint64_t*)ws->d_err, NDI_SEARCH_AUTO, ws->s[0]);
+    if (st != NDI_OK) return st;
+    CK(cudaMemcpyAsync(ws->h_pin, ws->d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws->s[0]));
+    CK(cudaStreamSynchronize(ws->s[0]));
+    uint64_t word; memcpy(&word, ws->h_pin, sizeof(word));
+    const int64_t nvalid = word == NDI_ERR_WORD_NONE ? nq : (int64_t)word;
+    if (nvalid > 0) {
+        CK(cudaMemcpyAsync(idx, ws->d_out[0], (size_t)nvalid * sizeof(int64_t), cudaMemcpyDeviceToHost, ws->s[0]));
+        CK(cudaStreamSynchronize(ws->s[0]));
+    }
+    if (word != NDI_ERR_WORD_NONE) {
+        if (first_bad) *first_bad = (int64_t)word;
+        return fail(NDI_NAN_QUERY, "not implemented: failed to convert NaN to usize (query %lld)", (long long)word);
+    }
+    return NDI_OK;
+}
+
+// ---- Interp1D ------------------------------------------------------------------------------------------------
+ndi_status ndi_interp1d_create(ndi_dtype dtype, const void* x, int64_t n, const void* data, int64_t w, uint32_t flags,
+                               ndi_interp1d** out) {
+    if (!out) return fail(NDI_INVALID_ARGUMENT, "null handle pointer");
+    *out = nullptr;
+    if (!dtype_ok(dtype)) return fail(NDI_UNSUPPORTED_DTYPE, "unsupported dtype %d", (int)dtype);
+    if (!x || !data) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    if (n < 2 || w < 1) return fail(NDI_INVALID_ARGUMENT, "need n >= 2 and w >= 1, got n=%lld w=%lld", (long long)n, (long long)w);
+    if (n > 0x7fffffffll) return fail(NDI_INVALID_ARGUMENT, "grid longer than 2^31-1");
+    int dev = 0; CK(cudaGetDevice(&dev));
+    ndi_status st; Workspace* ws = workspace(dev, &st); if (!ws) return st;
+    const size_t es = elem_size(dtype);
+    ndi_interp1d* h = new ndi_interp1d{dtype, dev, n, w, nullptr, nullptr, nullptr, nullptr, false, false, 0, NDI_SEARCH_AUTO};
+    bool ox = false, od = false;
+    if ((st = take_table(x, (size_t)n * es, flags, ws->s[0], &h->x, &ox)) != NDI_OK) { delete h; return st; }
+    if ((st = take_table(data, (size_t)n * (size_t)w * es, flags, ws->s[0], &h->data, &od)) != NDI_OK) {
+        if (ox) cudaFree(h->x);
+        delete h; return st;
+    }
+    h->owns_tables = ox;
+    int32_t res[2] = {0, 0};
+    st = classify_grid(dtype, h->x, n, ws, res);           // also drains the upload
+    if (st == NDI_OK && !(flags & NDI_ASSUME_VALID) && res[0] != NDI_MONO_RISING_STRICT)
+        st = fail(NDI_NOT_MONOTONIC, "Values in the x axis need to be strictly monotonic rising");
+    if (st != NDI_OK) { ndi_interp1d_destroy(h); return st; }
+    h->uniform_hint = res[0] == NDI_MONO_RISING_STRICT ? res[1] : 0;
+    *out = h;
+    return NDI_OK;
+}
+
+ndi_status ndi_interp1d_destroy(ndi_interp1d* h) {
+    if (!h) return NDI_OK;
+    DeviceGuard g(h->device);
+    if (h->owns_tables) { cudaFree(h->x); cudaFree(h->data); }
+    if (h->owns_coeffs) { cudaFree(h->a); cudaFree(h->b); }
+    delete h;
+    return NDI_OK;
+}
+
+ndi_status ndi_interp1d_info(const ndi_interp1d* h, ndi_dtype* dtype, int64_t* n, int64_t* w, int32_t* has_spline, int32_t* device) {
+    if (!h) return fail(NDI_INVALID_ARGUMENT, "null handle");
+    if (dtype) *dtype = h->dtype;
+    if (n) *n = h->n;
+    if (w) *w = h->w;
+    if (has_spline) *has_spline = h->a != nullptr;
+    if (device) *device = h->device;
+    return NDI_OK;
+}
+ndi_status ndi_interp1d_set_search_mode(ndi_interp1d* h, int32_t mode) {
+    if (!h || mode < 0 || mode > 3) return fail(NDI_INVALID_ARGUMENT, "bad search mode");
+    h->search_mode = mode;
+    return NDI_OK;
+}
+ndi_status ndi_interp1d_device_ptrs(const ndi_interp1d* h, const void** x, const void** data, const void** a, const void** b) {
+    if (!h) return fail(NDI_INVALID_ARGUMENT, "null handle");
+    if (x) *x = h->x;
+    if (data) *data = h->data;
+    if (a) *a = h->a;
+    if (b) *b = h->b;
+    return NDI_OK;
+}
+
+ndi_status ndi_interp1d_clone_to_device(const ndi_interp1d* h, int32_t device, ndi_interp1d** out) {
+    if (!h || !out) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    *out = nullptr;
+    DeviceGuard g(device);
+    const size_t es = elem_size(h->dtype);
+    ndi_interp1d* c = new ndi_interp1d(*h);
+    c->device = device; c->owns_tables = true; c->owns_coeffs = h->a != nullptr;
+    c->x = c->data = c->a = c->b = nullptr;
+    auto copy = [&](void** dst, const void* src, size_t bytes) -> ndi_status {
+        CK(cudaMalloc(dst, bytes));
+        CK(cudaMemcpyPeer(*dst, device, src, h->device, bytes));   // NVLink peer copy
+        return NDI_OK;
+    };
+    ndi_status st = copy(&c->x, h->x, (size_t)h->n * es);
+    if (st == NDI_OK) st = copy(&c->data, h->data, (size_t)h->n * h->w * es);
+    if (st == NDI_OK && h->a) st = copy(&c->a, h->a, (size_t)(h->n - 1) * h->w * es);
+    if (st == NDI_OK && h->b) st = copy(&c->b, h->b, (size_t)(h->n - 1) * h->w * es);
+    if (st != NDI_OK) { cudaFree(c->x); cudaFree(c->data); cudaFree(c->a); cudaFree(c->b); delete c; return st; }
+    *out = c;
+    return NDI_OK;
+}
+
+}  // extern "C"
+
+// ---- host-buffer pipeline -----------------------------------------------------------------------------------
+namespace {
+
+struct HostEval {
+    int device; size_t es; int ncoord; int64_t w;
+    const void* q[2]; int64_t nq; void* out;
+    // launch(q0_dev, q1_dev, nq, out_dev, err_dev, stream) evaluates a contiguous range of queries
+    // validate(q0_dev, q1_dev, nq, err_dev, stream) is the K7 pre-pass over all queries
+};
+
+template <class Launch, class Validate>
+ndi_status run_host_eval(const HostEval& he, Launch&& launch, Validate&& validate, uint64_t* err_word) {
+    *err_word = NDI_ERR_WORD_NONE;
+    if (he.nq <= 0) return NDI_OK;
+    DeviceGuard g(he.device);
+    ndi_status st; Workspace* ws = workspace(he.device, &st); if (!ws) return st;
+    const size_t qbytes = (size_t)he.nq * he.es;
+    const size_t row = (size_t)he.w * he.es;
+    for (int c = 0; c < he.ncoord; ++c) {
+        if ((st = grow(&ws->d_q[c], &ws->d_q_cap[c], qbytes)) != NDI_OK) return st;
+        CK(cudaMemcpyAsync(ws->d_q[c], he.q[c], qbytes, cudaMemcpyHostToDevice, ws->s[0]));
+    }
+    const void* dq0 = ws->d_q[0];
+    const void* dq1 = he.ncoord > 1 ? ws->d_q[1] : nullptr;
+    unsigned long long* d_err = ws->d_err;
+    const size_t total = (size_t)he.nq * row;
+
+    if (total <= kSmallBytes) {
+        // latency path: fused launch, one synchronisation
+        if ((st = grow(&ws->d_out[0], &ws->d_out_cap[0], total)) != NDI_OK) return st;
+        CK(cudaMemsetAsync(d_err, 0xff, sizeof(uint64_t), ws->s[0]));
+        if ((st = launch(dq0, dq1, he.nq, ws->d_out[0], d_err, ws->s[0])) != NDI_OK) return st;
+        CK(cudaMemcpyAsync(ws->h_pin, d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws->s[0]));
+        CK(cudaMemcpyAsync(ws->h_pin + 64, ws->d_out[0], total, cudaMemcpyDeviceToHost, ws->s[0]));
+        CK(cudaStreamSynchronize(ws->s[0]));
+        memcpy(err_word, ws->h_pin, sizeof(uint64_t));
+        int64_t nvalid = he.nq;
+        if (*err_word != NDI_ERR_WORD_NONE) nvalid = (int64_t)(he.ncoord > 1 ? *err_word >> 1 : *err_word);
+        memcpy(he.out, ws->h_pin + 64, (size_t)nvalid * row);
+        return NDI_OK;
+    }
+
+    // K7 pre-pass: where would the reference stop?
+    CK(cudaMemsetAsync(d_err, 0xff, sizeof(uint64_t), ws->s[0]));
+    if ((st = validate(dq0, dq1, he.nq, d_err, ws->s[0])) != NDI_OK) return st;
+    CK(cudaMemcpyAsync(ws->h_pin, d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws->s[0]));
+    CK(cudaStreamSynchronize(ws->s[0]));
+    memcpy(err_word, ws->h_pin, sizeof(uint64_t));
+    int64_t nvalid = he.nq;
+    if (*err_word != NDI_ERR_WORD_NONE) nvalid = (int64_t)(he.ncoord > 1 ? *err_word >> 1 : *err_word);
+
+    int64_t per_chunk = (int64_t)(kChunkBytes / row);
+    per_chunk = per_chunk < 32 ? 32 : (per_chunk & ~31ll);
+    const size_t chunk_bytes = (size_t)per_chunk * row;
+    int slot = 0;
+    for (int64_t lo = 0; lo < nvalid; lo += per_chunk, slot ^= 1) {
+        const int64_t cnt = nvalid - lo < per_chunk ? nvalid - lo : per_chunk;
+        if ((st = grow(&ws->d_out[slot], &ws->d_out_cap[slot], chunk_bytes < total ? chunk_bytes : total)) != NDI_OK) return st;
+        const void* c0 = (const unsigned char*)dq0 + (size_t)lo * he.es;
+        const void* c1 = dq1 ? (const unsigned char*)dq1 + (size_t)lo * he.es : nullptr;
+        if ((st = launch(c0, c1, cnt, ws->d_out[slot], nullptr, ws->s[slot])) != NDI_OK) return st;
+        CK(cudaMemcpyAsync((unsigned char*)he.out + (size_t)lo * row, ws->d_out[slot], (size_t)cnt * row,
+                           cudaMemcpyDeviceToHost, ws->s[slot]));
+    }
+    CK(cudaStreamSynchronize(ws->s[0]));
+    CK(cudaStreamSynchronize(ws->s[1]));
+    return NDI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+static ndi_status check_eval_args(const void* h, const void* q, int64_t nq, const void* out) {
+    if (!h) return fail(NDI_INVALID_ARGUMENT, "null handle");
+    if (nq < 0) return fail(NDI_INVALID_ARGUMENT, "negative query count");
+    if (nq > 0 && (!q || !out)) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    return NDI_OK;
+}
+
+ndi_status ndi_interp1d_linear_dev(const ndi_interp1d* h, const void* q_dev, int64_t nq, int32_t extrapolate,
+                                   void* out_dev, uint64_t* err_word_dev, void* stream) {
+    ndi_status st = check_eval_args(h, q_dev, nq, out_dev); if (st != NDI_OK) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (err_word_dev) CK(cudaMemsetAsync(err_word_dev, 0xff, sizeof(uint64_t), s));
+    return dispatch(h->dtype, [&](auto tag) -> ndi_status {
+        using T = decltype(tag);
+        SearchCfg sc = make_search(h->n, sizeof(T), h->uniform_hint, h->search_mode, nq, 0);
+        CK(launch_interp1d_linear<T>((const T*)h->x, h->n, sc, (const T*)h->data, h->w, (const T*)q_dev, nq, extrapolate != 0,
+                                     (T*)out_dev, (unsigned long long*)err_word_dev, s));
+        return NDI_OK;
+    });
+}
+
+ndi_status ndi_interp1d_linear(const ndi_interp1d* h, const void* q, int64_t nq, int32_t extrapolate, void* out,
+                               int64_t* first_bad) {
+    if (first_bad) *first_bad = -1;
+    ndi_status st = check_eval_args(h, q, nq, out); if (st != NDI_OK) return st;
+    HostEval he{h->device, elem_size(h->dtype), 1, h->w, {q, nullptr}, nq, out};
+    uint64_t word;
+    st = dispatch(h->dtype, [&](auto tag) -> ndi_status {
+        using T = decltype(tag);
+        SearchCfg sc = make_search(h->n, sizeof(T), h->uniform_hint, h->search_mode, nq, 0);
+        return run_host_eval(he,
+            [&](const void* q0, const void*, int64_t cnt, void* o, unsigned long long* err, cudaStream_t s) -> ndi_status {
+                CK(launch_interp1d_linear<T>((const T*)h->x, h->n, sc, (const T*)h->data, h->w, (const T*)q0, cnt, extrapolate != 0, (T*)o, err, s));
+                return NDI_OK;
+            },
+            [&](const void* q0, const void*, int64_t cnt, unsigned long long* err, cudaStream_t s) -> ndi_status {
+                CK(launch_validate_queries<T>((const T*)h->x, h->n, nullptr, 0, (const T*)q0, nullptr, cnt,
+                                              extrapolate ? CHECK_NOT_NAN : CHECK_IN_RANGE, err, s));
+                return NDI_OK;
+            }, &word);
+    });
+    if (st != NDI_OK) return st;
+    if (word != NDI_ERR_WORD_NONE) {
+        if (first_bad) *first_bad = (int64_t)word;
+        return extrapolate ? fail(NDI_NAN_QUERY, "not implemented: failed to convert NaN to usize (query %lld)", (long long)word)
+                           : fail(NDI_OUT_OF_BOUNDS, "query %lld is not in range", (long long)word);
+    }
+    return NDI_OK;
+}
+
+// ---- cubic spline ---------------------------------------------------------------------------------------------
+ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int32_t* left_kind, const void* left_val,
+                                     const int32_t* right_kind, const void* right_val, int64_t* bad_column) {
+    if (bad_column) *bad_column = -1;
+    if (!h) return fail(NDI_INVALID_ARGUMENT, "null handle");
+    if (bc_kind < NDI_BC_NOT_A_KNOT || bc_kind > NDI_BC_INDIVIDUAL) return fail(NDI_INVALID_ARGUMENT, "bad boundary kind %d", bc_kind);
+    if (h->n < 3) return fail(NDI_INVALID_ARGUMENT, "The chosen Interpolation strategy needs at least 3 data points");
+    if (bc_kind == NDI_BC_INDIVIDUAL) {
+        if (!left_kind || !left_val || !right_kind || !right_val) return fail(NDI_INVALID_ARGUMENT, "Individual boundaries need all four arrays");
+        for (int64_t c = 0; c < h->w; ++c)
+            if (left_kind[c] < 0 || left_kind[c] > NDI_SB_SECOND_DERIV || right_kind[c] < 0 || right_kind[c] > NDI_SB_SECOND_DERIV)
+                return fail(NDI_INVALID_ARGUMENT, "bad single-boundary kind in column %lld", (long long)c);
+    }
+    DeviceGuard g(h->device);
+    ndi_status st; Workspace* ws = workspace(h->device, &st); if (!ws) return st;
+    return dispatch_float(h->dtype, [&](auto tag) -> ndi_status {
+        using T = decltype(tag);
+        const size_t coef_bytes = (size_t)(h->n - 1) * h->w * sizeof(T);
+        T *a = nullptr, *b = nullptr, *scratch = nullptr, *lv = nullptr, *rv = nullptr;
+        int32_t *lk = nullptr, *rk = nullptr;
+        auto cleanup = [&](bool keep) {
+            cudaFree(scratch); cudaFree(lv); cudaFree(rv); cudaFree(lk); cudaFree(rk);
+            if (!keep) { cudaFree(a); cudaFree(b); }
+        };
+        auto body = [&]() -> ndi_status {
+            CK(cudaMalloc(&a, coef_bytes));
+            CK(cudaMalloc(&b, coef_bytes));
+            CK(cudaMalloc(&scratch, spline_scratch_elems<T>(h->n, h->w, bc_kind) * sizeof(T)));
+            if (bc_kind == NDI_BC_INDIVIDUAL) {
+                CK(cudaMalloc(&lk, h->w * sizeof(int32_t))); CK(cudaMalloc(&rk, h->w * sizeof(int32_t)));
+                CK(cudaMalloc(&lv, h->w * sizeof(T))); CK(cudaMalloc(&rv, h->w * sizeof(T)));
+                CK(cudaMemcpyAsync(lk, left_kind, h->w * sizeof(int32_t), cudaMemcpyHostToDevice, ws->s[0]));
+                CK(cudaMemcpyAsync(rk, right_kind, h->w * sizeof(int32_t), cudaMemcpyHostToDevice, ws->s[0]));
+                CK(cudaMemcpyAsync(lv, left_val, h->w * sizeof(T), cudaMemcpyHostToDevice, ws->s[0]));
+                CK(cudaMemcpyAsync(rv, right_val, h->w * sizeof(T), cudaMemcpyHostToDevice, ws->s[0]));
+            }
+            CK(cudaMemsetAsync(ws->d_err, 0xff, sizeof(uint64_t), ws->s[0]));
+            CK(launch_spline_build<T>((const T*)h->x, h->n, (const T*)h->data, h->w, bc_kind, lk, lv, rk, rv, a, b, scratch, ws->d_err, ws->s[0]));
+            CK(cudaMemcpyAsync(ws->h_pin, ws->d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws->s[0]));
+            CK(cudaStreamSynchronize(ws->s[0]));
+            return NDI_OK;
+        };
+        ndi_status s2 = body();
+        if (s2 != NDI_OK) { cleanup(false); return s2; }
+        uint64_t word; memcpy(&word, ws->h_pin, sizeof(word));
+        if (word != NDI_ERR_WORD_NONE) {
+            cleanup(false);
+            if (bad_column) *bad_column = (int64_t)word;
+            return fail(NDI_PERIODIC_MISMATCH, "for periodic boundary condition the first and last value must be equal (column %lld)", (long long)word);
+        }
+        cleanup(true);
+        if (h->owns_coeffs) { cudaFree(h->a); cudaFree(h->b); }
+        h->a = a; h->b = b; h->owns_coeffs = true;
+        return NDI_OK;
+    });
+}
+
+ndi_status ndi_interp1d_spline_coeffs(const ndi_interp1d* h, void* a, void* b) {
+    if (!h || !a || !b) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    if (!h->a) return fail(NDI_NO_SPLINE, "no spline coefficients: call ndi_interp1d_spline_build first");
+    DeviceGuard g(h->device);
+    const size_t bytes = (size_t)(h->n - 1) * h->w * elem_size(h->dtype);
+    CK(cudaMemcpy(a, h->a, bytes, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b, h->b, bytes, cudaMemcpyDeviceToHost));
+    return NDI_OK;
+}
+
+ndi_status ndi_interp1d_spline_set_coeffs(ndi_interp1d* h, const void* a, const void* b, uint32_t flags) {
+    if (!h || !a || !b) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    if (h->dtype == NDI_I32) return fail(NDI_UNSUPPORTED_DTYPE, "cubic splines need a float dtype");
+    DeviceGuard g(h->device);
+    const size_t bytes = (size_t)(h->n - 1) * h->w * elem_size(h->dtype);
+    void *na = nullptr, *nb = nullptr; bool oa = false, ob = false;
+    ndi_status st = take_table(a, bytes, flags, nullptr, &na, &oa);
+    if (st == NDI_OK) st = take_table(b, bytes, flags, nullptr, &nb, &ob);
+    if (st == NDI_OK) { cudaError_t e = cudaStreamSynchronize(nullptr); if (e != cudaSuccess) st = cuda_fail(e, "sync"); }
+    if (st != NDI_OK) { if (oa) cudaFree(na); if (ob) cudaFree(nb); return st; }
+    if (h->owns_coeffs) { cudaFree(h->a); cudaFree(h->b); }
+    h->a = na; h->b = nb; h->owns_coeffs = oa;
+    return NDI_OK;
+}
+
+ndi_status ndi_interp1d_cubic_dev(const ndi_interp1d* h, const void* q_dev, int64_t nq, int32_t extrap_mode,
+                                  void* out_dev, uint64_t* err_word_dev, void* stream) {
+    ndi_status st = check_eval_args(h, q_dev, nq, out_dev); if (st != NDI_OK) return st;
+    if (!h->a) return fail(NDI_NO_SPLINE, "no spline coefficients: call ndi_interp1d_spline_build first");
+    if (extrap_mode < 0 || extrap_mode > 2) return fail(NDI_INVALID_ARGUMENT, "bad extrapolation mode %d", extrap_mode);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (err_word_dev) CK(cudaMemsetAsync(err_word_dev, 0xff, sizeof(uint64_t), s));
+    return dispatch_float(h->dtype, [&](auto tag) -> ndi_status {
+        using T = decltype(tag);
+        SearchCfg sc = make_search(h->n, sizeof(T), h->uniform_hint, h->search_mode, nq, 0);
+        CK(launch_interp1d_cubic<T>((const T*)h->x, h->n, sc, (const T*)h->data, (const T*)h->a, (const T*)h->b, h->w,
+                                    (const T*)q_dev, nq, extrap_mode, (T*)out_dev, (unsigned long long*)err_word_dev, s));
+        return NDI_OK;
+    });
+}
+
+ndi_status ndi_interp1d_cubic(const ndi_interp1d* h, const void* q, int64_t nq, int32_t extrap_mode, void* out,
+                              int64_t* first_bad) {
+    if (first_bad) *first_bad = -1;
+    ndi_status st = check_eval_args(h, q, nq, out); if (st != NDI_OK) return st;
+    if (!h->a) return fail(NDI_NO_SPLINE, "no spline coefficients: call ndi_interp1d_spline_build first");
+    if (extrap_mode < 0 || extrap_mode > 2) return fail(NDI_INVALID_ARGUMENT, "bad extrapolation mode %d", extrap_mode);
+    HostEval he{h->device, elem_size(h->dtype), 1, h->w, {q, nullptr}, nq, out};
+    uint64_t word;
+    st = dispatch_float(h->dtype, [&](auto tag) -> ndi_status {
+        using T = decltype(tag);
+        SearchCfg sc = make_search(h->n, sizeof(T), h->uniform_hint, h->search_mode, nq, 0);
+        const int check = extrap_mode == NDI_EXTRAP_NO ? CHECK_IN_RANGE : (extrap_mode == NDI_EXTRAP_YES ? CHECK_NOT_NAN : CHECK_FINITE_IF_OUTSIDE);
+        return run_host_eval(he,
+            [&](const void* q0, const void*, int64_t cnt, void* o, unsigned long long* err, cudaStream_t s) -> ndi_status {
+                CK(launch_interp1d_cubic<T>((const T*)h->x, h->n, sc, (const T*)h->data, (const T*)h->a, (const T*)h->b, h->w,
+                                            (const T*)q0, cnt, extrap_mode, (T*)o, err, s));
+                return NDI_OK;
+            },
+            [&](const void* q0, const void*, int64_t cnt, unsigned long long* err, cudaStream_t s) -> ndi_status {
+                CK(launch_validate_queries<T>((const T*)h->x, h->n, nullptr, 0, (const T*)q0, nullptr, cnt, check, err, s));
+                return NDI_OK;
+            }, &word);
+    });
+    if (st != NDI_OK) return st;
+    if (word != NDI_ERR_WORD_NONE) {
+        if (first_bad) *first_bad = (int64_t)word;
+        return extrap_mode ? fail(NDI_NAN_QUERY, "not implemented: failed to convert NaN to usize (query %lld)", (long long)word)
+                           : fail(NDI_OUT_OF_BOUNDS, "query %lld is not in range", (long long)word);
+    }
+    return NDI_OK;
+}
+
+// ---- Interp2D ---------------------------------------------------------------------------------------------------
+ndi_status ndi_interp2d_create(ndi_dtype dtype, const void* x, int64_t n, const void* y, int64_t m, const void* data,
+                               int64_t w, uint32_t flags, ndi_interp2d** out) {
+    if (!out) return fail(NDI_INVALID_ARGUMENT, "null handle pointer");
+    *out = nullptr;
+    if (!dtype_ok(dtype)) return fail(NDI_UNSUPPORTED_DTYPE, "unsupported dtype %d", (int)dtype);
+    if (!x || !y || !data) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    if (n < 2 || m < 2 || w < 1) return fail(NDI_INVALID_ARGUMENT, "need n, m >= 2 and w >= 1");
+    if (n > 0x7fffffffll || m > 0x7fffffffll) return fail(NDI_INVALID_ARGUMENT, "grid longer than 2^31-1");
+    int dev = 0; CK(cudaGetDevice(&dev));
+    ndi_status st; Workspace* ws = workspace(dev, &st); if (!ws) return st;
+    const size_t es = elem_size(dtype);
+    ndi_interp2d* h = new ndi_interp2d{dtype, dev, n, m, w, nullptr, nullptr, nullptr, false, 0, 0, NDI_SEARCH_AUTO};
+    bool o1 = false, o2 = false, o3 = false;
+    st = take_table(x, (size_t)n * es, flags, ws->s[0], &h->x, &o1);
+    if (st == NDI_OK) st = take_table(y, (size_t)m * es, flags, ws->s[0], &h->y, &o2);
+    if (st == NDI_OK) st = take_table(data, (size_t)n * (size_t)m * (size_t)w * es, flags, ws->s[0], &h->data, &o3);
+    if (st != NDI_OK) { if (o1) cudaFree(h->x); if (o2) cudaFree(h->y); if (o3) cudaFree(h->data); delete h; return st; }
+    h->owns_tables = o1;
+    int32_t rx[2] = {0, 0}, ry[2] = {0, 0};
+    st = classify_grid(dtype, h->x, n, ws, rx);
+    if (st == NDI_OK) st = classify_grid(dtype, h->y, m, ws, ry);
+    if (st == NDI_OK && !(flags & NDI_ASSUME_VALID)) {          // x before y: interp2d/mod.rs:500-509
+        if (rx[0] != NDI_MONO_RISING_STRICT) st = fail(NDI_NOT_MONOTONIC, "The x-axis needs to be strictly monotonic rising");
+        else if (ry[0] != NDI_MONO_RISING_STRICT) st = fail(NDI_NOT_MONOTONIC, "The y-axis needs to be strictly monotonic rising");
+    }
+    if (st != NDI_OK) { ndi_interp2d_destroy(h); return st; }
+    h->hint_x = rx[0] == NDI_MONO_RISING_STRICT ? rx[1] : 0;
+    h->hint_y = ry[0] == NDI_MONO_RISING_STRICT ? ry[1] : 0;
+    *out = h;
+    return NDI_OK;
+}
+
+ndi_status ndi_interp2d_destroy(ndi_interp2d* h) {
+    if (!h) return NDI_OK;
+    DeviceGuard g(h->device);
+    if (h->owns_tables) { cudaFree(h->x); cudaFree(h->y); cudaFree(h->data); }
+    delete h;
+    return NDI_OK;
+}
+ndi_status ndi_interp2d_info(const ndi_interp2d* h, ndi_dtype* dtype, int64_t* n, int64_t* m, int64_t* w, int32_t* device) {
+    if (!h) return fail(NDI_INVALID_ARGUMENT, "null handle");
+    if (dtype) *dtype = h->dtype;
+    if (n) *n = h->n;
+    if (m) *m = h->m;
+    if (w) *w = h->w;
+    if (device) *device = h->device;
+    return NDI_OK;
+}
+ndi_status ndi_interp2d_set_search_mode(ndi_interp2d* h, int32_t mode) {
+    if (!h || mode < 0 || mode > 3) return fail(NDI_INVALID_ARGUMENT, "bad search mode");
+    h->search_mode = mode;
+    return NDI_OK;
+}
+ndi_status ndi_interp2d_device_ptrs(const ndi_interp2d* h, const void** x, const void** y, const void** data) {
+    if (!h) return fail(NDI_INVALID_ARGUMENT, "null handle");
+    if (x) *x = h->x;
+    if (y) *y = h->y;
+    if (data) *data = h->data;
+    return NDI_OK;
+}
+ndi_status ndi_interp2d_clone_to_device(const ndi_interp2d* h, int32_t device, ndi_interp2d** out) {
+    if (!h || !out) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    *out = nullptr;
+    DeviceGuard g(device);
+    const size_t es = elem_size(h->dtype);
+    ndi_interp2d* c = new ndi_interp2d(*h);
+    c->device = device; c->owns_tables = true;
+    c->x = c->y = c->data = nullptr;
+    auto copy = [&](void** dst, const void* src, size_t bytes) -> ndi_status {
+        CK(cudaMalloc(dst, bytes));
+        CK(cudaMemcpyPeer(*dst, device, src, h->device, bytes));
+        return NDI_OK;
+    };
+    ndi_status st = copy(&c->x, h->x, (size_t)h->n * es);
+    if (st == NDI_OK) st = copy(&c->y, h->y, (size_t)h->m * es);
+    if (st == NDI_OK) st = copy(&c->data, h->data, (size_t)h->n * h->m * h->w * es);
+    if (st != NDI_OK) { cudaFree(c->x); cudaFree(c->y); cudaFree(c->data); delete c; return st; }
+    *out = c;
+    return NDI_OK;
+}
+
+static void search2(const ndi_interp2d* h, size_t es, int64_t nq, SearchCfg* sx, SearchCfg* sy) {
+    *sx = make_search(h->n, es, h->hint_x, h->search_mode, nq, 0);
+    *sy = make_search(h->m, es, h->hint_y, h->search_mode, nq, sx->smem ? (size_t)h->n * es + 16 : 0);
+}
+
+ndi_status ndi_interp2d_bilinear_dev(const ndi_interp2d* h, const void* qx_dev, const void* qy_dev, int64_t nq,
+                                     int32_t extrapolate, void* out_dev, uint64_t* err_word_dev, void* stream) {
+    ndi_status st = check_eval_args(h, qx_dev, nq, out_dev); if (st != NDI_OK) return st;
+    if (nq > 0 && !qy_dev) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (err_word_dev) CK(cudaMemsetAsync(err_word_dev, 0xff, sizeof(uint64_t), s));
+    return dispatch(h->dtype, [&](auto tag) -> ndi_status {
+        using T = decltype(tag);
+        SearchCfg sx, sy; search2(h, sizeof(T), nq, &sx, &sy);
+        CK(launch_interp2d_bilinear<T>((const T*)h->x, h->n, sx, (const T*)h->y, h->m, sy, (const T*)h->data, h->w,
+                                       (const T*)qx_dev, (const T*)qy_dev, nq, extrapolate != 0, (T*)out_dev,
+                                       (unsigned long long*)err_word_dev, s));
+        return NDI_OK;
+    });
+}
+
+ndi_status ndi_interp2d_bilinear(const ndi_interp2d* h, const void* qx, const void* qy, int64_t nq, int32_t extrapolate,
+                                 void* out, int64_t* first_bad, int32_t* bad_axis) {
+    if (first_bad) *first_bad = -1;
+    if (bad_axis) *bad_axis = -1;
+    ndi_status st = check_eval_args(h, qx, nq, out); if (st != NDI_OK) return st;
+    if (nq > 0 && !qy) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    HostEval he{h->device, elem_size(h->dtype), 2, h->w, {qx, qy}, nq, out};
+    uint64_t word;
+    st = dispatch(h->dtype, [&](auto tag) -> ndi_status {
+        using T = decltype(tag);
+        SearchCfg sx, sy; search2(h, sizeof(T), nq, &sx, &sy);
+        return run_host_eval(he,
+            [&](const void* q0, const void* q1, int64_t cnt, void* o, unsigned long long* err, cudaStream_t s) -> ndi_status {
+                CK(launch_interp2d_bilinear<T>((const T*)h->x, h->n, sx, (const T*)h->y, h->m, sy, (const T*)h->data, h->w,
+                                               (const T*)q0, (const T*)q1, cnt, extrapolate != 0, (T*)o, err, s));
+                return NDI_OK;
+            },
+            [&](const void* q0, const void* q1, int64_t cnt, unsigned long long* err, cudaStream_t s) -> ndi_status {
+                CK(launch_validate_queries<T>((const T*)h->x, h->n, (const T*)h->y, h->m, (const T*)q0, (const T*)q1, cnt,
+                                              extrapolate ? CHECK_NOT_NAN : CHECK_IN_RANGE, err, s));
+                return NDI_OK;
+            }, &word);
+    });
+    if (st != NDI_OK) return st;
+    if (word != NDI_ERR_WORD_NONE) {
+        const int64_t idx = (int64_t)(word >> 1);
+        const int axis = (int)(word & 1);
+        if (first_bad) *first_bad = idx;
+        if (bad_axis) *bad_axis = axis;
+        return extrapolate ? fail(NDI_NAN_QUERY, "not implemented: failed to convert NaN to usize (query %lld)", (long long)idx)
+                           : fail(NDI_OUT_OF_BOUNDS, "%s of query %lld is not in range", axis ? "y" : "x", (long long)idx);
+    }
+    return NDI_OK;
+}
+
+}  // extern "C"

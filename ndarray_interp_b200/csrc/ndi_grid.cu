@@ -1,0 +1,153 @@
+// ndi_grid.cu -- K1: VectorExtensions::monotonic_prop on the device
+// (src/vector_extensions.rs:40-53 and the MonotonicState machine at :115-198).
+//
+// The reference folds a state machine over windows(2) with an early exit.  The machine has
+// seven states and the input alphabet is the ordering of one adjacent pair {<, ==, >, unordered},
+// so the fold is a composition of maps {0..6} -> {0..6}.  Composition is associative, which makes
+// the classification an ordered parallel reduction that is EXACT for every input, including the
+// state-dependent NaN behaviour (an unordered pair means "Falling" from Init/NotStrict but
+// "NotMonotonic" from a Likely state, :136-170) that a flag-OR reduction would get wrong.
+// A map is packed 3 bits per state into one 32-bit word.
+//
+// The same launch also answers whether the even-spacing guess of get_lower_index
+// (:68-90) hits on every cell, which the evaluation kernels use to pick the O(1) search path.
+#include <type_traits>
+
+#include "ndi_device.cuh"
+#include "ndi_internal.h"
+
+namespace ndi {
+
+enum : uint32_t { S_INIT = 0, S_NOT_STRICT = 1, S_R_STRICT = 2, S_R = 3, S_F_STRICT = 4, S_F = 5, S_NM = 6 };
+
+__host__ __device__ constexpr uint32_t pack7(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g) {
+    return a | (b << 3) | (c << 6) | (d << 9) | (e << 12) | (f << 15) | (g << 18);
+}
+//                                        Init        NotStrict  R_strict   R        F_strict   F     NM
+constexpr uint32_t MAP_ID = pack7(S_INIT,     S_NOT_STRICT, S_R_STRICT, S_R,  S_F_STRICT, S_F,  S_NM);
+constexpr uint32_t MAP_LT = pack7(S_R_STRICT, S_R,          S_R_STRICT, S_R,  S_NM,       S_NM, S_NM);   // a <  b
+constexpr uint32_t MAP_EQ = pack7(S_NOT_STRICT, S_NOT_STRICT, S_R,      S_R,  S_F,        S_F,  S_NM);   // a == b
+constexpr uint32_t MAP_GT = pack7(S_F_STRICT, S_F,          S_NM,       S_NM, S_F_STRICT, S_F,  S_NM);   // a >  b
+constexpr uint32_t MAP_UN = pack7(S_F_STRICT, S_F,          S_NM,       S_NM, S_NM,       S_NM, S_NM);   // unordered
+
+__device__ __forceinline__ uint32_t map_apply(uint32_t f, uint32_t s) { return (f >> (3 * s)) & 7u; }
+// (f then g)
+__device__ __forceinline__ uint32_t map_compose(uint32_t f, uint32_t g) {
+    uint32_t r = 0;
+#pragma unroll
+    for (uint32_t s = 0; s < 7; ++s) r |= map_apply(g, map_apply(f, s)) << (3 * s);
+    return r;
+}
+template <class T>
+__device__ __forceinline__ uint32_t pair_map(T a, T b) {
+    if (a < b) return MAP_LT;
+    if (a == b) return MAP_EQ;
+    if (a > b) return MAP_GT;
+    return MAP_UN;
+}
+
+constexpr int kGridBlock = 256;
+constexpr int kGridMaxBlocks = 256;     // partial maps + 2 control words fit the scratch
+
+size_t grid_classify_scratch_words() { return kGridMaxBlocks + 4; }
+
+// ordered block reduction of maps and AND-reduction of the guess flag
+__device__ __forceinline__ void block_reduce(uint32_t& f, uint32_t& ok, uint32_t* sh_f, uint32_t* sh_ok) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ordered warp reduction: after step o, lane l holds the composition of lanes [l, l+2o)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t g = __shfl_down_sync(0xffffffffu, f, o);
+        if (lane + o < 32) f = map_compose(f, g);
+        ok &= __shfl_down_sync(0xffffffffu, ok, o) | (lane + o < 32 ? 0u : 1u);
+    }
+    if (lane == 0) { sh_f[warp] = f; sh_ok[warp] = ok; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = MAP_ID, a_ok = 1;
+        for (int w = 0; w < kGridBlock / 32; ++w) { acc = map_compose(acc, sh_f[w]); a_ok &= sh_ok[w]; }
+        f = acc; ok = a_ok;
+    }
+}
+
+// scratch: [0..kGridMaxBlocks) partial maps, [kGridMaxBlocks] ticket, [kGridMaxBlocks+1] guess AND
+template <class T>
+__global__ void __launch_bounds__(kGridBlock) grid_classify_kernel(const T* __restrict__ x, long long n,
+                                                                  int32_t* __restrict__ result, uint32_t* scratch) {
+    __shared__ uint32_t sh_f[kGridBlock / 32], sh_ok[kGridBlock / 32];
+    __shared__ bool last;
+    const long long npairs = n - 1;
+    // contiguous chunk of pairs per block, contiguous sub-chunk per thread (order matters)
+    const long long per_block = (npairs + gridDim.x - 1) / gridDim.x;
+    const long long b_lo = per_block * blockIdx.x, b_hi = min(npairs, b_lo + per_block);
+    const long long per_thread = (per_block + kGridBlock - 1) / kGridBlock;
+    const long long t_lo = min(b_hi, b_lo + per_thread * threadIdx.x), t_hi = min(b_hi, t_lo + per_thread);
+    uint32_t f = MAP_ID, ok = 1;
+    if (t_lo < t_hi) {
+        T a = x[t_lo];
+        for (long long i = t_lo; i < t_hi; ++i) {
+            const T b = x[i + 1];
+            f = map_compose(f, pair_map<T>(a, b));
+            // does the O(1) guess of get_lower_index land in cell i for a point inside it?
+            if (n <= 0x7fffffff) {
+                T mid;
+                if constexpr (std::is_same_v<T, double>) mid = 0.5 * (a + b);
+                else if constexpr (std::is_same_v<T, float>) mid = 0.5f * (a + b);
+                else mid = (T)(((long long)a + (long long)b) / 2);
+                if (a <= mid && mid < b) {
+                    T g0 = x[0], gl = x[n - 1];
+                    T est = calc_frac<T>(g0, (T)0, gl, (T)(n - 1), mid);
+                    if (!(est >= (T)0 && est < (T)(n - 1) && (long long)est == i)) ok = 0;
+                } else if (!(a < b)) ok = 0;
+            } else ok = 0;
+            a = b;
+        }
+    }
+    block_reduce(f, ok, sh_f, sh_ok);
+    if (threadIdx.x == 0) {
+        scratch[blockIdx.x] = f;
+        if (!ok) atomicAnd(&scratch[kGridMaxBlocks + 1], 0u);
+        __threadfence();
+        uint32_t ticket = atomicAdd(&scratch[kGridMaxBlocks], 1u);
+        last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        uint32_t acc = MAP_ID;
+        for (unsigned b = 0; b < gridDim.x; ++b) acc = map_compose(acc, ((volatile uint32_t*)scratch)[b]);
+        const uint32_t s = map_apply(acc, S_INIT);
+        int32_t mono;                                   // MonotonicState::finish (:191-197)
+        switch (s) {
+        case S_R_STRICT: mono = 1; break;
+        case S_R:        mono = 2; break;
+        case S_F_STRICT: mono = 3; break;
+        case S_F:        mono = 4; break;
+        default:         mono = 0; break;               // NotStrict (all equal) and NM -> NotMonotonic
+        }
+        result[0] = mono;
+        result[1] = (mono == 1 && ((volatile uint32_t*)scratch)[kGridMaxBlocks + 1] != 0) ? 1 : 0;
+    }
+}
+
+template <class T>
+cudaError_t launch_grid_classify(const T* x, int64_t n, int32_t* result_dev, uint32_t* scratch_dev, cudaStream_t st) {
+    // ticket = 0, guess flag = all ones; partial maps are fully overwritten
+    cudaError_t e = cudaMemsetAsync(scratch_dev + kGridMaxBlocks, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(scratch_dev + kGridMaxBlocks + 1, 0xff, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    if (n <= 1) return cudaMemsetAsync(result_dev, 0, 2 * sizeof(int32_t), st);   // :41-43
+    long long npairs = n - 1;
+    long long want = (npairs + (long long)kGridBlock * 8 - 1) / ((long long)kGridBlock * 8);   // >= 8 pairs per thread
+    int blocks = (int)(want < 1 ? 1 : (want > kGridMaxBlocks ? kGridMaxBlocks : want));
+    grid_classify_kernel<T><<<blocks, kGridBlock, 0, st>>>(x, (long long)n, result_dev, scratch_dev);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template cudaError_t launch_grid_classify<float>(const float*, int64_t, int32_t*, uint32_t*, cudaStream_t);
+template cudaError_t launch_grid_classify<double>(const double*, int64_t, int32_t*, uint32_t*, cudaStream_t);
+template cudaError_t launch_grid_classify<int32_t>(const int32_t*, int64_t, int32_t*, uint32_t*, cudaStream_t);
+
+}  // namespace ndi

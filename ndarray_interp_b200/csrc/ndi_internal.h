@@ -1,0 +1,75 @@
+// ndi_internal.h -- launcher prototypes shared between the kernel translation units and the
+// C ABI (ndi_api.cu).  Nothing here is exported.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ndi {
+
+// how the lower-index search reads one grid
+struct SearchCfg {
+    int top_step;   // largest power of two <= n-2 (bisect_top_step)
+    int guess;      // 1: try the O(1) even-spacing guess first (uniform grids)
+    int smem;       // 1: stage the grid into shared memory with a bulk copy
+};
+
+// largest power of two <= n-2 (0 when n == 2): the first probe distance of the bisection
+inline int bisect_top_step(int64_t n) {
+    int s = 0;
+    if (n - 2 >= 1) { s = 1; while ((int64_t)s * 2 <= n - 2) s *= 2; }
+    return s;
+}
+
+struct DeviceInfo {
+    int device;
+    int sm_count;
+    size_t smem_optin;   // max dynamic shared memory per block
+};
+const DeviceInfo& device_info();          // of the current device
+void count_launch();                      // bumps ndi_kernel_launch_count()
+
+// ---- evaluation (ndi_eval.cu) -----------------------------------------------------------
+template <class T>
+cudaError_t launch_lower_index(const T* grid, int64_t n, SearchCfg sc, const T* q, int64_t nq, int64_t* idx,
+                               unsigned long long* err, cudaStream_t st);
+
+// mode for validate_queries / the fused checks: which queries make the reference fail
+enum QueryCheck { CHECK_IN_RANGE = 0, CHECK_NOT_NAN = 1, CHECK_FINITE_IF_OUTSIDE = 2 };
+// K7 pre-pass used by the host entry points: first query (row-major) the reference would fail on
+template <class T>
+cudaError_t launch_validate_queries(const T* g0_gl_x /* grid x */, int64_t n, const T* gy, int64_t m,
+                                    const T* qx, const T* qy, int64_t nq, int check, unsigned long long* err,
+                                    cudaStream_t st);
+
+template <class T>
+cudaError_t launch_interp1d_linear(const T* grid, int64_t n, SearchCfg sc, const T* data, int64_t w, const T* q,
+                                   int64_t nq, int extrapolate, T* out, unsigned long long* err, cudaStream_t st);
+template <class T>
+cudaError_t launch_interp1d_cubic(const T* grid, int64_t n, SearchCfg sc, const T* data, const T* a, const T* b,
+                                  int64_t w, const T* q, int64_t nq, int extrap_mode, T* out,
+                                  unsigned long long* err, cudaStream_t st);
+template <class T>
+cudaError_t launch_interp2d_bilinear(const T* gx, int64_t n, SearchCfg scx, const T* gy, int64_t m, SearchCfg scy,
+                                     const T* data, int64_t w, const T* qx, const T* qy, int64_t nq, int extrapolate,
+                                     T* out, unsigned long long* err, cudaStream_t st);
+
+// ---- grid checks (ndi_grid.cu) -----------------------------------------------------------
+// result[0] = Monotonic enum, result[1] = 1 when the even-spacing guess hits on every cell
+template <class T>
+cudaError_t launch_grid_classify(const T* x, int64_t n, int32_t* result_dev, uint32_t* scratch_dev,
+                                 cudaStream_t st);
+size_t grid_classify_scratch_words();
+
+// ---- spline construction (ndi_spline.cu) -----------------------------------------------------
+// Builds a, b ((n-1) x w each) on the device.  For bc_kind == INDIVIDUAL the four arrays are
+// device arrays of w entries.  scratch: n*w elements for INDIVIDUAL, else 4*n elements.
+// err: device word, set to the first column with a periodic mismatch.
+template <class T>
+cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w, int bc_kind, const int32_t* lk,
+                                const T* lv, const int32_t* rk, const T* rv, T* a, T* b, T* scratch,
+                                unsigned long long* err, cudaStream_t st);
+template <class T>
+size_t spline_scratch_elems(int64_t n, int64_t w, int bc_kind);
+
+}  // namespace ndi

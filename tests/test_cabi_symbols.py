@@ -1,0 +1,62 @@
+"""CPU-side checks of the drop-in boundary: the library builds/loads and exports every symbol
+include/ndi_b200.h declares; the product path fails loudly without a GPU (no CPU fallback)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ndi_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ndi_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from ndarray_interp_b200 import build
+    so = build.build()
+    out = subprocess.check_output(["nm", "-D", "--defined-only", so], text=True)
+    exported = set(re.findall(r" T (ndi_[a-z0-9_]+)", out))
+    declared = _declared()
+    assert len(declared) >= 25
+    missing = [s for s in declared if s not in exported]
+    assert not missing, f"declared in ndi_b200.h but not exported: {missing}"
+
+
+def test_ctypes_signatures_cover_the_header():
+    from ndarray_interp_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+    lib = _lib.load()                      # types every entry point; AttributeError if one is missing
+    assert b"sm_100a" in lib.ndi_version_string()
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(HEADER).read()
+    assert "torch" not in src.lower().replace("no torch", "") and "at::" not in src and "Tensor" not in src
+
+
+def test_product_does_not_touch_the_oracle():
+    """the product package must never import / link / call anything under oracle/"""
+    pkg = os.path.join(ROOT, "ndarray_interp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                for pat in (r"libndi_oracle", r"oracle_py", r"\bora_[a-z]", r"from\s+oracle", r"import\s+oracle",
+                            r"#include[^\n]*oracle", r"oracle/"):
+                    assert not re.search(pat, text), f"{f} uses the oracle ({pat})"
+    out = subprocess.check_output(["ldd", os.path.join(pkg, "libndi_b200.so")], text=True)
+    assert "oracle" not in out
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="only meaningful on a box without a GPU")
+def test_fails_loudly_without_a_gpu():
+    from ndarray_interp_b200 import _lib
+    from ndarray_interp_b200.interp1d import Interp1D
+    with pytest.raises(_lib.NdiLibraryError, match="no CPU fallback"):
+        Interp1D.builder(np.array([1.0, 2.0, 3.0])).build()

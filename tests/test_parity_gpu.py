@@ -1,0 +1,298 @@
+"""Randomised differential parity: the CUDA path (through the C ABI) against the CPU oracle on the
+same seeded inputs.  Everything is compared BIT FOR BIT -- the kernels keep the reference's
+operation order (no FMA, IEEE division), so the 4-ulp (linear / bilinear) and 1e-12 / 1e-5
+relative (cubic, f64 / f32) bars of BASELINE.json are met with zero slack.  The tolerance the
+spec allows is asserted as well, so a future kernel that trades exactness for speed has a bar
+to be held to."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from ndarray_interp_b200 import InterpolateError, Panic, _lib as L
+from ndarray_interp_b200.interp1d import Interp1D, Linear
+from ndarray_interp_b200.interp2d import Bilinear, Interp2D
+from ndarray_interp_b200.vector_extensions import Monotonic, get_lower_index, monotonic_prop
+from oracle import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+DTS = [np.float32, np.float64, np.int32]
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    return bool(np.array_equal(a.view(np.uint8), b.view(np.uint8))) or bool(
+        np.array_equal(a, b, equal_nan=np.issubdtype(a.dtype, np.floating)))
+
+
+def ulp_diff(a, b):
+    """max distance in units of last place (floats)"""
+    it = {4: np.int32, 8: np.int64}[a.itemsize]
+    ai, bi = a.view(it).astype(np.int64), b.view(it).astype(np.int64)
+    ai = np.where(ai < 0, np.iinfo(it).min - ai, ai)
+    bi = np.where(bi < 0, np.iinfo(it).min - bi, bi)
+    return int(np.abs(ai - bi).max(initial=0))
+
+
+def make_grid(rng, n, dt, kind):
+    if np.issubdtype(dt, np.integer):
+        if kind == "uniform":
+            return (np.arange(n) + 5).astype(dt)
+        return np.cumsum(rng.integers(1, 9, n)).astype(dt)
+    if kind == "uniform":
+        return np.linspace(-3.0, 11.0, n).astype(dt)
+    if kind == "exp":
+        g = np.cumsum(np.exp(rng.uniform(-4, 2, n)))
+        return g.astype(dt)
+    g = np.cumsum(rng.uniform(0.5, 1.5, n))
+    return g.astype(dt)
+
+
+def make_queries(rng, g, nq, dt, outside):
+    lo, hi = float(g[0]), float(g[-1])
+    span = hi - lo
+    if outside:
+        q = rng.uniform(lo - 0.2 * span, hi + 0.2 * span, nq)
+    else:
+        q = rng.uniform(lo, hi, nq)
+    if np.issubdtype(dt, np.integer):
+        q = np.round(q)
+        if not outside:
+            q = np.clip(q, g[0], g[-1])
+        return q.astype(dt)
+    q = q.astype(dt)
+    if not outside:
+        q = np.clip(q, g[0], g[-1])
+    # sprinkle exact knots and the two ends
+    k = min(nq, 8)
+    q[:k] = g[rng.integers(0, len(g), k)]
+    if nq > 9:
+        q[8], q[9] = g[0], g[-1]
+    return q
+
+
+def make_data(rng, shape, dt):
+    if np.issubdtype(dt, np.integer):
+        return rng.integers(-1000, 1000, shape).astype(dt)
+    return rng.normal(size=shape).astype(dt)
+
+
+# ---- K2 ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", DTS, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("kind", ["uniform", "random", "exp"])
+@pytest.mark.parametrize("n", [2, 3, 10, 1000, 65536, 70001])
+def test_lower_index_matches_oracle(dt, kind, n):
+    if kind == "exp" and np.issubdtype(dt, np.integer):
+        pytest.skip("float only")
+    rng = np.random.default_rng(n * 7 + len(kind))
+    g = make_grid(rng, n, dt, kind)
+    if len(np.unique(g)) != n:
+        pytest.skip("grid collapsed in this dtype")
+    for nq in (1, 33, 40000):
+        q = make_queries(rng, g, nq, dt, outside=True)
+        if np.issubdtype(dt, np.floating) and nq > 20:
+            q[10], q[11] = np.inf, -np.inf
+        st, ref, _ = O.lower_index(g, q)
+        assert st == O.ST_OK
+        got = get_lower_index(g, q)
+        assert np.array_equal(got, ref)          # indices are bit-exact by contract
+
+
+def test_lower_index_nan_reports_first():
+    g = np.linspace(0, 1, 50)
+    q = np.random.default_rng(0).uniform(0, 1, 5000)
+    q[[4000, 1234, 4999]] = np.nan
+    lib = L.require_device()
+    idx = np.zeros(q.shape, np.int64)
+    bad = C.c_int64(-1)
+    st = lib.ndi_lower_index(L.F64, L.ptr(g), len(g), L.ptr(q), q.size, L.ptr(idx), C.byref(bad))
+    assert (st, bad.value) == (L.NAN_QUERY, 1234)
+    with pytest.raises(Panic):
+        get_lower_index(g, q)
+
+
+# ---- K1 ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [2, 3, 31, 257, 5000, 300001])
+def test_monotonic_matches_oracle(n):
+    rng = np.random.default_rng(n)
+    names = {"NotMonotonic": Monotonic.NotMonotonic, "RisingStrict": Monotonic.Rising(True),
+             "Rising": Monotonic.Rising(False), "FallingStrict": Monotonic.Falling(True),
+             "Falling": Monotonic.Falling(False)}
+    for dt in DTS:
+        base = np.sort(rng.integers(0, 10 * n, n)) if np.issubdtype(dt, np.integer) else np.sort(rng.uniform(0, 1, n))
+        variants = [base, base[::-1].copy(), np.unique(base) if len(np.unique(base)) > 1 else base]
+        strict = np.arange(n) * 3
+        variants += [strict, strict[::-1].copy(), np.zeros(n)]
+        for pos in {0, n // 2, n - 2}:
+            v = strict.copy()
+            if 0 <= pos < n - 1:
+                v[pos + 1] = v[pos]                   # one plateau
+                variants.append(v)
+                v2 = strict.copy(); v2[pos + 1] = v2[pos] - 1   # one dip
+                variants.append(v2)
+        if np.issubdtype(dt, np.floating):
+            for pos in {0, n // 2, n - 1}:
+                v = strict.astype(np.float64); v[pos] = np.nan
+                variants.append(v)
+        for v in variants:
+            v = np.ascontiguousarray(v).astype(dt)
+            assert monotonic_prop(v) == names[O.monotonic_prop(v)], (np.dtype(dt).name, n)
+            assert monotonic_prop(v[::-1]) == names[O.monotonic_prop(v, -1)]
+
+
+# ---- K3 ----------------------------------------------------------------------------------------------
+WIDTHS = [(), (1,), (2,), (3,), (4,), (5,), (7,), (8,), (12,), (16,), (31,), (32,), (33,), (64,), (100,), (128,),
+          (130,), (256,), (3, 5), (2, 2, 2), (1000,), (1024,)]
+
+
+@pytest.mark.parametrize("dt", DTS, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("trailing", WIDTHS, ids=lambda t: "w" + "x".join(map(str, t)))
+def test_linear_matches_oracle(dt, trailing):
+    rng = np.random.default_rng(len(trailing) * 1000 + int(np.prod(trailing, dtype=np.int64)))
+    n = 200
+    g = make_grid(rng, n, dt, "random")
+    data = make_data(rng, (n,) + trailing, dt)
+    interp = Interp1D.new_unchecked(g, data, Linear.new().extrapolate(True))
+    strict = Interp1D.new_unchecked(g, data, Linear.new())
+    for nq in (1, 31, 33, 3000):
+        q = make_queries(rng, g, nq, dt, outside=True)
+        st, ref, _ = O.interp1d_linear(g, data, q, True)
+        assert st == O.ST_OK
+        got = interp.interp_array(q)
+        assert same(got, ref)
+        if np.issubdtype(dt, np.floating):
+            assert ulp_diff(got, ref) <= 4           # the bar north_star states
+        qi = make_queries(rng, g, nq, dt, outside=False)
+        st, ref, _ = O.interp1d_linear(g, data, qi, False)
+        assert st == O.ST_OK
+        assert same(strict.interp_array(qi), ref)
+
+
+@pytest.mark.parametrize("mode", [L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS])
+@pytest.mark.parametrize("kind", ["uniform", "random", "exp"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_linear_every_search_mode_gives_the_same_bits(mode, kind, dt):
+    rng = np.random.default_rng(5)
+    for n in (2, 17, 4096, 13000, 65536):
+        g = make_grid(rng, n, dt, kind)
+        if len(np.unique(g)) != n:
+            continue
+        data = make_data(rng, (n, 4), dt)
+        interp = Interp1D.new_unchecked(g, data, Linear.new().extrapolate(True))
+        L.check(L.load().ndi_interp1d_set_search_mode(interp._handle(), mode))
+        q = make_queries(rng, g, 70000, dt, outside=True)
+        st, ref, _ = O.interp1d_linear(g, data, q, True)
+        assert same(interp.interp_array(q), ref)
+
+
+def test_linear_query_dim_path():
+    """BASELINE config 3 shape in miniature: 2-D query array, extrapolation, 5 % outside"""
+    rng = np.random.default_rng(3)
+    g = np.cumsum(np.exp(rng.uniform(-3, 1, 4096))).astype(np.float32)
+    data = rng.normal(size=(4096, 16)).astype(np.float32)
+    interp = Interp1D.new_unchecked(g, data, Linear.new().extrapolate(True))
+    q = make_queries(rng, g, 256 * 128, np.float32, outside=True).reshape(256, 128)
+    out = interp.interp_array(q)
+    assert out.shape == (256, 128, 16)
+    st, ref, _ = O.interp1d_linear(g, data, q, True)
+    assert same(out, ref)
+
+
+def test_linear_errors_first_bad_and_untouched_rows():
+    rng = np.random.default_rng(11)
+    g = np.cumsum(rng.uniform(0.5, 1.5, 300))
+    data = rng.normal(size=(300, 64))
+    interp = Interp1D.new_unchecked(g, data, Linear.new())
+    for nq, bad_at in [(100, [17, 60]), (40000, [39999]), (40000, [12345, 777, 30000]), (40000, [0])]:
+        q = rng.uniform(g[0], g[-1], nq)
+        q[bad_at] = g[-1] + 1.0
+        first = min(bad_at)
+        buf = np.full((nq, 64), -7.0)
+        with pytest.raises(InterpolateError.OutOfBounds):
+            interp.interp_array_into(q, buf)
+        st, ref, bad = O.interp1d_linear(g, data, q, False, out=np.full((nq, 64), -7.0))
+        assert (st, bad) == (O.ST_OUT_OF_BOUNDS, first)
+        assert same(buf, ref)                    # rows < first written, rows >= first untouched
+    # NaN: OutOfBounds without extrapolation, the NaN panic with it
+    q = rng.uniform(g[0], g[-1], 50); q[20] = np.nan
+    with pytest.raises(InterpolateError.OutOfBounds, match="x = NaN"):
+        interp.interp_array(q)
+    ex = Interp1D.new_unchecked(g, data, Linear.new().extrapolate(True))
+    with pytest.raises(Panic, match="failed to convert NaN to usize"):
+        ex.interp_array(q)
+    q = rng.uniform(g[0], g[-1], 40000); q[31000] = np.nan      # pre-pass path
+    with pytest.raises(Panic, match="failed to convert NaN to usize"):
+        ex.interp_array(q)
+
+
+def test_linear_multi_chunk_pipeline():
+    """> 64 MB of output: the two-stream chunked path"""
+    rng = np.random.default_rng(13)
+    g = np.cumsum(rng.uniform(0.5, 1.5, 512))
+    data = rng.normal(size=(512, 1024))
+    interp = Interp1D.new_unchecked(g, data, Linear.new())
+    q = np.sort(rng.uniform(g[0], g[-1], 20011))
+    st, ref, _ = O.interp1d_linear(g, data, q, False, nthreads=8)
+    assert st == O.ST_OK
+    assert same(interp.interp_array(q), ref)
+
+
+# ---- K4 ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", DTS, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("trailing", [(), (1,), (2,), (3,), (8,), (16,), (32,), (33,), (128,), (200,), (2, 3)],
+                         ids=lambda t: "w" + "x".join(map(str, t)))
+def test_bilinear_matches_oracle(dt, trailing):
+    rng = np.random.default_rng(77 + int(np.prod(trailing, dtype=np.int64)))
+    n, m = 40, 57
+    gx, gy = make_grid(rng, n, dt, "uniform"), make_grid(rng, m, dt, "random")
+    data = make_data(rng, (n, m) + trailing, dt)
+    ex = Interp2D.new_unchecked(gx, gy, data, Bilinear.new().extrapolate(True))
+    strict = Interp2D.new_unchecked(gx, gy, data, Bilinear.new())
+    for nq in (1, 33, 5000):
+        qx, qy = make_queries(rng, gx, nq, dt, True), make_queries(rng, gy, nq, dt, True)
+        st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, True)
+        assert st == O.ST_OK
+        got = ex.interp_array(qx, qy)
+        assert same(got, ref)
+        if np.issubdtype(dt, np.floating):
+            assert ulp_diff(got, ref) <= 4
+        qx, qy = make_queries(rng, gx, nq, dt, False), make_queries(rng, gy, nq, dt, False)
+        st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, False)
+        assert same(strict.interp_array(qx, qy), ref)
+
+
+def test_bilinear_error_axis_precedence():
+    rng = np.random.default_rng(2)
+    gx, gy = np.linspace(0, 1, 30), np.cumsum(rng.uniform(0.5, 1.5, 20))
+    data = rng.normal(size=(30, 20, 8))
+    interp = Interp2D.new_unchecked(gx, gy, data, Bilinear.new())
+    for nq in (200, 70000):
+        qx, qy = rng.uniform(0, 1, nq), rng.uniform(gy[0], gy[-1], nq)
+        qy[nq // 2] = gy[-1] + 1                  # y fails first ...
+        qx[nq // 2 + 5] = 2.0
+        with pytest.raises(InterpolateError.OutOfBounds, match="y = "):
+            interp.interp_array(qx, qy)
+        qx[nq // 2] = -1.0                        # ... unless x of the same query fails too
+        with pytest.raises(InterpolateError.OutOfBounds, match="x = -1.0"):
+            interp.interp_array(qx, qy)
+        buf = np.full((nq, 8), 3.0)
+        with pytest.raises(InterpolateError.OutOfBounds):
+            interp.interp_array_into(qx, qy, buf)
+        st, ref, bad, ax = O.interp2d_bilinear(gx, gy, data, qx, qy, False, out=np.full((nq, 8), 3.0))
+        assert (st, bad, ax) == (O.ST_OUT_OF_BOUNDS, nq // 2, 0)
+        assert same(buf, ref)
+
+
+@pytest.mark.parametrize("mode", [L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS])
+def test_bilinear_every_search_mode(mode):
+    rng = np.random.default_rng(9)
+    gx, gy = np.linspace(0, 1, 2048).astype(np.float32), np.cumsum(rng.uniform(0.5, 1.5, 777)).astype(np.float32)
+    data = rng.normal(size=(2048, 777, 8)).astype(np.float32)
+    interp = Interp2D.new_unchecked(gx, gy, data, Bilinear.new().extrapolate(True))
+    L.check(L.load().ndi_interp2d_set_search_mode(interp._handle(), mode))
+    qx, qy = make_queries(rng, gx, 50000, np.float32, True), make_queries(rng, gy, 50000, np.float32, True)
+    st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, True)
+    assert same(interp.interp_array(qx, qy), ref)
