@@ -41,7 +41,7 @@ class Interp1DStrategy:
         """the reference's batch loop (interp1d/mod.rs:334-342): stop at the first error.
         xs_flat: (Q,), out_rows: (Q, ...data.shape[1:]) C-contiguous."""
         for i in range(xs_flat.shape[0]):
-            self.interp_into(interpolator, out_rows[i], xs_flat[i])
+            self.interp_into(interpolator, out_rows[i, ...], xs_flat[i])      # [i, ...]: a view even when 0-d
 
     def _bind(self, interpolator):
         """called once by Interp1D; built-in strategies grab the device handle here"""

@@ -29,7 +29,7 @@ class Interp2DStrategy:
     def interp_batch_into(self, interpolator, xs_flat, ys_flat, out_rows):
         """the reference's batch loop (interp2d/mod.rs:297-306)"""
         for i in range(xs_flat.shape[0]):
-            self.interp_into(interpolator, out_rows[i], xs_flat[i], ys_flat[i])
+            self.interp_into(interpolator, out_rows[i, ...], xs_flat[i], ys_flat[i])
 
     def _bind(self, interpolator):
         pass
