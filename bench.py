@@ -273,6 +273,7 @@ def run_b200(args, wl, name):
     if wl["kind"] == "bilinear":
         gx, gy, data = replicated(host["x"]), replicated(host["y"]), replicated(host["data"])
         ip = D.DeviceInterp2D(gx, gy, data)
+        ip.set_search_mode(args.search_mode)
         qx, qy = torch.from_numpy(host["qx"]).to(dev), torch.from_numpy(host["qy"]).to(dev)
         out = torch.empty((wl["q"], wl["w"]), dtype=tdt, device=dev)
         err = D.new_err_word(dev)
@@ -282,6 +283,7 @@ def run_b200(args, wl, name):
     else:
         g, data = replicated(host["x"]), replicated(host["data"].reshape(wl["n"], wl["w"]))
         ip = D.DeviceInterp1D(g, data)
+        ip.set_search_mode(args.search_mode)
         if wl["kind"] == "cubic":
             # spline construction sharded over the trailing columns, coefficients all-gathered
             w = wl["w"]
@@ -417,7 +419,8 @@ def run_b200(args, wl, name):
             "config": {"workload": f"{name}: {wl['desc']}", "queries_per_gpu": wl["q"], "columns": wl["w"],
                        "l2": "working set per step (%.2f GB, output streamed once) exceeds the 126 MB L2; no explicit flush"
                              % (abytes / 1e9),
-                       "tables": "replicated per GPU by NCCL broadcast; queries sharded, no collective in the timed region"},
+                       "tables": "replicated per GPU by NCCL broadcast; queries sharded, no collective in the timed region",
+                       "search_mode": args.search_mode},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(name), "algorithmic_bytes": abytes, "peak_source": peak_src,
                          "frac_of_nominal_8000": achieved / 8000.0},
@@ -453,6 +456,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--search-mode", type=int, default=0,
+                    help="lower-index search strategy for measurement (0 auto, 1 global bisect, 2 smem bisect, 3 guess, 4 bucket table)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

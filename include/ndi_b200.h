@@ -102,6 +102,7 @@ typedef int32_t ndi_dtype;
 #define NDI_SEARCH_BINARY_GLOBAL 1 /* branch-free binary search, grid read through L1/L2 */
 #define NDI_SEARCH_BINARY_SMEM 2   /* grid staged into shared memory by a bulk (TMA) copy */
 #define NDI_SEARCH_UNIFORM_GUESS 3 /* O(1) even-spacing guess (vector_extensions.rs:68-90) + verify, binary fallback */
+#define NDI_SEARCH_BUCKET_LUT 4    /* O(1) expected on any grid: per-handle bucket table + exact finish on the grid */
 
 /* value of the device error word when no query failed */
 #define NDI_ERR_WORD_NONE UINT64_MAX

@@ -16,7 +16,7 @@ OK, OUT_OF_BOUNDS, NAN_QUERY, PERIODIC_MISMATCH, INVALID_ARGUMENT, NOT_MONOTONIC
 CUDA_ERROR = 100
 F32, F64, I32 = 0, 1, 2
 ASSUME_VALID, DEVICE_POINTERS, BORROW = 1, 2, 4
-SEARCH_AUTO, SEARCH_BINARY_GLOBAL, SEARCH_BINARY_SMEM, SEARCH_UNIFORM_GUESS = 0, 1, 2, 3
+SEARCH_AUTO, SEARCH_BINARY_GLOBAL, SEARCH_BINARY_SMEM, SEARCH_UNIFORM_GUESS, SEARCH_BUCKET_LUT = 0, 1, 2, 3, 4
 EXTRAP_NO, EXTRAP_YES, EXTRAP_PERIODIC = 0, 1, 2
 ERR_WORD_NONE = 2 ** 64 - 1
 

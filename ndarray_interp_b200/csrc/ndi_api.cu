@@ -137,20 +137,99 @@ static ndi_status grow(void** p, size_t* cap, size_t need) {
 }
 
 // ---- search configuration ----------------------------------------------------------------------------
-static SearchCfg make_search(int64_t n, size_t elem, int uniform_hint, int mode, int64_t nq, size_t other_smem) {
-    SearchCfg sc{bisect_top_step(n), 0, 0};
-    const size_t bytes = (size_t)n * elem;
+// A grid that does not fit the shared-memory budget gets a coarse table grid[0], grid[S], ... built
+// once per handle; the kernels bisect the coarse table in shared memory and finish in L1/L2.
+constexpr size_t kFullStageBytes = 48 * 1024;    // stage the whole grid up to this size
+constexpr size_t kCoarseBytes = 16 * 1024;       // target size of a coarse table
+
+struct GridMeta {
+    const void* grid; int64_t n; size_t elem; int uniform_hint;
+    const void* coarse; int coarse_n; int coarse_shift;
+    const void* lut; int lut_n; double g0d, scale;
+};
+
+// per-grid search aids owned by a handle: coarse table (two-level bisection) and bucket table
+struct GridAids {
+    void* coarse = nullptr; int coarse_n = 0, coarse_shift = 0;
+    void* lut = nullptr; int lut_n = 0; double g0d = 0, scale = 0;
+    void release() { cudaFree(coarse); cudaFree(lut); coarse = lut = nullptr; }
+    GridMeta meta(const void* grid, int64_t n, size_t elem, int hint) const {
+        return GridMeta{grid, n, elem, hint, coarse, coarse_n, coarse_shift, lut, lut_n, g0d, scale};
+    }
+};
+
+static SearchCfg make_search(const GridMeta& gm, int mode, int64_t nq, size_t other_smem) {
+    SearchCfg sc{bisect_top_step(gm.n), 0, 0, 0, 0, nullptr, nullptr, 0, 0.0, 0.0};
+    auto use_lut = [&]() { if (gm.lut) { sc.lut = gm.lut; sc.lut_n = gm.lut_n; sc.g0d = gm.g0d; sc.scale = gm.scale; } };
+    const size_t bytes = (size_t)gm.n * gm.elem;
     const size_t room = device_info().smem_optin > other_smem + 1024 ? device_info().smem_optin - other_smem - 1024 : 0;
+    auto stage = [&](size_t full_limit) {
+        if (bytes <= full_limit && bytes <= room) { sc.smem = 1; sc.stage_src = gm.grid; sc.stage_n = (int)gm.n; sc.coarse_shift = 0; }
+        else if (gm.coarse && (size_t)gm.coarse_n * gm.elem <= room) {
+            sc.smem = 1; sc.stage_src = gm.coarse; sc.stage_n = gm.coarse_n; sc.coarse_shift = gm.coarse_shift;
+        }
+    };
     switch (mode) {
     case NDI_SEARCH_BINARY_GLOBAL: break;
-    case NDI_SEARCH_BINARY_SMEM: sc.smem = bytes <= room; break;
+    case NDI_SEARCH_BINARY_SMEM: stage(gm.coarse ? kFullStageBytes : room); break;
     case NDI_SEARCH_UNIFORM_GUESS: sc.guess = 1; break;
-    default:   // AUTO: O(1) guess on grids where it always hits; else stage small grids for big batches
-        if (uniform_hint) sc.guess = 1;
-        else if (bytes <= 48 * 1024 && bytes <= room && nq >= 32768) sc.smem = 1;
+    case NDI_SEARCH_BUCKET_LUT: use_lut(); break;
+    default:   // AUTO: O(1) guess on grids where it always hits, else the bucket table;
+               // without either (no handle), shared-memory bisection for big batches
+        if (gm.uniform_hint) sc.guess = 1;
+        else if (gm.lut) use_lut();
+        else if (nq >= 32768) stage(kFullStageBytes);
         break;
     }
     return sc;
+}
+
+// search aids of one (non-uniform) grid, built once per handle on stream st (synchronises):
+//  - coarse table for a grid too large to stage whole (strided device-to-device copy)
+//  - bucket table for the O(1) search
+static ndi_status build_aids(ndi_dtype dtype, const void* grid, int64_t n, cudaStream_t st, GridAids* aids) {
+    const size_t elem = dtype == NDI_F64 ? 8 : 4;
+    *aids = GridAids{};
+    if ((size_t)n * elem > kFullStageBytes) {
+        int sh = 1;
+        while ((((size_t)n + ((size_t)1 << sh) - 1) >> sh) * elem > kCoarseBytes) ++sh;
+        const size_t S = (size_t)1 << sh;
+        const int count = (int)(((size_t)n + S - 1) / S);
+        CK(cudaMalloc(&aids->coarse, (size_t)count * elem));
+        CK(cudaMemcpy2DAsync(aids->coarse, elem, grid, S * elem, elem, (size_t)count, cudaMemcpyDeviceToDevice, st));
+        aids->coarse_n = count; aids->coarse_shift = sh;
+    }
+    // bucket table: ~4 buckets per grid point
+    unsigned char ends[16];
+    CK(cudaMemcpyAsync(ends, grid, elem, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ends + 8, (const unsigned char*)grid + (size_t)(n - 1) * elem, elem, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int nb = 16;
+    while (nb < 4 * n && nb < (1 << 24)) nb <<= 1;
+    double g0d, scale;
+    if (dtype == NDI_F32) {
+        float a, b; memcpy(&a, ends, 4); memcpy(&b, ends + 8, 4);
+        const float sc = (float)nb / (b - a);            // same float arithmetic as bucket_of()
+        g0d = a; scale = sc;
+    } else if (dtype == NDI_F64) {
+        double a, b; memcpy(&a, ends, 8); memcpy(&b, ends + 8, 8);
+        g0d = a; scale = (double)nb / (b - a);
+    } else {
+        int32_t a, b; memcpy(&a, ends, 4); memcpy(&b, ends + 8, 4);
+        g0d = a; scale = (double)nb / ((double)b - (double)a);
+    }
+    if (scale > 0 && scale < 1e300 && scale == scale) {
+        CK(cudaMalloc(&aids->lut, (size_t)nb * sizeof(int) * 2));
+        ndi_status s2 = dispatch(dtype, [&](auto tag) -> ndi_status {
+            using T = decltype(tag);
+            CK(launch_build_lut<T>((const T*)grid, n, g0d, scale, nb, aids->lut, st));
+            return NDI_OK;
+        });
+        if (s2 != NDI_OK) return s2;
+        aids->lut_n = nb; aids->g0d = g0d; aids->scale = scale;
+    }
+    CK(cudaStreamSynchronize(st));
+    return NDI_OK;
 }
 
 }  // namespace ndi
@@ -163,12 +242,17 @@ struct ndi_interp1d {
     void* x; void* data; void* a; void* b;
     bool owns_tables, owns_coeffs;
     int uniform_hint; int search_mode;
+    GridAids aids;
+    GridMeta meta() const { return aids.meta(x, n, dtype == NDI_F64 ? (size_t)8 : (size_t)4, uniform_hint); }
 };
 struct ndi_interp2d {
     ndi_dtype dtype; int device; int64_t n, m, w;
     void* x; void* y; void* data;
     bool owns_tables;
     int hint_x, hint_y; int search_mode;
+    GridAids aids_x, aids_y;
+    GridMeta meta_x() const { return aids_x.meta(x, n, dtype == NDI_F64 ? (size_t)8 : (size_t)4, hint_x); }
+    GridMeta meta_y() const { return aids_y.meta(y, m, dtype == NDI_F64 ? (size_t)8 : (size_t)4, hint_y); }
 };
 
 // upload or adopt one table
@@ -243,7 +327,7 @@ ndi_status ndi_lower_index_dev(ndi_dtype dtype, const void* grid_dev, int64_t n,
     if (err_word_dev) CK(cudaMemsetAsync(err_word_dev, 0xff, sizeof(uint64_t), st));
     return dispatch(dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
-        SearchCfg sc = make_search(n, sizeof(T), 0, search_mode, nq, 0);
+        SearchCfg sc = make_search(GridMeta{grid_dev, n, sizeof(T), 0, nullptr, 0, 0, nullptr, 0, 0.0, 0.0}, search_mode, nq, 0);
         CK(launch_lower_index<T>((const T*)grid_dev, n, sc, (const T*)q_dev, nq, idx_dev, (unsigned long long*)err_word_dev, st));
         return NDI_OK;
     });
@@ -292,7 +376,10 @@ ndi_status ndi_interp1d_create(ndi_dtype dtype, const void* x, int64_t n, const 
     int dev = 0; CK(cudaGetDevice(&dev));
     ndi_status st; Workspace* ws = workspace(dev, &st); if (!ws) return st;
     const size_t es = elem_size(dtype);
-    ndi_interp1d* h = new ndi_interp1d{dtype, dev, n, w, nullptr, nullptr, nullptr, nullptr, false, false, 0, NDI_SEARCH_AUTO};
+    ndi_interp1d* h = new ndi_interp1d();
+    h->dtype = dtype; h->device = dev; h->n = n; h->w = w;
+    h->x = h->data = h->a = h->b = nullptr; h->owns_tables = h->owns_coeffs = false;
+    h->uniform_hint = 0; h->search_mode = NDI_SEARCH_AUTO;
     bool ox = false, od = false;
     if ((st = take_table(x, (size_t)n * es, flags, ws->s[0], &h->x, &ox)) != NDI_OK) { delete h; return st; }
     if ((st = take_table(data, (size_t)n * (size_t)w * es, flags, ws->s[0], &h->data, &od)) != NDI_OK) {
@@ -306,6 +393,10 @@ ndi_status ndi_interp1d_create(ndi_dtype dtype, const void* x, int64_t n, const 
         st = fail(NDI_NOT_MONOTONIC, "Values in the x axis need to be strictly monotonic rising");
     if (st != NDI_OK) { ndi_interp1d_destroy(h); return st; }
     h->uniform_hint = res[0] == NDI_MONO_RISING_STRICT ? res[1] : 0;
+    if (!h->uniform_hint) {
+        st = build_aids(dtype, h->x, n, ws->s[0], &h->aids);
+        if (st != NDI_OK) { ndi_interp1d_destroy(h); return st; }
+    }
     *out = h;
     return NDI_OK;
 }
@@ -315,6 +406,7 @@ ndi_status ndi_interp1d_destroy(ndi_interp1d* h) {
     DeviceGuard g(h->device);
     if (h->owns_tables) { cudaFree(h->x); cudaFree(h->data); }
     if (h->owns_coeffs) { cudaFree(h->a); cudaFree(h->b); }
+    h->aids.release();
     delete h;
     return NDI_OK;
 }
@@ -329,7 +421,7 @@ ndi_status ndi_interp1d_info(const ndi_interp1d* h, ndi_dtype* dtype, int64_t* n
     return NDI_OK;
 }
 ndi_status ndi_interp1d_set_search_mode(ndi_interp1d* h, int32_t mode) {
-    if (!h || mode < 0 || mode > 3) return fail(NDI_INVALID_ARGUMENT, "bad search mode");
+    if (!h || mode < 0 || mode > NDI_SEARCH_BUCKET_LUT) return fail(NDI_INVALID_ARGUMENT, "bad search mode");
     h->search_mode = mode;
     return NDI_OK;
 }
@@ -359,7 +451,9 @@ ndi_status ndi_interp1d_clone_to_device(const ndi_interp1d* h, int32_t device, n
     if (st == NDI_OK) st = copy(&c->data, h->data, (size_t)h->n * h->w * es);
     if (st == NDI_OK && h->a) st = copy(&c->a, h->a, (size_t)(h->n - 1) * h->w * es);
     if (st == NDI_OK && h->b) st = copy(&c->b, h->b, (size_t)(h->n - 1) * h->w * es);
-    if (st != NDI_OK) { cudaFree(c->x); cudaFree(c->data); cudaFree(c->a); cudaFree(c->b); delete c; return st; }
+    c->aids = GridAids{};
+    if (st == NDI_OK && !h->uniform_hint) st = build_aids(c->dtype, c->x, c->n, nullptr, &c->aids);
+    if (st != NDI_OK) { cudaFree(c->x); cudaFree(c->data); cudaFree(c->a); cudaFree(c->b); c->aids.release(); delete c; return st; }
     *out = c;
     return NDI_OK;
 }
@@ -453,7 +547,7 @@ ndi_status ndi_interp1d_linear_dev(const ndi_interp1d* h, const void* q_dev, int
     if (err_word_dev) CK(cudaMemsetAsync(err_word_dev, 0xff, sizeof(uint64_t), s));
     return dispatch(h->dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
-        SearchCfg sc = make_search(h->n, sizeof(T), h->uniform_hint, h->search_mode, nq, 0);
+        SearchCfg sc = make_search(h->meta(), h->search_mode, nq, 0);
         CK(launch_interp1d_linear<T>((const T*)h->x, h->n, sc, (const T*)h->data, h->w, (const T*)q_dev, nq, extrapolate != 0,
                                      (T*)out_dev, (unsigned long long*)err_word_dev, s));
         return NDI_OK;
@@ -468,7 +562,7 @@ ndi_status ndi_interp1d_linear(const ndi_interp1d* h, const void* q, int64_t nq,
     uint64_t word;
     st = dispatch(h->dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
-        SearchCfg sc = make_search(h->n, sizeof(T), h->uniform_hint, h->search_mode, nq, 0);
+        SearchCfg sc = make_search(h->meta(), h->search_mode, nq, 0);
         return run_host_eval(he,
             [&](const void* q0, const void*, int64_t cnt, void* o, unsigned long long* err, cudaStream_t s) -> ndi_status {
                 CK(launch_interp1d_linear<T>((const T*)h->x, h->n, sc, (const T*)h->data, h->w, (const T*)q0, cnt, extrapolate != 0, (T*)o, err, s));
@@ -580,7 +674,7 @@ ndi_status ndi_interp1d_cubic_dev(const ndi_interp1d* h, const void* q_dev, int6
     if (err_word_dev) CK(cudaMemsetAsync(err_word_dev, 0xff, sizeof(uint64_t), s));
     return dispatch_float(h->dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
-        SearchCfg sc = make_search(h->n, sizeof(T), h->uniform_hint, h->search_mode, nq, 0);
+        SearchCfg sc = make_search(h->meta(), h->search_mode, nq, 0);
         CK(launch_interp1d_cubic<T>((const T*)h->x, h->n, sc, (const T*)h->data, (const T*)h->a, (const T*)h->b, h->w,
                                     (const T*)q_dev, nq, extrap_mode, (T*)out_dev, (unsigned long long*)err_word_dev, s));
         return NDI_OK;
@@ -597,7 +691,7 @@ ndi_status ndi_interp1d_cubic(const ndi_interp1d* h, const void* q, int64_t nq, 
     uint64_t word;
     st = dispatch_float(h->dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
-        SearchCfg sc = make_search(h->n, sizeof(T), h->uniform_hint, h->search_mode, nq, 0);
+        SearchCfg sc = make_search(h->meta(), h->search_mode, nq, 0);
         const int check = extrap_mode == NDI_EXTRAP_NO ? CHECK_IN_RANGE : (extrap_mode == NDI_EXTRAP_YES ? CHECK_NOT_NAN : CHECK_FINITE_IF_OUTSIDE);
         return run_host_eval(he,
             [&](const void* q0, const void*, int64_t cnt, void* o, unsigned long long* err, cudaStream_t s) -> ndi_status {
@@ -631,7 +725,10 @@ ndi_status ndi_interp2d_create(ndi_dtype dtype, const void* x, int64_t n, const 
     int dev = 0; CK(cudaGetDevice(&dev));
     ndi_status st; Workspace* ws = workspace(dev, &st); if (!ws) return st;
     const size_t es = elem_size(dtype);
-    ndi_interp2d* h = new ndi_interp2d{dtype, dev, n, m, w, nullptr, nullptr, nullptr, false, 0, 0, NDI_SEARCH_AUTO};
+    ndi_interp2d* h = new ndi_interp2d();
+    h->dtype = dtype; h->device = dev; h->n = n; h->m = m; h->w = w;
+    h->x = h->y = h->data = nullptr; h->owns_tables = false;
+    h->hint_x = h->hint_y = 0; h->search_mode = NDI_SEARCH_AUTO;
     bool o1 = false, o2 = false, o3 = false;
     st = take_table(x, (size_t)n * es, flags, ws->s[0], &h->x, &o1);
     if (st == NDI_OK) st = take_table(y, (size_t)m * es, flags, ws->s[0], &h->y, &o2);
@@ -648,6 +745,9 @@ ndi_status ndi_interp2d_create(ndi_dtype dtype, const void* x, int64_t n, const 
     if (st != NDI_OK) { ndi_interp2d_destroy(h); return st; }
     h->hint_x = rx[0] == NDI_MONO_RISING_STRICT ? rx[1] : 0;
     h->hint_y = ry[0] == NDI_MONO_RISING_STRICT ? ry[1] : 0;
+    if (!h->hint_x) st = build_aids(dtype, h->x, n, ws->s[0], &h->aids_x);
+    if (st == NDI_OK && !h->hint_y) st = build_aids(dtype, h->y, m, ws->s[0], &h->aids_y);
+    if (st != NDI_OK) { ndi_interp2d_destroy(h); return st; }
     *out = h;
     return NDI_OK;
 }
@@ -656,6 +756,7 @@ ndi_status ndi_interp2d_destroy(ndi_interp2d* h) {
     if (!h) return NDI_OK;
     DeviceGuard g(h->device);
     if (h->owns_tables) { cudaFree(h->x); cudaFree(h->y); cudaFree(h->data); }
+    h->aids_x.release(); h->aids_y.release();
     delete h;
     return NDI_OK;
 }
@@ -669,7 +770,7 @@ ndi_status ndi_interp2d_info(const ndi_interp2d* h, ndi_dtype* dtype, int64_t* n
     return NDI_OK;
 }
 ndi_status ndi_interp2d_set_search_mode(ndi_interp2d* h, int32_t mode) {
-    if (!h || mode < 0 || mode > 3) return fail(NDI_INVALID_ARGUMENT, "bad search mode");
+    if (!h || mode < 0 || mode > NDI_SEARCH_BUCKET_LUT) return fail(NDI_INVALID_ARGUMENT, "bad search mode");
     h->search_mode = mode;
     return NDI_OK;
 }
@@ -696,14 +797,17 @@ ndi_status ndi_interp2d_clone_to_device(const ndi_interp2d* h, int32_t device, n
     ndi_status st = copy(&c->x, h->x, (size_t)h->n * es);
     if (st == NDI_OK) st = copy(&c->y, h->y, (size_t)h->m * es);
     if (st == NDI_OK) st = copy(&c->data, h->data, (size_t)h->n * h->m * h->w * es);
-    if (st != NDI_OK) { cudaFree(c->x); cudaFree(c->y); cudaFree(c->data); delete c; return st; }
+    c->aids_x = c->aids_y = GridAids{};
+    if (st == NDI_OK && !h->hint_x) st = build_aids(c->dtype, c->x, c->n, nullptr, &c->aids_x);
+    if (st == NDI_OK && !h->hint_y) st = build_aids(c->dtype, c->y, c->m, nullptr, &c->aids_y);
+    if (st != NDI_OK) { cudaFree(c->x); cudaFree(c->y); cudaFree(c->data); c->aids_x.release(); c->aids_y.release(); delete c; return st; }
     *out = c;
     return NDI_OK;
 }
 
 static void search2(const ndi_interp2d* h, size_t es, int64_t nq, SearchCfg* sx, SearchCfg* sy) {
-    *sx = make_search(h->n, es, h->hint_x, h->search_mode, nq, 0);
-    *sy = make_search(h->m, es, h->hint_y, h->search_mode, nq, sx->smem ? (size_t)h->n * es + 16 : 0);
+    *sx = make_search(h->meta_x(), h->search_mode, nq, 0);
+    *sy = make_search(h->meta_y(), h->search_mode, nq, sx->smem ? (size_t)sx->stage_n * es + 16 : 0);
 }
 
 ndi_status ndi_interp2d_bilinear_dev(const ndi_interp2d* h, const void* qx_dev, const void* qy_dev, int64_t nq,

@@ -11,7 +11,10 @@
 //     is processed by LPQ lanes per query with V-element (16-byte when possible) vector loads
 //     and stores, so that a warp's stores cover whole contiguous output rows:
 //       - thin rows (w <= 32*V):  LPQ = pow2ceil(w / V) lanes per query, 32/LPQ queries per
-//         round, LPQ rounds per tile -- one thread per query when w == 1;
+//         round, LPQ rounds per tile -- one thread per query when w == 1.  A warp takes TPW
+//         tiles per iteration and searches them in lock step (search_multi), so the
+//         dependent-probe latency of the bisection is paid once per TPW*32 queries; the row
+//         gathers of a few rounds are issued together before any of them is consumed.
 //       - wide rows (w > 32*V):   LPQ = 32, the row is cut into SLICES of 32*V columns and a
 //         (tile, slice) pair is one warp task; consecutive warps take consecutive slices of the
 //         same tile, so a block writes whole rows.  Within a task the table rows stay in
@@ -48,10 +51,50 @@ struct Eval2 {                       // bilinear
     long long ntasks; int nslices;
 };
 
-template <int LPQ> struct Rounds { static constexpr int QPR = 32 / LPQ; };
-
 __device__ __forceinline__ bool shfl_b(bool v, int src) { return __shfl_sync(0xffffffffu, (int)v, src) != 0; }
 template <class T> __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__host__ __device__ inline size_t stage_bytes(const SearchCfg& sc, size_t elem) {
+    return sc.smem ? (((size_t)sc.stage_n * elem + 15) & ~(size_t)15) : 0;
+}
+
+// grid view for the search: stages the grid (or its coarse table) into shared memory when asked
+template <class T>
+__device__ __forceinline__ GridView<T> make_grid_view(const T* grid, int n, const SearchCfg& sc, unsigned char* smem,
+                                                      uint64_t* bar) {
+    GridView<T> g;
+    g.fine = grid; g.top = grid; g.n = n; g.top_step = sc.top_step; g.shift = 0;
+    g.mode = sc.lut ? SEARCH_LUT : (sc.guess ? SEARCH_GUESS : SEARCH_BISECT);
+    g.lut = static_cast<const int2*>(sc.lut); g.nb = sc.lut_n; g.g0d = sc.g0d; g.scale = sc.scale;
+    if (sc.smem) {
+        g.top = stage_grid<T>(reinterpret_cast<T*>(smem), static_cast<const T*>(sc.stage_src), sc.stage_n, bar);
+        g.shift = sc.coarse_shift;
+    }
+    g.g0 = g.at(0); g.gl = g.at(n - 1);
+    return g;
+}
+
+// thin rows: tiles searched in lock step by one warp (TPW) and rounds whose gathers are issued
+// together (RB).  Tunable at build time for measurement.
+#ifndef NDI_TPW_LINEAR
+#define NDI_TPW_LINEAR 2
+#endif
+#ifndef NDI_TPW_CUBIC
+#define NDI_TPW_CUBIC 2
+#endif
+#ifndef NDI_TPW_BILINEAR
+#define NDI_TPW_BILINEAR 2
+#endif
+#ifndef NDI_RB_LINEAR
+#define NDI_RB_LINEAR 4
+#endif
+#ifndef NDI_RB_CUBIC
+#define NDI_RB_CUBIC 2
+#endif
+#ifndef NDI_RB_BILINEAR
+#define NDI_RB_BILINEAR 2
+#endif
+constexpr int kTilesLinear = NDI_TPW_LINEAR, kTilesCubic = NDI_TPW_CUBIC, kTilesBilinear = NDI_TPW_BILINEAR;
 
 // ------------------------------------------------------------------------------------------------
 // K3: Linear::interp_into x batch (linear.rs:73-98)
@@ -60,57 +103,88 @@ template <class T, int V, int LPQ>
 __global__ void __launch_bounds__(kBlock) interp1d_linear_kernel(const Eval1<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
-    const T* g = p.grid;
-    if (p.sc.smem) g = stage_grid<T>(reinterpret_cast<T*>(smem_raw), p.grid, p.n, &bar);
-    const T g0 = g[0], gl = g[p.n - 1];
+    const GridView<T> g = make_grid_view<T>(p.grid, p.n, p.sc, smem_raw, &bar);
+    const T g0 = g.g0, gl = g.gl;
     const int lane = threadIdx.x & 31;
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     for (long long task = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < p.ntasks; task += nwarps) {
-        const long long tile = (LPQ == 32) ? task / p.nslices : task;
-        const int slice = (LPQ == 32) ? (int)(task - tile * p.nslices) : 0;
-        const long long qbase = tile * 32;
-        const long long qi = qbase + lane;
-        const bool live = qi < p.nq;
-        const T x = live ? ld_query(p.q + qi) : g0;
-        // linear.rs:80-84: out of range (or NaN) without extrapolation is an error;
-        // with extrapolation only NaN fails (vector_extensions.rs:83-84)
-        const bool bad = live && (p.mode ? Ar<T>::is_nan(x) : !in_range(g0, gl, x));
-        const int idx = lower_index<T>(g, p.n, x, p.sc.top_step, p.sc.guess != 0);   // linear.rs:87
-        const T x1 = g[idx], x2 = g[idx + 1];                                          // linear.rs:90-91
-        const T dx21 = Ar<T>::sub(x2, x1), dxq = Ar<T>::sub(x, x1);
-        if (slice == 0) report_first_bad(p.err, bad, (unsigned long long)qi);
-        const bool skip = bad || !live;
-
         if constexpr (LPQ < 32) {
-            constexpr int QPR = 32 / LPQ;
-            const int sub = lane % LPQ;
+            constexpr int TPW = kTilesLinear, QPR = 32 / LPQ, RB = LPQ < NDI_RB_LINEAR ? LPQ : NDI_RB_LINEAR;
+            const long long qbase0 = task * (32 * TPW);
+            T x[TPW]; int idx[TPW]; T dx21[TPW], dxq[TPW]; bool skip[TPW];
 #pragma unroll
-            for (int r = 0; r < LPQ; ++r) {
-                const int src = r * QPR + lane / LPQ;
-                const int is = __shfl_sync(0xffffffffu, idx, src);
-                const T d21 = shfl_t(dx21, src), dq = shfl_t(dxq, src);
-                const bool sk = shfl_b(skip, src);
-                if (!sk) {
-                    const T* row = p.data + (long long)is * p.w;
-                    T* o = p.out + (qbase + src) * p.w;
-                    for (long long col = (long long)sub * V; col < p.w; col += LPQ * V) {
-                        const Vec<T, V> y1 = ld_table<T, V>(row + col);
-                        const Vec<T, V> y2 = ld_table<T, V>(row + p.w + col);
-                        Vec<T, V> res;
+            for (int t = 0; t < TPW; ++t) {
+                const long long qi = qbase0 + t * 32 + lane;
+                x[t] = qi < p.nq ? ld_query(p.q + qi) : g0;
+            }
+            search_multi<T, TPW>(g, x, idx, dx21, dxq);                               // linear.rs:87, :90-91 (x1, x2)
 #pragma unroll
-                        for (int e = 0; e < V; ++e) res.v[e] = calc_frac_pre<T>(y1.v[e], y2.v[e], d21, dq);  // linear.rs:94-96
-                        st_stream<T, V>(o + col, res);
+            for (int t = 0; t < TPW; ++t) {
+                const long long qi = qbase0 + t * 32 + lane;
+                const bool live = qi < p.nq;
+                // linear.rs:80-84: out of range (or NaN) without extrapolation is an error;
+                // with extrapolation only NaN fails (vector_extensions.rs:83-84)
+                const bool bad = live && (p.mode ? Ar<T>::is_nan(x[t]) : !in_range(g0, gl, x[t]));
+                const T x1 = dx21[t], x2 = dxq[t];
+                dx21[t] = Ar<T>::sub(x2, x1); dxq[t] = Ar<T>::sub(x[t], x1);
+                if (qbase0 + t * 32 < p.nq) report_first_bad(p.err, bad, (unsigned long long)qi);
+                skip[t] = bad || !live;
+            }
+            const int sub = lane % LPQ, qsel = lane / LPQ;
+            const long long col = (long long)sub * V;
+            const bool colok = col < p.w;
+#pragma unroll
+            for (int t = 0; t < TPW; ++t) {
+                const long long qbase = qbase0 + t * 32;
+                if (qbase >= p.nq) break;
+#pragma unroll
+                for (int r0 = 0; r0 < LPQ; r0 += RB) {
+                    Vec<T, V> y1[RB], y2[RB]; bool ok[RB]; T d21[RB], dq[RB];
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {                                     // issue all gathers of the batch
+                        const int src = (r0 + j) * QPR + qsel;
+                        const int is = __shfl_sync(0xffffffffu, idx[t], src);
+                        d21[j] = shfl_t(dx21[t], src); dq[j] = shfl_t(dxq[t], src);
+                        ok[j] = !shfl_b(skip[t], src) && colok;
+                        if (ok[j]) {
+                            const T* row = p.data + (long long)is * p.w + col;
+                            y1[j] = ld_table<T, V>(row);
+                            y2[j] = ld_table<T, V>(row + p.w);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {
+                        if (ok[j]) {
+                            const int src = (r0 + j) * QPR + qsel;
+                            Vec<T, V> res;
+#pragma unroll
+                            for (int e = 0; e < V; ++e) res.v[e] = calc_frac_pre<T>(y1[j].v[e], y2[j].v[e], d21[j], dq[j]);  // linear.rs:94-96
+                            st_stream<T, V>(p.out + (qbase + src) * p.w + col, res);
+                        }
                     }
                 }
             }
         } else {
+            const long long tile = task / p.nslices;
+            const int slice = (int)(task - tile * p.nslices);
+            const long long qbase = tile * 32;
+            const long long qi = qbase + lane;
+            const bool live = qi < p.nq;
+            T x[1] = {live ? ld_query(p.q + qi) : g0};
+            int idx[1]; T xl[1], xr[1];
+            search_multi<T, 1>(g, x, idx, xl, xr);
+            const bool bad = live && (p.mode ? Ar<T>::is_nan(x[0]) : !in_range(g0, gl, x[0]));
+            const T x1 = xl[0], x2 = xr[0];
+            const T dx21 = Ar<T>::sub(x2, x1), dxq = Ar<T>::sub(x[0], x1);
+            if (slice == 0) report_first_bad(p.err, bad, (unsigned long long)qi);
+            const bool skip = bad || !live;
             const long long col = ((long long)slice * 32 + lane) * V;
             const bool colok = col < p.w;
             int cur = -1;
             Vec<T, V> y1, y2;
             const int nlive = (int)min((long long)32, p.nq - qbase);
             for (int s = 0; s < nlive; ++s) {
-                const int is = __shfl_sync(0xffffffffu, idx, s);
+                const int is = __shfl_sync(0xffffffffu, idx[0], s);
                 const T d21 = shfl_t(dx21, s), dq = shfl_t(dxq, s);
                 const bool sk = shfl_b(skip, s);
                 if (sk || !colok) continue;
@@ -146,69 +220,107 @@ __device__ __forceinline__ T cubic_point(T yl, T yr, T al, T bl, T t, T omt, T t
     return Ar<T>::add(lin, Ar<T>::mul(tt, cur));
 }
 
+// range check, periodic wrap and NaN test of one query (cubic_spline.rs:797-809); returns `bad`
+template <class T>
+__device__ __forceinline__ bool cubic_prepare(T& x, T g0, T gl, int mode) {
+    const bool inr = in_range(g0, gl, x);                                              // :797
+    if (mode == 0) return !inr;                                                        // :798-802
+    if (mode == 2 && !inr) x = Ar<T>::add(rem_euclid<T>(Ar<T>::sub(x, g0), Ar<T>::sub(gl, g0)), g0);  // :805-809
+    return Ar<T>::is_nan(x);                                                           // NaN reaches get_lower_index
+}
+
 template <class T, int V, int LPQ>
 __global__ void __launch_bounds__(kBlock) interp1d_cubic_kernel(const Eval1<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
-    const T* g = p.grid;
-    if (p.sc.smem) g = stage_grid<T>(reinterpret_cast<T*>(smem_raw), p.grid, p.n, &bar);
-    const T g0 = g[0], gl = g[p.n - 1];
+    const GridView<T> g = make_grid_view<T>(p.grid, p.n, p.sc, smem_raw, &bar);
+    const T g0 = g.g0, gl = g.gl;
     const T one = (T)1;
     const int lane = threadIdx.x & 31;
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     for (long long task = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < p.ntasks; task += nwarps) {
-        const long long tile = (LPQ == 32) ? task / p.nslices : task;
-        const int slice = (LPQ == 32) ? (int)(task - tile * p.nslices) : 0;
-        const long long qbase = tile * 32;
-        const long long qi = qbase + lane;
-        const bool live = qi < p.nq;
-        T x = live ? ld_query(p.q + qi) : g0;
-        const bool inr = in_range(g0, gl, x);                                          // :797
-        bool bad = false;
-        if (p.mode == 0) bad = !inr;                                                   // :798-802
-        else if (p.mode == 2 && !inr) x = Ar<T>::add(rem_euclid<T>(Ar<T>::sub(x, g0), Ar<T>::sub(gl, g0)), g0);  // :805-809
-        if (p.mode != 0) bad = Ar<T>::is_nan(x);                                       // NaN reaches get_lower_index
-        bad = bad && live;
-        const int idx = lower_index<T>(g, p.n, x, p.sc.top_step, p.sc.guess != 0);   // :811
-        const T xl = g[idx], xr = g[idx + 1];
-        const T t = Ar<T>::div(Ar<T>::sub(x, xl), Ar<T>::sub(xr, xl));                 // :818
-        const T omt = Ar<T>::sub(one, t);
-        const T tt = Ar<T>::mul(t, omt);
-        if (slice == 0) report_first_bad(p.err, bad, (unsigned long long)qi);
-        const bool skip = bad || !live;
-
         if constexpr (LPQ < 32) {
-            constexpr int QPR = 32 / LPQ;
-            const int sub = lane % LPQ;
+            constexpr int TPW = kTilesCubic, QPR = 32 / LPQ, RB = LPQ < NDI_RB_CUBIC ? LPQ : NDI_RB_CUBIC;
+            const long long qbase0 = task * (32 * TPW);
+            T x[TPW]; int idx[TPW]; T tq[TPW], omt[TPW], tt[TPW]; bool skip[TPW], bad[TPW];
 #pragma unroll
-            for (int r = 0; r < LPQ; ++r) {
-                const int src = r * QPR + lane / LPQ;
-                const int is = __shfl_sync(0xffffffffu, idx, src);
-                const T ts = shfl_t(t, src), os = shfl_t(omt, src), tts = shfl_t(tt, src);
-                const bool sk = shfl_b(skip, src);
-                if (!sk) {
-                    const long long ro = (long long)is * p.w;
-                    T* o = p.out + (qbase + src) * p.w;
-                    for (long long col = (long long)sub * V; col < p.w; col += LPQ * V) {
-                        const Vec<T, V> yl = ld_table<T, V>(p.data + ro + col);
-                        const Vec<T, V> yr = ld_table<T, V>(p.data + ro + p.w + col);
-                        const Vec<T, V> al = ld_table<T, V>(p.a + ro + col);
-                        const Vec<T, V> bl = ld_table<T, V>(p.b + ro + col);
-                        Vec<T, V> res;
+            for (int t = 0; t < TPW; ++t) {
+                const long long qi = qbase0 + t * 32 + lane;
+                const bool live = qi < p.nq;
+                x[t] = live ? ld_query(p.q + qi) : g0;
+                bad[t] = cubic_prepare<T>(x[t], g0, gl, p.mode) && live;
+            }
+            search_multi<T, TPW>(g, x, idx, tq, omt);                                 // :811 (+ x_left, x_right)
 #pragma unroll
-                        for (int e = 0; e < V; ++e) res.v[e] = cubic_point<T>(yl.v[e], yr.v[e], al.v[e], bl.v[e], ts, os, tts);
-                        st_stream<T, V>(o + col, res);
+            for (int t = 0; t < TPW; ++t) {
+                const long long qi = qbase0 + t * 32 + lane;
+                const T xl = tq[t], xr = omt[t];
+                tq[t] = Ar<T>::div(Ar<T>::sub(x[t], xl), Ar<T>::sub(xr, xl));          // :818
+                omt[t] = Ar<T>::sub(one, tq[t]);
+                tt[t] = Ar<T>::mul(tq[t], omt[t]);
+                if (qbase0 + t * 32 < p.nq) report_first_bad(p.err, bad[t], (unsigned long long)qi);
+                skip[t] = bad[t] || !(qi < p.nq);
+            }
+            const int sub = lane % LPQ, qsel = lane / LPQ;
+            const long long col = (long long)sub * V;
+            const bool colok = col < p.w;
+#pragma unroll
+            for (int t = 0; t < TPW; ++t) {
+                const long long qbase = qbase0 + t * 32;
+                if (qbase >= p.nq) break;
+#pragma unroll
+                for (int r0 = 0; r0 < LPQ; r0 += RB) {
+                    Vec<T, V> yl[RB], yr[RB], al[RB], bl[RB]; bool ok[RB]; T ts[RB], os[RB], tts[RB];
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {
+                        const int src = (r0 + j) * QPR + qsel;
+                        const int is = __shfl_sync(0xffffffffu, idx[t], src);
+                        ts[j] = shfl_t(tq[t], src); os[j] = shfl_t(omt[t], src); tts[j] = shfl_t(tt[t], src);
+                        ok[j] = !shfl_b(skip[t], src) && colok;
+                        if (ok[j]) {
+                            const long long ro = (long long)is * p.w + col;
+                            yl[j] = ld_table<T, V>(p.data + ro);
+                            yr[j] = ld_table<T, V>(p.data + ro + p.w);
+                            al[j] = ld_table<T, V>(p.a + ro);
+                            bl[j] = ld_table<T, V>(p.b + ro);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {
+                        if (ok[j]) {
+                            const int src = (r0 + j) * QPR + qsel;
+                            Vec<T, V> res;
+#pragma unroll
+                            for (int e = 0; e < V; ++e)
+                                res.v[e] = cubic_point<T>(yl[j].v[e], yr[j].v[e], al[j].v[e], bl[j].v[e], ts[j], os[j], tts[j]);
+                            st_stream<T, V>(p.out + (qbase + src) * p.w + col, res);
+                        }
                     }
                 }
             }
         } else {
+            const long long tile = task / p.nslices;
+            const int slice = (int)(task - tile * p.nslices);
+            const long long qbase = tile * 32;
+            const long long qi = qbase + lane;
+            const bool live = qi < p.nq;
+            T x[1] = {live ? ld_query(p.q + qi) : g0};
+            const bool bad = cubic_prepare<T>(x[0], g0, gl, p.mode) && live;
+            int idx[1]; T xls[1], xrs[1];
+            search_multi<T, 1>(g, x, idx, xls, xrs);
+            const T xl = xls[0], xr = xrs[0];
+            const T t = Ar<T>::div(Ar<T>::sub(x[0], xl), Ar<T>::sub(xr, xl));
+            const T omt = Ar<T>::sub(one, t);
+            const T tt = Ar<T>::mul(t, omt);
+            if (slice == 0) report_first_bad(p.err, bad, (unsigned long long)qi);
+            const bool skip = bad || !live;
             const long long col = ((long long)slice * 32 + lane) * V;
             const bool colok = col < p.w;
             int cur = -1;
             Vec<T, V> yl, yr, al, bl;
             const int nlive = (int)min((long long)32, p.nq - qbase);
             for (int s = 0; s < nlive; ++s) {
-                const int is = __shfl_sync(0xffffffffu, idx, s);
+                const int is = __shfl_sync(0xffffffffu, idx[0], s);
                 const T ts = shfl_t(t, s), os = shfl_t(omt, s), tts = shfl_t(tt, s);
                 const bool sk = shfl_b(skip, s);
                 if (sk || !colok) continue;
@@ -232,74 +344,113 @@ __global__ void __launch_bounds__(kBlock) interp1d_cubic_kernel(const Eval1<T> p
 // ------------------------------------------------------------------------------------------------
 // K4: Bilinear::interp_into x batch (bilinear.rs:64-99)
 // ------------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ T bilinear_point(T z11, T z12, T z21, T z22, T d21x, T dqx, T d21y, T dqy) {
+    const T z1 = calc_frac_pre<T>(z11, z21, d21x, dqx);                               // bilinear.rs:94
+    const T z2 = calc_frac_pre<T>(z12, z22, d21x, dqx);                               // :95
+    return calc_frac_pre<T>(z1, z2, d21y, dqy);                                       // :96
+}
+
 template <class T, int V, int LPQ>
 __global__ void __launch_bounds__(kBlock) interp2d_bilinear_kernel(const Eval2<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar[2];
-    const T* gx = p.gx;
-    const T* gy = p.gy;
-    if (p.scx.smem) gx = stage_grid<T>(reinterpret_cast<T*>(smem_raw), p.gx, p.n, &bar[0]);
-    if (p.scy.smem) {
-        size_t off = p.scx.smem ? (((size_t)p.n * sizeof(T) + 15) & ~(size_t)15) : 0;
-        gy = stage_grid<T>(reinterpret_cast<T*>(smem_raw + off), p.gy, p.m, &bar[1]);
-    }
-    const T gx0 = gx[0], gxl = gx[p.n - 1], gy0 = gy[0], gyl = gy[p.m - 1];
+    const GridView<T> gx = make_grid_view<T>(p.gx, p.n, p.scx, smem_raw, &bar[0]);
+    const GridView<T> gy = make_grid_view<T>(p.gy, p.m, p.scy, smem_raw + stage_bytes(p.scx, sizeof(T)), &bar[1]);
+    const T gx0 = gx.g0, gxl = gx.gl, gy0 = gy.g0, gyl = gy.gl;
     const int lane = threadIdx.x & 31;
     const long long rowx = (long long)p.m * p.w;      // elements between x-rows
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     for (long long task = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < p.ntasks; task += nwarps) {
-        const long long tile = (LPQ == 32) ? task / p.nslices : task;
-        const int slice = (LPQ == 32) ? (int)(task - tile * p.nslices) : 0;
-        const long long qbase = tile * 32;
-        const long long qi = qbase + lane;
-        const bool live = qi < p.nq;
-        const T x = live ? ld_query(p.qx + qi) : gx0;
-        const T y = live ? ld_query(p.qy + qi) : gy0;
-        // bilinear.rs:71-80: x is checked before y
-        bool badx, bady;
-        if (p.extrapolate) { badx = Ar<T>::is_nan(x); bady = Ar<T>::is_nan(y); }
-        else { badx = !in_range(gx0, gxl, x); bady = !in_range(gy0, gyl, y); }
-        const bool bad = live && (badx || bady);
-        const int ix = lower_index<T>(gx, p.n, x, p.scx.top_step, p.scx.guess != 0);  // :82
-        const int iy = lower_index<T>(gy, p.m, y, p.scy.top_step, p.scy.guess != 0);
-        const T x1 = gx[ix], x2 = gx[ix + 1], y1 = gy[iy], y2 = gy[iy + 1];
-        const T dx21 = Ar<T>::sub(x2, x1), dxq = Ar<T>::sub(x, x1);
-        const T dy21 = Ar<T>::sub(y2, y1), dyq = Ar<T>::sub(y, y1);
-        const long long cell = ((long long)ix * p.m + iy) * p.w;                      // z11 (:83)
-        if (slice == 0) report_first_bad(p.err, bad, 2ull * (unsigned long long)qi + (badx ? 0ull : 1ull));
-        const bool skip = bad || !live;
-
-        auto point = [&](T z11, T z12, T z21, T z22, T d21x, T dqx, T d21y, T dqy) -> T {
-            const T z1 = calc_frac_pre<T>(z11, z21, d21x, dqx);                       // :94
-            const T z2 = calc_frac_pre<T>(z12, z22, d21x, dqx);                       // :95
-            return calc_frac_pre<T>(z1, z2, d21y, dqy);                               // :96
-        };
-
         if constexpr (LPQ < 32) {
-            constexpr int QPR = 32 / LPQ;
-            const int sub = lane % LPQ;
+            constexpr int TPW = kTilesBilinear, QPR = 32 / LPQ, RB = LPQ < NDI_RB_BILINEAR ? LPQ : NDI_RB_BILINEAR;
+            const long long qbase0 = task * (32 * TPW);
+            T x[TPW], y[TPW]; int ix[TPW], iy[TPW];
+            long long cell[TPW]; T ax[TPW], bx[TPW], ay[TPW], by[TPW]; bool skip[TPW];
 #pragma unroll
-            for (int r = 0; r < LPQ; ++r) {
-                const int src = r * QPR + lane / LPQ;
-                const long long cs = __shfl_sync(0xffffffffu, cell, src);
-                const T ax = shfl_t(dx21, src), bx = shfl_t(dxq, src), ay = shfl_t(dy21, src), by = shfl_t(dyq, src);
-                const bool sk = shfl_b(skip, src);
-                if (!sk) {
-                    T* o = p.out + (qbase + src) * p.w;
-                    for (long long col = (long long)sub * V; col < p.w; col += LPQ * V) {
-                        const T* c0 = p.data + cs + col;
-                        const Vec<T, V> z11 = ld_table<T, V>(c0);
-                        const Vec<T, V> z12 = ld_table<T, V>(c0 + p.w);
-                        const Vec<T, V> z21 = ld_table<T, V>(c0 + rowx);
-                        const Vec<T, V> z22 = ld_table<T, V>(c0 + rowx + p.w);
-                        Vec<T, V> res;
+            for (int t = 0; t < TPW; ++t) {
+                const long long qi = qbase0 + t * 32 + lane;
+                const bool live = qi < p.nq;
+                x[t] = live ? ld_query(p.qx + qi) : gx0;
+                y[t] = live ? ld_query(p.qy + qi) : gy0;
+            }
+            search_multi<T, TPW>(gx, x, ix, ax, bx);                                  // bilinear.rs:82 (+ x1, x2)
+            search_multi<T, TPW>(gy, y, iy, ay, by);
 #pragma unroll
-                        for (int e = 0; e < V; ++e) res.v[e] = point(z11.v[e], z12.v[e], z21.v[e], z22.v[e], ax, bx, ay, by);
-                        st_stream<T, V>(o + col, res);
+            for (int t = 0; t < TPW; ++t) {
+                const long long qi = qbase0 + t * 32 + lane;
+                const bool live = qi < p.nq;
+                bool badx, bady;                                                       // :71-80: x is checked before y
+                if (p.extrapolate) { badx = Ar<T>::is_nan(x[t]); bady = Ar<T>::is_nan(y[t]); }
+                else { badx = !in_range(gx0, gxl, x[t]); bady = !in_range(gy0, gyl, y[t]); }
+                const bool bad = live && (badx || bady);
+                const T x1 = ax[t], x2 = bx[t], y1 = ay[t], y2 = by[t];
+                ax[t] = Ar<T>::sub(x2, x1); bx[t] = Ar<T>::sub(x[t], x1);
+                ay[t] = Ar<T>::sub(y2, y1); by[t] = Ar<T>::sub(y[t], y1);
+                cell[t] = ((long long)ix[t] * p.m + iy[t]) * p.w;                     // z11 (:83)
+                if (qbase0 + t * 32 < p.nq)
+                    report_first_bad(p.err, bad, 2ull * (unsigned long long)qi + (badx ? 0ull : 1ull));
+                skip[t] = bad || !live;
+            }
+            const int sub = lane % LPQ, qsel = lane / LPQ;
+            const long long col = (long long)sub * V;
+            const bool colok = col < p.w;
+#pragma unroll
+            for (int t = 0; t < TPW; ++t) {
+                const long long qbase = qbase0 + t * 32;
+                if (qbase >= p.nq) break;
+#pragma unroll
+                for (int r0 = 0; r0 < LPQ; r0 += RB) {
+                    Vec<T, V> z11[RB], z12[RB], z21[RB], z22[RB]; bool ok[RB]; T sax[RB], sbx[RB], say[RB], sby[RB];
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {
+                        const int src = (r0 + j) * QPR + qsel;
+                        const long long cs = __shfl_sync(0xffffffffu, cell[t], src);
+                        sax[j] = shfl_t(ax[t], src); sbx[j] = shfl_t(bx[t], src);
+                        say[j] = shfl_t(ay[t], src); sby[j] = shfl_t(by[t], src);
+                        ok[j] = !shfl_b(skip[t], src) && colok;
+                        if (ok[j]) {
+                            const T* c0 = p.data + cs + col;
+                            z11[j] = ld_table<T, V>(c0);
+                            z12[j] = ld_table<T, V>(c0 + p.w);
+                            z21[j] = ld_table<T, V>(c0 + rowx);
+                            z22[j] = ld_table<T, V>(c0 + rowx + p.w);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {
+                        if (ok[j]) {
+                            const int src = (r0 + j) * QPR + qsel;
+                            Vec<T, V> res;
+#pragma unroll
+                            for (int e = 0; e < V; ++e)
+                                res.v[e] = bilinear_point<T>(z11[j].v[e], z12[j].v[e], z21[j].v[e], z22[j].v[e], sax[j], sbx[j], say[j], sby[j]);
+                            st_stream<T, V>(p.out + (qbase + src) * p.w + col, res);
+                        }
                     }
                 }
             }
         } else {
+            const long long tile = task / p.nslices;
+            const int slice = (int)(task - tile * p.nslices);
+            const long long qbase = tile * 32;
+            const long long qi = qbase + lane;
+            const bool live = qi < p.nq;
+            T x[1] = {live ? ld_query(p.qx + qi) : gx0};
+            T y[1] = {live ? ld_query(p.qy + qi) : gy0};
+            bool badx, bady;
+            if (p.extrapolate) { badx = Ar<T>::is_nan(x[0]); bady = Ar<T>::is_nan(y[0]); }
+            else { badx = !in_range(gx0, gxl, x[0]); bady = !in_range(gy0, gyl, y[0]); }
+            const bool bad = live && (badx || bady);
+            int ix[1], iy[1]; T x1s[1], x2s[1], y1s[1], y2s[1];
+            search_multi<T, 1>(gx, x, ix, x1s, x2s);
+            search_multi<T, 1>(gy, y, iy, y1s, y2s);
+            const T x1 = x1s[0], x2 = x2s[0], y1 = y1s[0], y2 = y2s[0];
+            const T dx21 = Ar<T>::sub(x2, x1), dxq = Ar<T>::sub(x[0], x1);
+            const T dy21 = Ar<T>::sub(y2, y1), dyq = Ar<T>::sub(y[0], y1);
+            const long long cell = ((long long)ix[0] * p.m + iy[0]) * p.w;
+            if (slice == 0) report_first_bad(p.err, bad, 2ull * (unsigned long long)qi + (badx ? 0ull : 1ull));
+            const bool skip = bad || !live;
             const long long col = ((long long)slice * 32 + lane) * V;
             const bool colok = col < p.w;
             long long cur = -1;
@@ -320,7 +471,7 @@ __global__ void __launch_bounds__(kBlock) interp2d_bilinear_kernel(const Eval2<T
                 }
                 Vec<T, V> res;
 #pragma unroll
-                for (int e = 0; e < V; ++e) res.v[e] = point(z11.v[e], z12.v[e], z21.v[e], z22.v[e], ax, bx, ay, by);
+                for (int e = 0; e < V; ++e) res.v[e] = bilinear_point<T>(z11.v[e], z12.v[e], z21.v[e], z22.v[e], ax, bx, ay, by);
                 st_stream<T, V>(p.out + (qbase + s) * p.w + col, res);
             }
         }
@@ -336,17 +487,27 @@ __global__ void __launch_bounds__(kBlock) lower_index_kernel(const T* __restrict
                                                             long long* __restrict__ idx, unsigned long long* err) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
-    const T* g = grid;
-    if (sc.smem) g = stage_grid<T>(reinterpret_cast<T*>(smem_raw), grid, n, &bar);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long nq_pad = (nq + 31) & ~31ll;       // whole warps, so the ballot in report_first_bad is full
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nq_pad; i += stride) {
-        const bool live = i < nq;
-        const T x = live ? ld_query(q + i) : g[0];
-        const bool bad = live && Ar<T>::is_nan(x);
-        const int r = lower_index<T>(g, n, x, sc.top_step, sc.guess != 0);
-        report_first_bad(err, bad, (unsigned long long)i);
-        if (live && !bad) idx[i] = r;
+    constexpr int K = 4;
+    const GridView<T> g = make_grid_view<T>(grid, n, sc, smem_raw, &bar);
+    const T g0 = g.g0;
+    const long long span = (long long)blockDim.x * K;
+    const long long nspans = (nq + span - 1) / span;
+    for (long long sp = blockIdx.x; sp < nspans; sp += gridDim.x) {
+        T x[K]; int r[K]; T vlo[K], vhi[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const long long i = sp * span + (long long)k * blockDim.x + threadIdx.x;
+            x[k] = i < nq ? ld_query(q + i) : g0;
+        }
+        search_multi<T, K>(g, x, r, vlo, vhi);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const long long i = sp * span + (long long)k * blockDim.x + threadIdx.x;
+            const bool live = i < nq;
+            const bool bad = live && Ar<T>::is_nan(x[k]);
+            report_first_bad(err, bad, (unsigned long long)i);
+            if (live && !bad) idx[i] = r[k];
+        }
     }
 }
 
@@ -405,15 +566,19 @@ static int pick_vec(long long w, std::initializer_list<const void*> ptrs) {
 
 struct Shape { int v; int lpq; int nslices; long long ntasks; };
 
-template <class T>
-static Shape pick_shape(long long w, long long nq, int v) {
+static Shape pick_shape(long long w, long long nq, int v, int tiles_per_warp) {
     Shape s;
     s.v = v;
     long long groups = (w + v - 1) / v;
     s.lpq = pow2ceil(groups);
-    s.nslices = s.lpq == 32 ? (int)((groups + 31) / 32) : 1;
     long long tiles = (nq + 31) / 32;
-    s.ntasks = tiles * s.nslices;
+    if (s.lpq == 32) {
+        s.nslices = (int)((groups + 31) / 32);
+        s.ntasks = tiles * s.nslices;
+    } else {
+        s.nslices = 1;
+        s.ntasks = (tiles + tiles_per_warp - 1) / tiles_per_warp;
+    }
     return s;
 }
 
@@ -462,15 +627,13 @@ static cudaError_t launch_eval(K kernel, const P& p, size_t smem, cudaStream_t s
         NDI_LPQ_SWITCH(KERNEL, T, 1, SH.lpq, P, SMEM, ST)                                 \
     }
 
-static size_t grid_smem_bytes(int smem, long long n, size_t elem) { return smem ? (((size_t)n * elem + 15) & ~(size_t)15) : 0; }
-
 template <class T>
 cudaError_t launch_interp1d_linear(const T* grid, int64_t n, SearchCfg sc, const T* data, int64_t w, const T* q,
                                    int64_t nq, int extrapolate, T* out, unsigned long long* err, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    Shape sh = pick_shape<T>(w, nq, pick_vec<T>(w, {data, out}));
+    Shape sh = pick_shape(w, nq, pick_vec<T>(w, {data, out}), kTilesLinear);
     Eval1<T> p{grid, (int)n, sc, data, nullptr, nullptr, (long long)w, q, (long long)nq, extrapolate, out, err, sh.ntasks, sh.nslices};
-    size_t smem = grid_smem_bytes(sc.smem, n, sizeof(T));
+    size_t smem = stage_bytes(sc, sizeof(T));
     NDI_VEC_SWITCH(interp1d_linear_kernel, T, sh, p, smem, st)
 }
 
@@ -479,9 +642,9 @@ cudaError_t launch_interp1d_cubic(const T* grid, int64_t n, SearchCfg sc, const 
                                   int64_t w, const T* q, int64_t nq, int extrap_mode, T* out,
                                   unsigned long long* err, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    Shape sh = pick_shape<T>(w, nq, pick_vec<T>(w, {data, a, b, out}));
+    Shape sh = pick_shape(w, nq, pick_vec<T>(w, {data, a, b, out}), kTilesCubic);
     Eval1<T> p{grid, (int)n, sc, data, a, b, (long long)w, q, (long long)nq, extrap_mode, out, err, sh.ntasks, sh.nslices};
-    size_t smem = grid_smem_bytes(sc.smem, n, sizeof(T));
+    size_t smem = stage_bytes(sc, sizeof(T));
     NDI_VEC_SWITCH(interp1d_cubic_kernel, T, sh, p, smem, st)
 }
 
@@ -490,9 +653,9 @@ cudaError_t launch_interp2d_bilinear(const T* gx, int64_t n, SearchCfg scx, cons
                                      const T* data, int64_t w, const T* qx, const T* qy, int64_t nq, int extrapolate,
                                      T* out, unsigned long long* err, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    Shape sh = pick_shape<T>(w, nq, pick_vec<T>(w, {data, out}));
+    Shape sh = pick_shape(w, nq, pick_vec<T>(w, {data, out}), kTilesBilinear);
     Eval2<T> p{gx, (int)n, scx, gy, (int)m, scy, data, (long long)w, qx, qy, (long long)nq, extrapolate, out, err, sh.ntasks, sh.nslices};
-    size_t smem = grid_smem_bytes(scx.smem, n, sizeof(T)) + grid_smem_bytes(scy.smem, m, sizeof(T));
+    size_t smem = stage_bytes(scx, sizeof(T)) + stage_bytes(scy, sizeof(T));
     NDI_VEC_SWITCH(interp2d_bilinear_kernel, T, sh, p, smem, st)
 }
 
@@ -500,10 +663,10 @@ template <class T>
 cudaError_t launch_lower_index(const T* grid, int64_t n, SearchCfg sc, const T* q, int64_t nq, int64_t* idx,
                                unsigned long long* err, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    size_t smem = grid_smem_bytes(sc.smem, n, sizeof(T));
+    size_t smem = stage_bytes(sc, sizeof(T));
     cudaError_t e = prep_smem(lower_index_kernel<T>, smem);
     if (e != cudaSuccess) return e;
-    long long blocks = (nq + kBlock - 1) / kBlock;
+    long long blocks = (nq + (long long)kBlock * 4 - 1) / ((long long)kBlock * 4);
     long long cap = (long long)device_info().sm_count * 8;
     lower_index_kernel<T><<<(int)(blocks < cap ? blocks : cap), kBlock, smem, st>>>(grid, (int)n, sc, q, (long long)nq,
                                                                                    (long long*)idx, err);

@@ -146,6 +146,35 @@ cudaError_t launch_grid_classify(const T* x, int64_t n, int32_t* result_dev, uin
     return cudaGetLastError();
 }
 
+// ---- bucket table for the O(1) search (see ndi_device.cuh, SEARCH_LUT) ----------------------------
+// count(b) = number of grid points whose bucket is < b; bucket_of(g[i]) is non-decreasing in i, so
+// count(b) is a lower bound found by bisection.  One thread per bucket.
+template <class T>
+__global__ void __launch_bounds__(256) build_lut_kernel(const T* __restrict__ x, int n, double g0d, double scale, int nb,
+                                                        int2* __restrict__ lut) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    auto count_below = [&](int bb) {
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (bucket_of<T>(x[mid], g0d, scale, nb) < bb) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    lut[b] = make_int2(count_below(b), count_below(b + 1));
+}
+
+template <class T>
+cudaError_t launch_build_lut(const T* x, int64_t n, double g0d, double scale, int nb, void* lut_dev, cudaStream_t st) {
+    build_lut_kernel<T><<<(nb + 255) / 256, 256, 0, st>>>(x, (int)n, g0d, scale, nb, static_cast<int2*>(lut_dev));
+    count_launch();
+    return cudaGetLastError();
+}
+template cudaError_t launch_build_lut<float>(const float*, int64_t, double, double, int, void*, cudaStream_t);
+template cudaError_t launch_build_lut<double>(const double*, int64_t, double, double, int, void*, cudaStream_t);
+template cudaError_t launch_build_lut<int32_t>(const int32_t*, int64_t, double, double, int, void*, cudaStream_t);
+
 template cudaError_t launch_grid_classify<float>(const float*, int64_t, int32_t*, uint32_t*, cudaStream_t);
 template cudaError_t launch_grid_classify<double>(const double*, int64_t, int32_t*, uint32_t*, cudaStream_t);
 template cudaError_t launch_grid_classify<int32_t>(const int32_t*, int64_t, int32_t*, uint32_t*, cudaStream_t);

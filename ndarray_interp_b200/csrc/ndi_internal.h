@@ -9,9 +9,15 @@ namespace ndi {
 
 // how the lower-index search reads one grid
 struct SearchCfg {
-    int top_step;   // largest power of two <= n-2 (bisect_top_step)
-    int guess;      // 1: try the O(1) even-spacing guess first (uniform grids)
-    int smem;       // 1: stage the grid into shared memory with a bulk copy
+    int top_step;           // largest power of two <= n-2 (bisect_top_step)
+    int guess;              // 1: try the O(1) even-spacing guess first (uniform grids)
+    int smem;               // 1: stage `stage_n` elements from `stage_src` into shared memory (bulk copy)
+    int coarse_shift;       // log2 of the stride of the staged table (0: it is the whole grid)
+    int stage_n;
+    const void* stage_src;  // the grid itself, or the handle's coarse table grid[0], grid[S], grid[2S], ...
+    const void* lut;        // non-null: bucket-table search (int2 per bucket, see ndi_device.cuh)
+    int lut_n;              // number of buckets
+    double g0d, scale;      // bucket(x) = (x - g0d) * scale
 };
 
 // largest power of two <= n-2 (0 when n == 2): the first probe distance of the bisection
@@ -60,6 +66,9 @@ template <class T>
 cudaError_t launch_grid_classify(const T* x, int64_t n, int32_t* result_dev, uint32_t* scratch_dev,
                                  cudaStream_t st);
 size_t grid_classify_scratch_words();
+// bucket table of a strictly rising grid: lut[b] = (#points in buckets < b, #points in buckets <= b)
+template <class T>
+cudaError_t launch_build_lut(const T* x, int64_t n, double g0d, double scale, int nb, void* lut_dev, cudaStream_t st);
 
 // ---- spline construction (ndi_spline.cu) -----------------------------------------------------
 // Builds a, b ((n-1) x w each) on the device.  For bc_kind == INDIVIDUAL the four arrays are

@@ -66,7 +66,7 @@ def test_c3_linear_extrapolate_f32_full_size(D):
     q = (float(g[0]) + span * rng.uniform(-0.026, 1.026, (4096, 4096))).astype(np.float32)
     ip = D.DeviceInterp1D(dev(g), dev(y))
     outs = []
-    for mode in (L.SEARCH_AUTO, L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS):
+    for mode in (L.SEARCH_AUTO, L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS, L.SEARCH_BUCKET_LUT):
         ip.set_search_mode(mode)
         err = D.new_err_word()
         out = ip.linear(dev(q), True, err=err)

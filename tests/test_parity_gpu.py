@@ -171,7 +171,7 @@ def test_linear_matches_oracle(dt, trailing):
         assert same(strict.interp_array(qi), ref)
 
 
-@pytest.mark.parametrize("mode", [L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS])
+@pytest.mark.parametrize("mode", [L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS, L.SEARCH_BUCKET_LUT])
 @pytest.mark.parametrize("kind", ["uniform", "random", "exp"])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_linear_every_search_mode_gives_the_same_bits(mode, kind, dt):
@@ -286,7 +286,7 @@ def test_bilinear_error_axis_precedence():
         assert same(buf, ref)
 
 
-@pytest.mark.parametrize("mode", [L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS])
+@pytest.mark.parametrize("mode", [L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS, L.SEARCH_BUCKET_LUT])
 def test_bilinear_every_search_mode(mode):
     rng = np.random.default_rng(9)
     gx, gy = np.linspace(0, 1, 2048).astype(np.float32), np.cumsum(rng.uniform(0.5, 1.5, 777)).astype(np.float32)
