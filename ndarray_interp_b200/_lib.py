@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libndi_b200.so")
+# NDI_B200_LIB: A/B-test another in-tree build of the same sources (see build.py --out / --define)
+SO_PATH = os.environ.get("NDI_B200_LIB") or os.path.join(_HERE, "libndi_b200.so")
 
 OK, OUT_OF_BOUNDS, NAN_QUERY, PERIODIC_MISMATCH, INVALID_ARGUMENT, NOT_MONOTONIC, NO_SPLINE, UNSUPPORTED_DTYPE, \
     NO_DEVICE = range(9)

@@ -39,15 +39,19 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: build a variant (-DNAME=VALUE ...) into another .so for A/B measurements"""
+    so = os.path.join(HERE, out) if out else SO
+    if not out and not force and not stale():
         return SO
     objs = []
     procs = []
+    tag = ("_" + os.path.splitext(os.path.basename(out))[0]) if out else ""
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        o = os.path.join(HERE, "build", s.replace(".cu", tag + ".o"))
+        cmd = ([nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+               + ["-c", os.path.join(CSRC, s), "-o", o])
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     failed = False
@@ -58,10 +62,17 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", SO] + objs
+    link = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", so] + objs
     subprocess.check_call(link)
-    return SO
+    return so
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--define", action="append", default=[], help="NAME=VALUE, e.g. NDI_TPW_LINEAR=1")
+    ap.add_argument("--out", default=None, help="variant library name, e.g. libndi_b200_v1.so")
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.verbose, defines=a.define, out=a.out))

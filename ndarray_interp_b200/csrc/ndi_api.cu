@@ -139,6 +139,9 @@ static ndi_status grow(void** p, size_t* cap, size_t need) {
 // ---- search configuration ----------------------------------------------------------------------------
 // A grid that does not fit the shared-memory budget gets a coarse table grid[0], grid[S], ... built
 // once per handle; the kernels bisect the coarse table in shared memory and finish in L1/L2.
+#ifndef NDI_LUT_PER_POINT
+#define NDI_LUT_PER_POINT 8                      // buckets per grid point (rounded up to a power of two)
+#endif
 constexpr size_t kFullStageBytes = 48 * 1024;    // stage the whole grid up to this size
 constexpr size_t kCoarseBytes = 16 * 1024;       // target size of a coarse table
 
@@ -205,7 +208,7 @@ static ndi_status build_aids(ndi_dtype dtype, const void* grid, int64_t n, cudaS
     CK(cudaMemcpyAsync(ends + 8, (const unsigned char*)grid + (size_t)(n - 1) * elem, elem, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     int nb = 16;
-    while (nb < 4 * n && nb < (1 << 24)) nb <<= 1;
+    while (nb < (int64_t)NDI_LUT_PER_POINT * n && nb < (1 << 24)) nb <<= 1;
     double g0d, scale;
     if (dtype == NDI_F32) {
         float a, b; memcpy(&a, ends, 4); memcpy(&b, ends + 8, 4);
@@ -219,7 +222,7 @@ static ndi_status build_aids(ndi_dtype dtype, const void* grid, int64_t n, cudaS
         g0d = a; scale = (double)nb / ((double)b - (double)a);
     }
     if (scale > 0 && scale < 1e300 && scale == scale) {
-        CK(cudaMalloc(&aids->lut, (size_t)nb * sizeof(int) * 2));
+        CK(cudaMalloc(&aids->lut, (size_t)nb * lut_entry_bytes(elem)));
         ndi_status s2 = dispatch(dtype, [&](auto tag) -> ndi_status {
             using T = decltype(tag);
             CK(launch_build_lut<T>((const T*)grid, n, g0d, scale, nb, aids->lut, st));

@@ -65,7 +65,7 @@ __device__ __forceinline__ GridView<T> make_grid_view(const T* grid, int n, cons
     GridView<T> g;
     g.fine = grid; g.top = grid; g.n = n; g.top_step = sc.top_step; g.shift = 0;
     g.mode = sc.lut ? SEARCH_LUT : (sc.guess ? SEARCH_GUESS : SEARCH_BISECT);
-    g.lut = static_cast<const int2*>(sc.lut); g.nb = sc.lut_n; g.g0d = sc.g0d; g.scale = sc.scale;
+    g.lut = sc.lut; g.nb = sc.lut_n; g.g0d = sc.g0d; g.scale = sc.scale;
     if (sc.smem) {
         g.top = stage_grid<T>(reinterpret_cast<T*>(smem), static_cast<const T*>(sc.stage_src), sc.stage_n, bar);
         g.shift = sc.coarse_shift;
@@ -75,24 +75,26 @@ __device__ __forceinline__ GridView<T> make_grid_view(const T* grid, int n, cons
 }
 
 // thin rows: tiles searched in lock step by one warp (TPW) and rounds whose gathers are issued
-// together (RB).  Tunable at build time for measurement.
+// together (RB).  Tunable at build time for measurement.  Measured on B200 (profiles/r01): with the
+// bucket-table search the chains are short, and TPW = RB = 1 wins on every thin workload because
+// the registers saved buy occupancy (C3 0.37 vs 0.41 ms at TPW 2 / RB 4, C5a 3.7 vs 5.2 ms).
 #ifndef NDI_TPW_LINEAR
-#define NDI_TPW_LINEAR 2
+#define NDI_TPW_LINEAR 1
 #endif
 #ifndef NDI_TPW_CUBIC
-#define NDI_TPW_CUBIC 2
+#define NDI_TPW_CUBIC 1
 #endif
 #ifndef NDI_TPW_BILINEAR
-#define NDI_TPW_BILINEAR 2
+#define NDI_TPW_BILINEAR 1
 #endif
 #ifndef NDI_RB_LINEAR
-#define NDI_RB_LINEAR 4
+#define NDI_RB_LINEAR 1
 #endif
 #ifndef NDI_RB_CUBIC
-#define NDI_RB_CUBIC 2
+#define NDI_RB_CUBIC 1
 #endif
 #ifndef NDI_RB_BILINEAR
-#define NDI_RB_BILINEAR 2
+#define NDI_RB_BILINEAR 1
 #endif
 constexpr int kTilesLinear = NDI_TPW_LINEAR, kTilesCubic = NDI_TPW_CUBIC, kTilesBilinear = NDI_TPW_BILINEAR;
 

@@ -151,7 +151,8 @@ cudaError_t launch_grid_classify(const T* x, int64_t n, int32_t* result_dev, uin
 // count(b) is a lower bound found by bisection.  One thread per bucket.
 template <class T>
 __global__ void __launch_bounds__(256) build_lut_kernel(const T* __restrict__ x, int n, double g0d, double scale, int nb,
-                                                        int2* __restrict__ lut) {
+                                                        typename LutEntry<T>::type* __restrict__ lut) {
+    typedef typename LutEntry<T>::type Entry;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     auto count_below = [&](int bb) {
@@ -162,12 +163,25 @@ __global__ void __launch_bounds__(256) build_lut_kernel(const T* __restrict__ x,
         }
         return lo;
     };
-    lut[b] = make_int2(count_below(b), count_below(b + 1));
+    const int c0 = count_below(b), c1 = count_below(b + 1);
+    if constexpr (sizeof(Entry) == 16) {
+        Entry e;
+        if (c0 == c1 && c0 >= 1 && c0 <= n - 1) {      // no grid point in this bucket: one interval for all of it
+            const T lo = x[c0 - 1], hi = x[c0];
+            e.x = c0 - 1; e.y = *reinterpret_cast<const int*>(&lo); e.z = *reinterpret_cast<const int*>(&hi); e.w = 0;
+        } else { e.x = -(c0 + 1); e.y = c1; e.z = 0; e.w = 0; }
+        lut[b] = e;
+    } else {
+        lut[b] = make_int2(c0, c1);
+    }
 }
+
+size_t lut_entry_bytes(size_t elem) { return elem == 4 ? 16 : 8; }
 
 template <class T>
 cudaError_t launch_build_lut(const T* x, int64_t n, double g0d, double scale, int nb, void* lut_dev, cudaStream_t st) {
-    build_lut_kernel<T><<<(nb + 255) / 256, 256, 0, st>>>(x, (int)n, g0d, scale, nb, static_cast<int2*>(lut_dev));
+    build_lut_kernel<T><<<(nb + 255) / 256, 256, 0, st>>>(x, (int)n, g0d, scale, nb,
+                                                        static_cast<typename LutEntry<T>::type*>(lut_dev));
     count_launch();
     return cudaGetLastError();
 }

@@ -15,7 +15,7 @@ struct SearchCfg {
     int coarse_shift;       // log2 of the stride of the staged table (0: it is the whole grid)
     int stage_n;
     const void* stage_src;  // the grid itself, or the handle's coarse table grid[0], grid[S], grid[2S], ...
-    const void* lut;        // non-null: bucket-table search (int2 per bucket, see ndi_device.cuh)
+    const void* lut;        // non-null: bucket-table search (LutEntry per bucket, see ndi_device.cuh)
     int lut_n;              // number of buckets
     double g0d, scale;      // bucket(x) = (x - g0d) * scale
 };
@@ -66,7 +66,8 @@ template <class T>
 cudaError_t launch_grid_classify(const T* x, int64_t n, int32_t* result_dev, uint32_t* scratch_dev,
                                  cudaStream_t st);
 size_t grid_classify_scratch_words();
-// bucket table of a strictly rising grid: lut[b] = (#points in buckets < b, #points in buckets <= b)
+// bucket table of a strictly rising grid (entry format: LutEntry in ndi_device.cuh)
+size_t lut_entry_bytes(size_t elem);
 template <class T>
 cudaError_t launch_build_lut(const T* x, int64_t n, double g0d, double scale, int nb, void* lut_dev, cudaStream_t st);
 

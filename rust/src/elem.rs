@@ -1,0 +1,19 @@
+//! Element types the device path is instantiated for.
+use std::fmt::Debug;
+
+use num_traits::{Num, NumCast};
+
+/// f32, f64 and i32 -- the types the reference's tests exercise.
+pub trait NdiElem: Num + NumCast + PartialOrd + Copy + Debug + Send + 'static {
+    /// `ndi_dtype` code of `include/ndi_b200.h`
+    const DTYPE: i32;
+}
+impl NdiElem for f32 {
+    const DTYPE: i32 = crate::ffi::NDI_F32;
+}
+impl NdiElem for f64 {
+    const DTYPE: i32 = crate::ffi::NDI_F64;
+}
+impl NdiElem for i32 {
+    const DTYPE: i32 = crate::ffi::NDI_I32;
+}
