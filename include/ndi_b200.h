@@ -189,6 +189,12 @@ ndi_status ndi_interp2d_set_search_mode(ndi_interp2d* h, int32_t search_mode);
 ndi_status ndi_interp2d_device_ptrs(const ndi_interp2d* h, const void** x_dev, const void** y_dev,
                                     const void** data_dev);
 ndi_status ndi_interp2d_clone_to_device(const ndi_interp2d* h, int32_t device, ndi_interp2d** out);
+/* Locality binning of query batches: the batch loop of interp2d/mod.rs:255-307 is order-independent,
+ * so a launch may group the queries by table band before evaluating them (csrc/ndi_bin.cu); results
+ * and error reporting are unchanged.  AUTO bins when the table exceeds L2 and the batch is large.
+ * band_rows > 0 fixes the band height in grid intervals (0: sized from L2). */
+enum { NDI_BIN_AUTO = 0, NDI_BIN_OFF = 1, NDI_BIN_ON = 2 };
+ndi_status ndi_interp2d_set_binning(ndi_interp2d* h, int32_t mode, int32_t band_rows);
 
 /* Bilinear::interp_into over a query batch (bilinear.rs:64-99 x interp2d/mod.rs:215-307).
  * *bad_axis: 0 = x failed, 1 = y failed (x is checked first, bilinear.rs:71-80). */
@@ -197,6 +203,15 @@ ndi_status ndi_interp2d_bilinear(const ndi_interp2d* h, const void* qx, const vo
 /* error word = 2 * query_index + axis */
 ndi_status ndi_interp2d_bilinear_dev(const ndi_interp2d* h, const void* qx_dev, const void* qy_dev, int64_t nq,
                                      int32_t extrapolate, void* out_dev, uint64_t* err_word_dev, void* stream);
+
+/* ---- self-test ------------------------------------------------------------------------------ */
+/* The Linear / Bilinear kernels form the reciprocal of a query's divisor once and finish every
+ * quotient with two fused multiply-adds (csrc/ndi_device.cuh: rcp_refined, div_by) instead of a full
+ * IEEE division per element (linear.rs:32).  This entry point counts the operand pairs for which that
+ * differs from the correctly rounded quotient: a = 1.m_a * 2^a_exp for m_a in [a_mant_begin,
+ * a_mant_begin + a_mant_count), b = 1.m_b * 2^b_exp for every 23-bit m_b.  Must report 0. */
+ndi_status ndi_selftest_fdiv(uint32_t a_mant_begin, uint32_t a_mant_count, int32_t a_exp, int32_t b_exp,
+                             uint64_t* mismatches);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,7 @@ F32, F64, I32 = 0, 1, 2
 ASSUME_VALID, DEVICE_POINTERS, BORROW = 1, 2, 4
 SEARCH_AUTO, SEARCH_BINARY_GLOBAL, SEARCH_BINARY_SMEM, SEARCH_UNIFORM_GUESS, SEARCH_BUCKET_LUT = 0, 1, 2, 3, 4
 EXTRAP_NO, EXTRAP_YES, EXTRAP_PERIODIC = 0, 1, 2
+BIN_AUTO, BIN_OFF, BIN_ON = 0, 1, 2
 ERR_WORD_NONE = 2 ** 64 - 1
 
 DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32}
@@ -56,6 +57,8 @@ SIGNATURES = {
     "ndi_interp2d_set_search_mode": (_i32, [_vp, _i32]),
     "ndi_interp2d_device_ptrs": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "ndi_interp2d_clone_to_device": (_i32, [_vp, _i32, C.POINTER(_vp)]),
+    "ndi_selftest_fdiv": (_i32, [_u32, _u32, _i32, _i32, C.POINTER(_u64)]),
+    "ndi_interp2d_set_binning": (_i32, [_vp, _i32, _i32]),
     "ndi_interp2d_bilinear": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _pi64, _pi32]),
     "ndi_interp2d_bilinear_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
 }

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -56,10 +57,18 @@ const DeviceInfo& device_info() {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(dev);
     if (it != cache.end()) return it->second;
-    DeviceInfo di{dev, 148, 48 * 1024};
+    DeviceInfo di{dev, 148, 48 * 1024, (size_t)126 << 20};
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) di.sm_count = v;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && v > 0) di.smem_optin = (size_t)v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev) == cudaSuccess && v > 0) di.l2_bytes = (size_t)v;
+    // per-launch scratch (query binning) comes from the stream-ordered pool; keep freed blocks cached
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     return cache.emplace(dev, di).first->second;
 }
 
@@ -245,6 +254,7 @@ struct ndi_interp1d {
     void* x; void* data; void* a; void* b;
     bool owns_tables, owns_coeffs;
     int uniform_hint; int search_mode;
+    int fast_tables = 0;             // f32: every data value is 0 or in [2^-56, 2^30] (hoisted-reciprocal division allowed)
     GridAids aids;
     GridMeta meta() const { return aids.meta(x, n, dtype == NDI_F64 ? (size_t)8 : (size_t)4, uniform_hint); }
 };
@@ -253,6 +263,8 @@ struct ndi_interp2d {
     void* x; void* y; void* data;
     bool owns_tables;
     int hint_x, hint_y; int search_mode;
+    int bin_mode = NDI_BIN_AUTO; int band_rows = 0;   // locality binning of query batches (ndi_bin.cu)
+    int fast_tables = 0;
     GridAids aids_x, aids_y;
     GridMeta meta_x() const { return aids_x.meta(x, n, dtype == NDI_F64 ? (size_t)8 : (size_t)4, hint_x); }
     GridMeta meta_y() const { return aids_y.meta(y, m, dtype == NDI_F64 ? (size_t)8 : (size_t)4, hint_y); }
@@ -281,7 +293,36 @@ static ndi_status classify_grid(ndi_dtype dtype, const void* x_dev, int64_t n, W
     return NDI_OK;
 }
 
+// one pass over an f32 table: may the kernels use the hoisted-reciprocal division? (ndi_device.cuh)
+static ndi_status scan_fast_tables(ndi_dtype dtype, const void* data_dev, size_t count, Workspace* ws, int* fast) {
+    *fast = 0;
+    static const bool disabled = getenv("NDI_NO_FAST_DIV") != nullptr;
+    if (dtype != NDI_F32 || disabled) return NDI_OK;
+    const int32_t one = 1;
+    CK(cudaMemcpyAsync(ws->d_res, &one, sizeof(one), cudaMemcpyHostToDevice, ws->s[0]));
+    CK(launch_table_fast_div((const float*)data_dev, count, ws->d_res, ws->s[0]));
+    CK(cudaMemcpyAsync(ws->h_pin, ws->d_res, sizeof(int32_t), cudaMemcpyDeviceToHost, ws->s[0]));
+    CK(cudaStreamSynchronize(ws->s[0]));
+    int32_t v; memcpy(&v, ws->h_pin, sizeof(v));
+    *fast = v;
+    return NDI_OK;
+}
+
 extern "C" {
+
+ndi_status ndi_selftest_fdiv(uint32_t a_mant_begin, uint32_t a_mant_count, int32_t a_exp, int32_t b_exp, uint64_t* mismatches) {
+    if (!mismatches || a_exp < -126 || a_exp > 127 || b_exp < -126 || b_exp > 127 ||
+        (uint64_t)a_mant_begin + a_mant_count > (1u << 23))
+        return fail(NDI_INVALID_ARGUMENT, "bad mantissa or exponent range");
+    int dev = 0; CK(cudaGetDevice(&dev));
+    ndi_status st; Workspace* ws = workspace(dev, &st); if (!ws) return st;
+    CK(cudaMemsetAsync(ws->d_err, 0, sizeof(uint64_t), ws->s[0]));
+    CK(launch_selftest_fdiv(a_mant_begin, a_mant_count, a_exp, b_exp, ws->d_err, ws->s[0]));
+    CK(cudaMemcpyAsync(ws->h_pin, ws->d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws->s[0]));
+    CK(cudaStreamSynchronize(ws->s[0]));
+    memcpy(mismatches, ws->h_pin, sizeof(uint64_t));
+    return NDI_OK;
+}
 
 const char* ndi_version_string(void) { return "ndarray-interp-b200 0.1 (sm_100a)"; }
 const char* ndi_last_error_message(void) { return g_err; }
@@ -400,6 +441,7 @@ ndi_status ndi_interp1d_create(ndi_dtype dtype, const void* x, int64_t n, const 
         st = build_aids(dtype, h->x, n, ws->s[0], &h->aids);
         if (st != NDI_OK) { ndi_interp1d_destroy(h); return st; }
     }
+    if ((st = scan_fast_tables(dtype, h->data, (size_t)n * (size_t)w, ws, &h->fast_tables)) != NDI_OK) { ndi_interp1d_destroy(h); return st; }
     *out = h;
     return NDI_OK;
 }
@@ -552,7 +594,7 @@ ndi_status ndi_interp1d_linear_dev(const ndi_interp1d* h, const void* q_dev, int
         using T = decltype(tag);
         SearchCfg sc = make_search(h->meta(), h->search_mode, nq, 0);
         CK(launch_interp1d_linear<T>((const T*)h->x, h->n, sc, (const T*)h->data, h->w, (const T*)q_dev, nq, extrapolate != 0,
-                                     (T*)out_dev, (unsigned long long*)err_word_dev, s));
+                                     (T*)out_dev, (unsigned long long*)err_word_dev, h->fast_tables, s));
         return NDI_OK;
     });
 }
@@ -568,7 +610,7 @@ ndi_status ndi_interp1d_linear(const ndi_interp1d* h, const void* q, int64_t nq,
         SearchCfg sc = make_search(h->meta(), h->search_mode, nq, 0);
         return run_host_eval(he,
             [&](const void* q0, const void*, int64_t cnt, void* o, unsigned long long* err, cudaStream_t s) -> ndi_status {
-                CK(launch_interp1d_linear<T>((const T*)h->x, h->n, sc, (const T*)h->data, h->w, (const T*)q0, cnt, extrapolate != 0, (T*)o, err, s));
+                CK(launch_interp1d_linear<T>((const T*)h->x, h->n, sc, (const T*)h->data, h->w, (const T*)q0, cnt, extrapolate != 0, (T*)o, err, h->fast_tables, s));
                 return NDI_OK;
             },
             [&](const void* q0, const void*, int64_t cnt, unsigned long long* err, cudaStream_t s) -> ndi_status {
@@ -750,6 +792,7 @@ ndi_status ndi_interp2d_create(ndi_dtype dtype, const void* x, int64_t n, const 
     h->hint_y = ry[0] == NDI_MONO_RISING_STRICT ? ry[1] : 0;
     if (!h->hint_x) st = build_aids(dtype, h->x, n, ws->s[0], &h->aids_x);
     if (st == NDI_OK && !h->hint_y) st = build_aids(dtype, h->y, m, ws->s[0], &h->aids_y);
+    if (st == NDI_OK) st = scan_fast_tables(dtype, h->data, (size_t)n * (size_t)m * (size_t)w, ws, &h->fast_tables);
     if (st != NDI_OK) { ndi_interp2d_destroy(h); return st; }
     *out = h;
     return NDI_OK;
@@ -813,6 +856,69 @@ static void search2(const ndi_interp2d* h, size_t es, int64_t nq, SearchCfg* sx,
     *sy = make_search(h->meta_y(), h->search_mode, nq, sx->smem ? (size_t)sx->stage_n * es + 16 : 0);
 }
 
+ndi_status ndi_interp2d_set_binning(ndi_interp2d* h, int32_t mode, int32_t band_rows) {
+    if (!h || mode < NDI_BIN_AUTO || mode > NDI_BIN_ON || band_rows < 0) return fail(NDI_INVALID_ARGUMENT, "bad binning mode");
+    h->bin_mode = mode; h->band_rows = band_rows;
+    return NDI_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+long env_long(const char* name, long dflt) {
+    const char* v = getenv(name);
+    return v && *v ? strtol(v, nullptr, 10) : dflt;
+}
+
+// Is grouping the queries by table band (ndi_bin.cu) worth its extra passes?  Estimated DRAM bytes
+// of the direct kernel (four gathers per query, each at least one 32-byte sector, missing L2 in
+// proportion to the part of the table that cannot stay resident) against the binned path (table
+// once + 28 B (f32) of extra query traffic per query).
+bool want_binning(const ndi_interp2d* h, int64_t nq, size_t es, BandPlan* bp) {
+    static const long env_mode = env_long("NDI_BIN_MODE", -1), env_band_mb = env_long("NDI_BAND_MB", 32);
+    const int mode = env_mode >= 0 ? (int)env_mode : h->bin_mode;
+    if (mode == NDI_BIN_OFF || nq < 2 || nq > 0xffffffffll) return false;
+    const double table = (double)h->n * (double)h->m * (double)h->w * (double)es;
+    *bp = plan_bands(h->n, h->m, h->w, es, (size_t)env_band_mb << 20, h->band_rows);
+    if (bp->nbands < 2) return false;
+    if (mode == NDI_BIN_ON) return true;
+    const double resident = 0.4 * (double)device_info().l2_bytes;   // what random gathers keep of L2 (two partitions, output stream)
+    if (table <= resident || nq < (1 << 18)) return false;
+    const double seg = (double)(h->w * es < 32 ? 32 : h->w * es);
+    const double direct = (double)nq * 4.0 * seg * (1.0 - resident / table);
+    const double binned = table + (double)nq * (double)(es + 2 * (4 + 2 * es));
+    return direct > 1.5 * binned;
+}
+
+// one bilinear evaluation of a device-resident batch: direct, or binned by table band
+template <class T>
+ndi_status bilinear_on_device(const ndi_interp2d* h, const SearchCfg& sx, const SearchCfg& sy, const T* qx, const T* qy,
+                              int64_t nq, int extrapolate, T* out, unsigned long long* err, cudaStream_t s) {
+    BandPlan bp;
+    if (!want_binning(h, nq, sizeof(T), &bp)) {
+        CK(launch_interp2d_bilinear<T>((const T*)h->x, h->n, sx, (const T*)h->y, h->m, sy, (const T*)h->data, h->w, qx, qy, nq,
+                                       extrapolate, out, err, nullptr, h->fast_tables, s));
+        return NDI_OK;
+    }
+    void* scratch = nullptr;
+    CK(cudaMallocAsync(&scratch, bin_scratch_bytes(nq, sizeof(T)), s));
+    // the scatter kernel keeps its chunk in static shared memory: leave room when staging the grid
+    const SearchCfg sbin = make_search(h->meta_x(), h->search_mode, nq, 48 * 1024);
+    const unsigned* perm = nullptr; const T *bx = nullptr, *by = nullptr;
+    cudaError_t e = launch_bin_queries<T>((const T*)h->x, h->n, sbin, qx, qy, nq, bp, scratch, &perm, &bx, &by, s);
+    if (e == cudaSuccess)
+        e = launch_interp2d_bilinear<T>((const T*)h->x, h->n, sx, (const T*)h->y, h->m, sy, (const T*)h->data, h->w, bx, by, nq,
+                                        extrapolate, out, err, perm, h->fast_tables, s);
+    cudaFreeAsync(scratch, s);
+    if (e != cudaSuccess) return cuda_fail(e, "binned bilinear launch");
+    return NDI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 ndi_status ndi_interp2d_bilinear_dev(const ndi_interp2d* h, const void* qx_dev, const void* qy_dev, int64_t nq,
                                      int32_t extrapolate, void* out_dev, uint64_t* err_word_dev, void* stream) {
     ndi_status st = check_eval_args(h, qx_dev, nq, out_dev); if (st != NDI_OK) return st;
@@ -822,10 +928,8 @@ ndi_status ndi_interp2d_bilinear_dev(const ndi_interp2d* h, const void* qx_dev, 
     return dispatch(h->dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
         SearchCfg sx, sy; search2(h, sizeof(T), nq, &sx, &sy);
-        CK(launch_interp2d_bilinear<T>((const T*)h->x, h->n, sx, (const T*)h->y, h->m, sy, (const T*)h->data, h->w,
-                                       (const T*)qx_dev, (const T*)qy_dev, nq, extrapolate != 0, (T*)out_dev,
-                                       (unsigned long long*)err_word_dev, s));
-        return NDI_OK;
+        return bilinear_on_device<T>(h, sx, sy, (const T*)qx_dev, (const T*)qy_dev, nq, extrapolate != 0, (T*)out_dev,
+                                     (unsigned long long*)err_word_dev, s);
     });
 }
 
@@ -842,9 +946,7 @@ ndi_status ndi_interp2d_bilinear(const ndi_interp2d* h, const void* qx, const vo
         SearchCfg sx, sy; search2(h, sizeof(T), nq, &sx, &sy);
         return run_host_eval(he,
             [&](const void* q0, const void* q1, int64_t cnt, void* o, unsigned long long* err, cudaStream_t s) -> ndi_status {
-                CK(launch_interp2d_bilinear<T>((const T*)h->x, h->n, sx, (const T*)h->y, h->m, sy, (const T*)h->data, h->w,
-                                               (const T*)q0, (const T*)q1, cnt, extrapolate != 0, (T*)o, err, s));
-                return NDI_OK;
+                return bilinear_on_device<T>(h, sx, sy, (const T*)q0, (const T*)q1, cnt, extrapolate != 0, (T*)o, err, s);
             },
             [&](const void* q0, const void* q1, int64_t cnt, unsigned long long* err, cudaStream_t s) -> ndi_status {
                 CK(launch_validate_queries<T>((const T*)h->x, h->n, (const T*)h->y, h->m, (const T*)q0, (const T*)q1, cnt,

@@ -40,6 +40,7 @@ struct Eval1 {                       // 1-D kernels
     const T* q; long long nq; int mode;
     T* out; unsigned long long* err;
     long long ntasks; int nslices;
+    int fast_tables;                 // every table value is 0 or in [2^-56, 2^30]: hoisted-reciprocal division allowed
 };
 template <class T>
 struct Eval2 {                       // bilinear
@@ -49,30 +50,17 @@ struct Eval2 {                       // bilinear
     const T* qx; const T* qy; long long nq; int extrapolate;
     T* out; unsigned long long* err;
     long long ntasks; int nslices;
+    const unsigned* perm;            // binned batch (ndi_bin.cu): output row of query i is perm[i]
+    int fast_tables;
 };
+
+// first-error report for a binned batch: lanes are not in query order, every failing lane reports
+__device__ __forceinline__ void report_bad_unordered(unsigned long long* err, bool bad, unsigned long long word) {
+    if (bad && err != nullptr) atomicMin(err, word);
+}
 
 __device__ __forceinline__ bool shfl_b(bool v, int src) { return __shfl_sync(0xffffffffu, (int)v, src) != 0; }
 template <class T> __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
-__host__ __device__ inline size_t stage_bytes(const SearchCfg& sc, size_t elem) {
-    return sc.smem ? (((size_t)sc.stage_n * elem + 15) & ~(size_t)15) : 0;
-}
-
-// grid view for the search: stages the grid (or its coarse table) into shared memory when asked
-template <class T>
-__device__ __forceinline__ GridView<T> make_grid_view(const T* grid, int n, const SearchCfg& sc, unsigned char* smem,
-                                                      uint64_t* bar) {
-    GridView<T> g;
-    g.fine = grid; g.top = grid; g.n = n; g.top_step = sc.top_step; g.shift = 0;
-    g.mode = sc.lut ? SEARCH_LUT : (sc.guess ? SEARCH_GUESS : SEARCH_BISECT);
-    g.lut = sc.lut; g.nb = sc.lut_n; g.g0d = sc.g0d; g.scale = sc.scale;
-    if (sc.smem) {
-        g.top = stage_grid<T>(reinterpret_cast<T*>(smem), static_cast<const T*>(sc.stage_src), sc.stage_n, bar);
-        g.shift = sc.coarse_shift;
-    }
-    g.g0 = g.at(0); g.gl = g.at(n - 1);
-    return g;
-}
 
 // thin rows: tiles searched in lock step by one warp (TPW) and rounds whose gathers are issued
 // together (RB).  Tunable at build time for measurement.  Measured on B200 (profiles/r01): with the
@@ -113,7 +101,7 @@ __global__ void __launch_bounds__(kBlock) interp1d_linear_kernel(const Eval1<T> 
         if constexpr (LPQ < 32) {
             constexpr int TPW = kTilesLinear, QPR = 32 / LPQ, RB = LPQ < NDI_RB_LINEAR ? LPQ : NDI_RB_LINEAR;
             const long long qbase0 = task * (32 * TPW);
-            T x[TPW]; int idx[TPW]; T dx21[TPW], dxq[TPW]; bool skip[TPW];
+            T x[TPW]; int idx[TPW]; T dx21[TPW], dxq[TPW]; bool skip[TPW]; Slope<T> slope[TPW];   // dx21/dxq: x1, x2 from the search
 #pragma unroll
             for (int t = 0; t < TPW; ++t) {
                 const long long qi = qbase0 + t * 32 + lane;
@@ -128,7 +116,8 @@ __global__ void __launch_bounds__(kBlock) interp1d_linear_kernel(const Eval1<T> 
                 // with extrapolation only NaN fails (vector_extensions.rs:83-84)
                 const bool bad = live && (p.mode ? Ar<T>::is_nan(x[t]) : !in_range(g0, gl, x[t]));
                 const T x1 = dx21[t], x2 = dxq[t];
-                dx21[t] = Ar<T>::sub(x2, x1); dxq[t] = Ar<T>::sub(x[t], x1);
+                dxq[t] = Ar<T>::sub(x[t], x1);
+                slope[t] = Slope<T>::make(Ar<T>::sub(x2, x1), dxq[t], p.fast_tables != 0);
                 if (qbase0 + t * 32 < p.nq) report_first_bad(p.err, bad, (unsigned long long)qi);
                 skip[t] = bad || !live;
             }
@@ -141,12 +130,12 @@ __global__ void __launch_bounds__(kBlock) interp1d_linear_kernel(const Eval1<T> 
                 if (qbase >= p.nq) break;
 #pragma unroll
                 for (int r0 = 0; r0 < LPQ; r0 += RB) {
-                    Vec<T, V> y1[RB], y2[RB]; bool ok[RB]; T d21[RB], dq[RB];
+                    Vec<T, V> y1[RB], y2[RB]; bool ok[RB]; Slope<T> sl[RB]; T dq[RB];
 #pragma unroll
                     for (int j = 0; j < RB; ++j) {                                     // issue all gathers of the batch
                         const int src = (r0 + j) * QPR + qsel;
                         const int is = __shfl_sync(0xffffffffu, idx[t], src);
-                        d21[j] = shfl_t(dx21[t], src); dq[j] = shfl_t(dxq[t], src);
+                        sl[j] = slope[t].from_lane(src); dq[j] = shfl_t(dxq[t], src);
                         ok[j] = !shfl_b(skip[t], src) && colok;
                         if (ok[j]) {
                             const T* row = p.data + (long long)is * p.w + col;
@@ -158,9 +147,7 @@ __global__ void __launch_bounds__(kBlock) interp1d_linear_kernel(const Eval1<T> 
                     for (int j = 0; j < RB; ++j) {
                         if (ok[j]) {
                             const int src = (r0 + j) * QPR + qsel;
-                            Vec<T, V> res;
-#pragma unroll
-                            for (int e = 0; e < V; ++e) res.v[e] = calc_frac_pre<T>(y1[j].v[e], y2[j].v[e], d21[j], dq[j]);  // linear.rs:94-96
+                            const Vec<T, V> res = lerp_vec<T, V>(y1[j], y2[j], sl[j], dq[j]);        // linear.rs:94-96
                             st_stream<T, V>(p.out + (qbase + src) * p.w + col, res);
                         }
                     }
@@ -177,7 +164,8 @@ __global__ void __launch_bounds__(kBlock) interp1d_linear_kernel(const Eval1<T> 
             search_multi<T, 1>(g, x, idx, xl, xr);
             const bool bad = live && (p.mode ? Ar<T>::is_nan(x[0]) : !in_range(g0, gl, x[0]));
             const T x1 = xl[0], x2 = xr[0];
-            const T dx21 = Ar<T>::sub(x2, x1), dxq = Ar<T>::sub(x[0], x1);
+            const T dxq = Ar<T>::sub(x[0], x1);
+            const Slope<T> slope = Slope<T>::make(Ar<T>::sub(x2, x1), dxq, p.fast_tables != 0);
             if (slice == 0) report_first_bad(p.err, bad, (unsigned long long)qi);
             const bool skip = bad || !live;
             const long long col = ((long long)slice * 32 + lane) * V;
@@ -187,7 +175,8 @@ __global__ void __launch_bounds__(kBlock) interp1d_linear_kernel(const Eval1<T> 
             const int nlive = (int)min((long long)32, p.nq - qbase);
             for (int s = 0; s < nlive; ++s) {
                 const int is = __shfl_sync(0xffffffffu, idx[0], s);
-                const T d21 = shfl_t(dx21, s), dq = shfl_t(dxq, s);
+                const Slope<T> sl = slope.from_lane(s);
+                const T dq = shfl_t(dxq, s);
                 const bool sk = shfl_b(skip, s);
                 if (sk || !colok) continue;
                 if (is != cur) {
@@ -196,9 +185,7 @@ __global__ void __launch_bounds__(kBlock) interp1d_linear_kernel(const Eval1<T> 
                     y2 = ld_table<T, V>(row + p.w);
                     cur = is;
                 }
-                Vec<T, V> res;
-#pragma unroll
-                for (int e = 0; e < V; ++e) res.v[e] = calc_frac_pre<T>(y1.v[e], y2.v[e], d21, dq);
+                const Vec<T, V> res = lerp_vec<T, V>(y1, y2, sl, dq);
                 st_stream<T, V>(p.out + (qbase + s) * p.w + col, res);
             }
         }
@@ -346,14 +333,7 @@ __global__ void __launch_bounds__(kBlock) interp1d_cubic_kernel(const Eval1<T> p
 // ------------------------------------------------------------------------------------------------
 // K4: Bilinear::interp_into x batch (bilinear.rs:64-99)
 // ------------------------------------------------------------------------------------------------
-template <class T>
-__device__ __forceinline__ T bilinear_point(T z11, T z12, T z21, T z22, T d21x, T dqx, T d21y, T dqy) {
-    const T z1 = calc_frac_pre<T>(z11, z21, d21x, dqx);                               // bilinear.rs:94
-    const T z2 = calc_frac_pre<T>(z12, z22, d21x, dqx);                               // :95
-    return calc_frac_pre<T>(z1, z2, d21y, dqy);                                       // :96
-}
-
-template <class T, int V, int LPQ>
+template <class T, int V, int LPQ, bool PERM>
 __global__ void __launch_bounds__(kBlock) interp2d_bilinear_kernel(const Eval2<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar[2];
@@ -368,13 +348,16 @@ __global__ void __launch_bounds__(kBlock) interp2d_bilinear_kernel(const Eval2<T
             constexpr int TPW = kTilesBilinear, QPR = 32 / LPQ, RB = LPQ < NDI_RB_BILINEAR ? LPQ : NDI_RB_BILINEAR;
             const long long qbase0 = task * (32 * TPW);
             T x[TPW], y[TPW]; int ix[TPW], iy[TPW];
-            long long cell[TPW]; T ax[TPW], bx[TPW], ay[TPW], by[TPW]; bool skip[TPW];
+            long long cell[TPW]; T ax[TPW], bx[TPW], ay[TPW], by[TPW]; bool skip[TPW];   // ax..by: x1, x2, y1, y2 from the search
+            Slope<T> slx[TPW], sly[TPW];
+            unsigned orow[TPW];                                                        // output row (PERM only)
 #pragma unroll
             for (int t = 0; t < TPW; ++t) {
                 const long long qi = qbase0 + t * 32 + lane;
                 const bool live = qi < p.nq;
                 x[t] = live ? ld_query(p.qx + qi) : gx0;
                 y[t] = live ? ld_query(p.qy + qi) : gy0;
+                if constexpr (PERM) orow[t] = live ? __ldcs(p.perm + qi) : 0u;
             }
             search_multi<T, TPW>(gx, x, ix, ax, bx);                                  // bilinear.rs:82 (+ x1, x2)
             search_multi<T, TPW>(gy, y, iy, ay, by);
@@ -387,10 +370,12 @@ __global__ void __launch_bounds__(kBlock) interp2d_bilinear_kernel(const Eval2<T
                 else { badx = !in_range(gx0, gxl, x[t]); bady = !in_range(gy0, gyl, y[t]); }
                 const bool bad = live && (badx || bady);
                 const T x1 = ax[t], x2 = bx[t], y1 = ay[t], y2 = by[t];
-                ax[t] = Ar<T>::sub(x2, x1); bx[t] = Ar<T>::sub(x[t], x1);
-                ay[t] = Ar<T>::sub(y2, y1); by[t] = Ar<T>::sub(y[t], y1);
+                bx[t] = Ar<T>::sub(x[t], x1); by[t] = Ar<T>::sub(y[t], y1);
+                slx[t] = Slope<T>::make(Ar<T>::sub(x2, x1), bx[t], p.fast_tables != 0);
+                sly[t] = Slope<T>::make(Ar<T>::sub(y2, y1), by[t], p.fast_tables != 0);
                 cell[t] = ((long long)ix[t] * p.m + iy[t]) * p.w;                     // z11 (:83)
-                if (qbase0 + t * 32 < p.nq)
+                if constexpr (PERM) report_bad_unordered(p.err, bad, 2ull * orow[t] + (badx ? 0ull : 1ull));
+                else if (qbase0 + t * 32 < p.nq)
                     report_first_bad(p.err, bad, 2ull * (unsigned long long)qi + (badx ? 0ull : 1ull));
                 skip[t] = bad || !live;
             }
@@ -403,13 +388,16 @@ __global__ void __launch_bounds__(kBlock) interp2d_bilinear_kernel(const Eval2<T
                 if (qbase >= p.nq) break;
 #pragma unroll
                 for (int r0 = 0; r0 < LPQ; r0 += RB) {
-                    Vec<T, V> z11[RB], z12[RB], z21[RB], z22[RB]; bool ok[RB]; T sax[RB], sbx[RB], say[RB], sby[RB];
+                    Vec<T, V> z11[RB], z12[RB], z21[RB], z22[RB]; bool ok[RB]; Slope<T> ssx[RB], ssy[RB]; T sbx[RB], sby[RB];
+                    long long srow[RB];
 #pragma unroll
                     for (int j = 0; j < RB; ++j) {
                         const int src = (r0 + j) * QPR + qsel;
                         const long long cs = __shfl_sync(0xffffffffu, cell[t], src);
-                        sax[j] = shfl_t(ax[t], src); sbx[j] = shfl_t(bx[t], src);
-                        say[j] = shfl_t(ay[t], src); sby[j] = shfl_t(by[t], src);
+                        if constexpr (PERM) srow[j] = __shfl_sync(0xffffffffu, orow[t], src);
+                        else srow[j] = qbase + src;
+                        ssx[j] = slx[t].from_lane(src); sbx[j] = shfl_t(bx[t], src);
+                        ssy[j] = sly[t].from_lane(src); sby[j] = shfl_t(by[t], src);
                         ok[j] = !shfl_b(skip[t], src) && colok;
                         if (ok[j]) {
                             const T* c0 = p.data + cs + col;
@@ -422,12 +410,8 @@ __global__ void __launch_bounds__(kBlock) interp2d_bilinear_kernel(const Eval2<T
 #pragma unroll
                     for (int j = 0; j < RB; ++j) {
                         if (ok[j]) {
-                            const int src = (r0 + j) * QPR + qsel;
-                            Vec<T, V> res;
-#pragma unroll
-                            for (int e = 0; e < V; ++e)
-                                res.v[e] = bilinear_point<T>(z11[j].v[e], z12[j].v[e], z21[j].v[e], z22[j].v[e], sax[j], sbx[j], say[j], sby[j]);
-                            st_stream<T, V>(p.out + (qbase + src) * p.w + col, res);
+                            const Vec<T, V> res = bilerp_vec<T, V>(z11[j], z12[j], z21[j], z22[j], ssx[j], sbx[j], ssy[j], sby[j]);
+                            st_stream<T, V>(p.out + srow[j] * p.w + col, res);
                         }
                     }
                 }
@@ -448,10 +432,15 @@ __global__ void __launch_bounds__(kBlock) interp2d_bilinear_kernel(const Eval2<T
             search_multi<T, 1>(gx, x, ix, x1s, x2s);
             search_multi<T, 1>(gy, y, iy, y1s, y2s);
             const T x1 = x1s[0], x2 = x2s[0], y1 = y1s[0], y2 = y2s[0];
-            const T dx21 = Ar<T>::sub(x2, x1), dxq = Ar<T>::sub(x[0], x1);
-            const T dy21 = Ar<T>::sub(y2, y1), dyq = Ar<T>::sub(y[0], y1);
+            const T dxq = Ar<T>::sub(x[0], x1), dyq = Ar<T>::sub(y[0], y1);
+            const Slope<T> slx = Slope<T>::make(Ar<T>::sub(x2, x1), dxq, p.fast_tables != 0);
+            const Slope<T> sly = Slope<T>::make(Ar<T>::sub(y2, y1), dyq, p.fast_tables != 0);
             const long long cell = ((long long)ix[0] * p.m + iy[0]) * p.w;
-            if (slice == 0) report_first_bad(p.err, bad, 2ull * (unsigned long long)qi + (badx ? 0ull : 1ull));
+            unsigned orow = 0;
+            if constexpr (PERM) {
+                orow = live ? __ldcs(p.perm + qi) : 0u;
+                if (slice == 0) report_bad_unordered(p.err, bad, 2ull * orow + (badx ? 0ull : 1ull));
+            } else if (slice == 0) report_first_bad(p.err, bad, 2ull * (unsigned long long)qi + (badx ? 0ull : 1ull));
             const bool skip = bad || !live;
             const long long col = ((long long)slice * 32 + lane) * V;
             const bool colok = col < p.w;
@@ -460,8 +449,11 @@ __global__ void __launch_bounds__(kBlock) interp2d_bilinear_kernel(const Eval2<T
             const int nlive = (int)min((long long)32, p.nq - qbase);
             for (int s = 0; s < nlive; ++s) {
                 const long long cs = __shfl_sync(0xffffffffu, cell, s);
-                const T ax = shfl_t(dx21, s), bx = shfl_t(dxq, s), ay = shfl_t(dy21, s), by = shfl_t(dyq, s);
+                const Slope<T> ssx = slx.from_lane(s), ssy = sly.from_lane(s);
+                const T bx = shfl_t(dxq, s), by = shfl_t(dyq, s);
                 const bool sk = shfl_b(skip, s);
+                long long srow = qbase + s;
+                if constexpr (PERM) srow = __shfl_sync(0xffffffffu, orow, s);
                 if (sk || !colok) continue;
                 if (cs != cur) {
                     const T* c0 = p.data + cs + col;
@@ -471,10 +463,8 @@ __global__ void __launch_bounds__(kBlock) interp2d_bilinear_kernel(const Eval2<T
                     z22 = ld_table<T, V>(c0 + rowx + p.w);
                     cur = cs;
                 }
-                Vec<T, V> res;
-#pragma unroll
-                for (int e = 0; e < V; ++e) res.v[e] = bilinear_point<T>(z11.v[e], z12.v[e], z21.v[e], z22.v[e], ax, bx, ay, by);
-                st_stream<T, V>(p.out + (qbase + s) * p.w + col, res);
+                const Vec<T, V> res = bilerp_vec<T, V>(z11, z12, z21, z22, ssx, bx, ssy, by);
+                st_stream<T, V>(p.out + srow * p.w + col, res);
             }
         }
     }
@@ -629,12 +619,16 @@ static cudaError_t launch_eval(K kernel, const P& p, size_t smem, cudaStream_t s
         NDI_LPQ_SWITCH(KERNEL, T, 1, SH.lpq, P, SMEM, ST)                                 \
     }
 
+template <class T, int V, int LPQ> constexpr auto bilinear_direct = interp2d_bilinear_kernel<T, V, LPQ, false>;
+template <class T, int V, int LPQ> constexpr auto bilinear_binned = interp2d_bilinear_kernel<T, V, LPQ, true>;
+
 template <class T>
 cudaError_t launch_interp1d_linear(const T* grid, int64_t n, SearchCfg sc, const T* data, int64_t w, const T* q,
-                                   int64_t nq, int extrapolate, T* out, unsigned long long* err, cudaStream_t st) {
+                                   int64_t nq, int extrapolate, T* out, unsigned long long* err, int fast_tables,
+                                   cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
     Shape sh = pick_shape(w, nq, pick_vec<T>(w, {data, out}), kTilesLinear);
-    Eval1<T> p{grid, (int)n, sc, data, nullptr, nullptr, (long long)w, q, (long long)nq, extrapolate, out, err, sh.ntasks, sh.nslices};
+    Eval1<T> p{grid, (int)n, sc, data, nullptr, nullptr, (long long)w, q, (long long)nq, extrapolate, out, err, sh.ntasks, sh.nslices, fast_tables};
     size_t smem = stage_bytes(sc, sizeof(T));
     NDI_VEC_SWITCH(interp1d_linear_kernel, T, sh, p, smem, st)
 }
@@ -645,7 +639,7 @@ cudaError_t launch_interp1d_cubic(const T* grid, int64_t n, SearchCfg sc, const 
                                   unsigned long long* err, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
     Shape sh = pick_shape(w, nq, pick_vec<T>(w, {data, a, b, out}), kTilesCubic);
-    Eval1<T> p{grid, (int)n, sc, data, a, b, (long long)w, q, (long long)nq, extrap_mode, out, err, sh.ntasks, sh.nslices};
+    Eval1<T> p{grid, (int)n, sc, data, a, b, (long long)w, q, (long long)nq, extrap_mode, out, err, sh.ntasks, sh.nslices, 0};
     size_t smem = stage_bytes(sc, sizeof(T));
     NDI_VEC_SWITCH(interp1d_cubic_kernel, T, sh, p, smem, st)
 }
@@ -653,12 +647,14 @@ cudaError_t launch_interp1d_cubic(const T* grid, int64_t n, SearchCfg sc, const 
 template <class T>
 cudaError_t launch_interp2d_bilinear(const T* gx, int64_t n, SearchCfg scx, const T* gy, int64_t m, SearchCfg scy,
                                      const T* data, int64_t w, const T* qx, const T* qy, int64_t nq, int extrapolate,
-                                     T* out, unsigned long long* err, cudaStream_t st) {
+                                     T* out, unsigned long long* err, const unsigned* perm, int fast_tables,
+                                     cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
     Shape sh = pick_shape(w, nq, pick_vec<T>(w, {data, out}), kTilesBilinear);
-    Eval2<T> p{gx, (int)n, scx, gy, (int)m, scy, data, (long long)w, qx, qy, (long long)nq, extrapolate, out, err, sh.ntasks, sh.nslices};
+    Eval2<T> p{gx, (int)n, scx, gy, (int)m, scy, data, (long long)w, qx, qy, (long long)nq, extrapolate, out, err, sh.ntasks, sh.nslices, perm, fast_tables};
     size_t smem = stage_bytes(scx, sizeof(T)) + stage_bytes(scy, sizeof(T));
-    NDI_VEC_SWITCH(interp2d_bilinear_kernel, T, sh, p, smem, st)
+    if (perm) { NDI_VEC_SWITCH(bilinear_binned, T, sh, p, smem, st) }
+    NDI_VEC_SWITCH(bilinear_direct, T, sh, p, smem, st)
 }
 
 template <class T>
@@ -690,10 +686,10 @@ cudaError_t launch_validate_queries(const T* gx, int64_t n, const T* gy, int64_t
 
 #define NDI_INST_COMMON(T)                                                                                             \
     template cudaError_t launch_interp1d_linear<T>(const T*, int64_t, SearchCfg, const T*, int64_t, const T*, int64_t, \
-                                                   int, T*, unsigned long long*, cudaStream_t);                        \
+                                                   int, T*, unsigned long long*, int, cudaStream_t);                   \
     template cudaError_t launch_interp2d_bilinear<T>(const T*, int64_t, SearchCfg, const T*, int64_t, SearchCfg,       \
                                                      const T*, int64_t, const T*, const T*, int64_t, int, T*,          \
-                                                     unsigned long long*, cudaStream_t);                               \
+                                                     unsigned long long*, const unsigned*, int, cudaStream_t);         \
     template cudaError_t launch_lower_index<T>(const T*, int64_t, SearchCfg, const T*, int64_t, int64_t*,              \
                                                unsigned long long*, cudaStream_t);                                     \
     template cudaError_t launch_validate_queries<T>(const T*, int64_t, const T*, int64_t, const T*, const T*, int64_t, \

@@ -193,4 +193,58 @@ template cudaError_t launch_grid_classify<float>(const float*, int64_t, int32_t*
 template cudaError_t launch_grid_classify<double>(const double*, int64_t, int32_t*, uint32_t*, cudaStream_t);
 template cudaError_t launch_grid_classify<int32_t>(const int32_t*, int64_t, int32_t*, uint32_t*, cudaStream_t);
 
+// ------------------------------------------------------------------------------------------------
+// May the evaluation kernels divide with a per-query reciprocal (ndi_device.cuh, div_by)?  Yes when
+// every table value is finite and either 0 or of magnitude in [2^-56, 2^30].  *flag must be 1 on entry.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) table_fast_div_kernel(const float* __restrict__ data, size_t count, int32_t* flag) {
+    bool ok = true;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const uint32_t u = __float_as_uint(__ldg(data + i)) & 0x7fffffffu;
+        // biased exponents: 2^-56 -> 71, 2^30 -> 157
+        ok = ok && (u == 0u || (u >= (71u << 23) && u <= (157u << 23)));
+    }
+    if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(flag, 0);
+}
+
+cudaError_t launch_table_fast_div(const float* data, size_t count, int32_t* flag_dev, cudaStream_t st) {
+    const size_t want = (count + 255) / 256;
+    const size_t cap = (size_t)device_info().sm_count * 16;
+    table_fast_div_kernel<<<(unsigned)(want < cap ? (want ? want : 1) : cap), 256, 0, st>>>(data, count, flag_dev);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// ndi_selftest_fdiv: div_by(a, b, rcp_refined(b)) against __fdiv_rn(a, b) for
+//   a = (1.m_a) * 2^a_exp with m_a in [a_mant_begin, a_mant_begin + a_mant_count), and
+//   b = (1.m_b) * 2^b_exp for ALL 2^23 mantissas m_b.
+// One block per 2^12 values of m_b; the reciprocal is formed once per b as in the kernels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) selftest_fdiv_kernel(uint32_t a_mant_begin, uint32_t a_mant_count, int a_exp, int b_exp,
+                                                           unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    const uint32_t a_hi = (uint32_t)(a_exp + 127) << 23, b_hi = (uint32_t)(b_exp + 127) << 23;
+    for (uint32_t k = 0; k < 16; ++k) {
+        const uint32_t mb = blockIdx.x * 4096u + k * 256u + threadIdx.x;
+        const float b = __uint_as_float(b_hi | mb);
+        const float r = rcp_refined(b);
+        for (uint32_t ma = a_mant_begin; ma < a_mant_begin + a_mant_count; ++ma) {
+            const float a = __uint_as_float(a_hi | ma);
+            bad += __float_as_uint(div_by(a, b, r)) != __float_as_uint(__fdiv_rn(a, b));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t launch_selftest_fdiv(uint32_t a_mant_begin, uint32_t a_mant_count, int a_exp, int b_exp,
+                                 unsigned long long* mismatches_dev, cudaStream_t st) {
+    selftest_fdiv_kernel<<<(1u << 23) / 4096u, 256, 0, st>>>(a_mant_begin, a_mant_count, a_exp, b_exp, mismatches_dev);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace ndi

@@ -31,6 +31,7 @@ struct DeviceInfo {
     int device;
     int sm_count;
     size_t smem_optin;   // max dynamic shared memory per block
+    size_t l2_bytes;
 };
 const DeviceInfo& device_info();          // of the current device
 void count_launch();                      // bumps ndi_kernel_launch_count()
@@ -50,7 +51,8 @@ cudaError_t launch_validate_queries(const T* g0_gl_x /* grid x */, int64_t n, co
 
 template <class T>
 cudaError_t launch_interp1d_linear(const T* grid, int64_t n, SearchCfg sc, const T* data, int64_t w, const T* q,
-                                   int64_t nq, int extrapolate, T* out, unsigned long long* err, cudaStream_t st);
+                                   int64_t nq, int extrapolate, T* out, unsigned long long* err, int fast_tables,
+                                   cudaStream_t st);
 template <class T>
 cudaError_t launch_interp1d_cubic(const T* grid, int64_t n, SearchCfg sc, const T* data, const T* a, const T* b,
                                   int64_t w, const T* q, int64_t nq, int extrap_mode, T* out,
@@ -58,7 +60,29 @@ cudaError_t launch_interp1d_cubic(const T* grid, int64_t n, SearchCfg sc, const 
 template <class T>
 cudaError_t launch_interp2d_bilinear(const T* gx, int64_t n, SearchCfg scx, const T* gy, int64_t m, SearchCfg scy,
                                      const T* data, int64_t w, const T* qx, const T* qy, int64_t nq, int extrapolate,
-                                     T* out, unsigned long long* err, cudaStream_t st);
+                                     T* out, unsigned long long* err, const unsigned* perm, int fast_tables,
+                                     cudaStream_t st);
+
+// ---- locality binning of 2-D query batches (ndi_bin.cu) --------------------------------------
+// The x-axis is cut into nbands bands of 2^band_shift intervals; launch_bin_queries groups the
+// queries by band.  perm != nullptr in launch_interp2d_bilinear: qx/qy are the binned copies and
+// the result of binned query i goes to output row perm[i].
+constexpr int kMaxBands = 256;
+struct BandPlan { int band_shift; int nbands; };
+// band_rows > 0 fixes the band height (tests); else bands of about band_bytes of table
+BandPlan plan_bands(int64_t n, int64_t m, int64_t w, size_t elem, size_t band_bytes, int band_rows);
+size_t bin_scratch_bytes(int64_t nq, size_t elem);
+template <class T>
+cudaError_t launch_bin_queries(const T* gx, int64_t n, SearchCfg scx, const T* qx, const T* qy, int64_t nq,
+                               BandPlan bp, void* scratch, const unsigned** perm, const T** bqx, const T** bqy,
+                               cudaStream_t st);
+
+// fast_tables (linear, bilinear; f32 only): 1 when launch_table_fast_div found every table value to
+// be 0 or in [2^-56, 2^30], which lets the kernels divide with a per-query reciprocal (ndi_device.cuh)
+cudaError_t launch_table_fast_div(const float* data, size_t count, int32_t* flag_dev, cudaStream_t st);
+// all-pairs check of div_by() against __fdiv_rn (ndi_selftest_fdiv)
+cudaError_t launch_selftest_fdiv(uint32_t a_mant_begin, uint32_t a_mant_count, int a_exp, int b_exp,
+                                 unsigned long long* mismatches_dev, cudaStream_t st);
 
 // ---- grid checks (ndi_grid.cu) -----------------------------------------------------------
 // result[0] = Monotonic enum, result[1] = 1 when the even-spacing guess hits on every cell

@@ -149,6 +149,10 @@ class DeviceInterp2D:
     def set_search_mode(self, mode):
         L.check(self.lib.ndi_interp2d_set_search_mode(self.h, int(mode)))
 
+    def set_binning(self, mode, band_rows=0):
+        """locality binning of query batches by table band: L.BIN_AUTO / BIN_OFF / BIN_ON"""
+        L.check(self.lib.ndi_interp2d_set_binning(self.h, int(mode), int(band_rows)))
+
     def bilinear(self, qx, qy, extrapolate=False, out=None, err=None, stream=None):
         assert qx.is_cuda and qy.is_cuda and qx.is_contiguous() and qy.is_contiguous() and qx.shape == qy.shape
         if out is None:

@@ -296,3 +296,145 @@ def test_bilinear_every_search_mode(mode):
     qx, qy = make_queries(rng, gx, 50000, np.float32, True), make_queries(rng, gy, 50000, np.float32, True)
     st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, True)
     assert same(interp.interp_array(qx, qy), ref)
+
+
+# ---- K8: query binning by table band (ndi_bin.cu) -----------------------------------------------------
+def _force_binning(interp, band_rows):
+    L.check(L.load().ndi_interp2d_set_binning(interp._handle(), L.BIN_ON, band_rows))
+
+
+@pytest.mark.parametrize("dt", DTS, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("trailing", [(), (2,), (8,), (32,), (33,), (200,)], ids=lambda t: "w" + "x".join(map(str, t)))
+@pytest.mark.parametrize("band_rows", [1, 4, 64])
+def test_bilinear_binned_matches_oracle(dt, trailing, band_rows):
+    """binning changes the evaluation order only: same bits as the oracle, hence as the direct kernel"""
+    rng = np.random.default_rng(501 + band_rows + int(np.prod(trailing, dtype=np.int64)))
+    n, m = 300, 41                                  # band_rows = 1 -> more than 256 bands wanted: the plan must coarsen
+    gx, gy = make_grid(rng, n, dt, "random"), make_grid(rng, m, dt, "uniform")
+    data = make_data(rng, (n, m) + trailing, dt)
+    ex = Interp2D.new_unchecked(gx, gy, data, Bilinear.new().extrapolate(True))
+    strict = Interp2D.new_unchecked(gx, gy, data, Bilinear.new())
+    _force_binning(ex, band_rows)
+    _force_binning(strict, band_rows)
+    for nq in (2, 33, 2048, 2049, 30011):
+        qx, qy = make_queries(rng, gx, nq, dt, True), make_queries(rng, gy, nq, dt, True)
+        st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, True)
+        assert st == O.ST_OK
+        assert same(ex.interp_array(qx, qy), ref)
+        qx, qy = make_queries(rng, gx, nq, dt, False), make_queries(rng, gy, nq, dt, False)
+        st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, False)
+        assert same(strict.interp_array(qx, qy), ref)
+
+
+def test_bilinear_binned_errors_like_the_reference():
+    rng = np.random.default_rng(23)
+    gx, gy = np.linspace(0, 1, 500), np.cumsum(rng.uniform(0.5, 1.5, 20))
+    data = rng.normal(size=(500, 20, 8))
+    interp = Interp2D.new_unchecked(gx, gy, data, Bilinear.new())
+    _force_binning(interp, 16)
+    for nq in (200, 70000):
+        qx, qy = rng.uniform(0, 1, nq), rng.uniform(gy[0], gy[-1], nq)
+        qy[nq // 2] = gy[-1] + 1
+        qx[nq // 2 + 5] = 2.0
+        qx[nq - 1] = np.nan
+        buf = np.full((nq, 8), 3.0)
+        with pytest.raises(InterpolateError.OutOfBounds, match="y = "):
+            interp.interp_array_into(qx, qy, buf)
+        st, ref, bad, ax = O.interp2d_bilinear(gx, gy, data, qx, qy, False, out=np.full((nq, 8), 3.0))
+        assert (st, bad, ax) == (O.ST_OUT_OF_BOUNDS, nq // 2, 1)
+        assert same(buf, ref)
+
+
+def test_bilinear_binned_device_api_error_word_and_rows():
+    """_dev entry point: one call, first failure = minimum over the (unordered) binned lanes"""
+    import torch
+    from ndarray_interp_b200 import device as D
+    rng = np.random.default_rng(29)
+    n, m, w, nq = 700, 64, 8, 100_000
+    gx, gy = np.cumsum(rng.uniform(0.5, 1.5, n)).astype(np.float32), np.linspace(-1, 1, m).astype(np.float32)
+    data = rng.normal(size=(n, m, w)).astype(np.float32)
+    qx = rng.uniform(gx[0], gx[-1], nq).astype(np.float32).clip(gx[0], gx[-1])
+    qy = rng.uniform(-1, 1, nq).astype(np.float32).clip(-1, 1)
+    bad = [91234, 5000, 5001, 77]
+    qx[bad[0]] = gx[-1] + 1; qy[bad[1]] = 2.0; qx[bad[2]] = np.nan; qy[bad[3]] = -3.0
+    st, ref, first, axis = O.interp2d_bilinear(gx, gy, data, qx, qy, False, out=np.zeros((nq, w), np.float32))
+    assert (first, axis) == (77, 1)
+    ip = D.DeviceInterp2D(torch.from_numpy(gx).cuda(), torch.from_numpy(gy).cuda(), torch.from_numpy(data).cuda())
+    outs = []
+    for mode, rows in [(L.BIN_OFF, 0), (L.BIN_ON, 32), (L.BIN_ON, 1)]:
+        ip.set_binning(mode, rows)
+        err = D.new_err_word()
+        out = torch.zeros((nq, w), dtype=torch.float32, device="cuda")
+        ip.bilinear(torch.from_numpy(qx).cuda(), torch.from_numpy(qy).cuda(), False, out=out, err=err)
+        assert D.err_word_value(err) == 2 * 77 + 1
+        outs.append(out.cpu().numpy())
+    good = np.ones(nq, bool); good[bad] = False
+    st, full, _, _ = O.interp2d_bilinear(gx, gy, data, qx[good], qy[good], False)
+    for o in outs:
+        assert same(o[good], full)                 # every passing row is written, failing rows are skipped
+        assert not o[bad].any()
+
+
+# ---- hoisted-reciprocal division (ndi_device.cuh: rcp_refined / div_by) ------------------------------
+def test_fdiv_selftest_sample():
+    """div_by(a, b, rcp_refined(b)) == __fdiv_rn(a, b): sampled numerator mantissas x ALL 2^23 divisor
+    mantissas, at the ends and in the middle of the exponent range the kernels admit
+    (b in [2^-40, 2^40], |a| in [2^-80, 2^80]).  The all-pairs run is scripts/exhaustive_fdiv.py."""
+    lib = L.require_device()
+    rng = np.random.default_rng(5)
+    starts = [0, (1 << 23) - 64, 1 << 22] + [int(v) for v in rng.integers(0, (1 << 23) - 64, 13)]
+    exps = [(0, 0), (-80, 40), (80, -40), (-80, -40), (80, 40), (3, -7)]
+    for i, s in enumerate(starts):
+        ea, eb = exps[i % len(exps)]
+        bad = C.c_uint64(123)
+        L.check(lib.ndi_selftest_fdiv(s, 64, ea, eb, C.byref(bad)))
+        assert bad.value == 0, (s, ea, eb, bad.value)
+
+
+@pytest.mark.parametrize("scale", [1e-30, 1e-17, 1.0, 1e9, 3e35], ids=lambda s: "x%g" % s)
+def test_f32_tables_outside_the_fast_division_range(scale):
+    """tables with tiny, huge, zero, denormal and infinite values: same bits as the oracle (IEEE division)"""
+    rng = np.random.default_rng(41)
+    n, m, w = 50, 37, 8
+    g = np.cumsum(rng.uniform(0.5, 1.5, n)).astype(np.float32)
+    gy = np.linspace(-2, 5, m).astype(np.float32)
+    d1 = (rng.normal(size=(n, w)) * scale).astype(np.float32)
+    d1[rng.integers(0, n, 40), rng.integers(0, w, 40)] = 0.0
+    d1[5] = d1[6]                                     # equal neighbours: zero numerators
+    d1[7, 0] = -0.0
+    d1[9, 1] = np.float32(1e-42)                      # denormal
+    d2 = (rng.normal(size=(n, m, w)) * scale).astype(np.float32)
+    d2[rng.integers(0, n, 200), rng.integers(0, m, 200)] = 0.0
+    d2[3] = d2[4]
+    d2[11, 5, 2] = np.float32(-1e-41)
+    with np.errstate(all="ignore"):
+        for extra in (None, np.inf):
+            if extra is not None:
+                d1[20, 3] = extra; d2[20, 20, 3] = -extra
+            q = make_queries(rng, g, 4000, np.float32, True)
+            st, ref, _ = O.interp1d_linear(g, d1, q, True)
+            assert same(Interp1D.new_unchecked(g, d1, Linear.new().extrapolate(True)).interp_array(q), ref)
+            qx, qy = make_queries(rng, g, 4000, np.float32, True), make_queries(rng, gy, 4000, np.float32, True)
+            st, ref, _, _ = O.interp2d_bilinear(g, gy, d2, qx, qy, True)
+            assert same(Interp2D.new_unchecked(g, gy, d2, Bilinear.new().extrapolate(True)).interp_array(qx, qy), ref)
+
+
+def test_f32_fast_division_edge_queries():
+    """in-range tables (fast path armed) with the per-query and per-element exits: extreme
+    extrapolation, grid steps outside [2^-40, 2^40], and second-stage numerators below 2^-80"""
+    rng = np.random.default_rng(43)
+    w = 8
+    gx = np.array([0.0, 1e-13, 1.0, 2.0, 3.0, 1e13, 2e13], dtype=np.float32)      # steps 1e-13 and 1e13
+    gy = np.array([0.0, 1.0, 2.0, 4.0], dtype=np.float32)
+    data = rng.normal(size=(len(gx), len(gy), w)).astype(np.float32)
+    data[0] = 0.0; data[1, :, ::2] = 0.0                                          # z1, z2 tiny next to the knot at 0
+    qx = np.concatenate([np.float32(1e-30) * np.arange(1, 200, dtype=np.float32), rng.uniform(0, 3, 500).astype(np.float32),
+                         np.float32([1e-14, 5e-14, 1e12, 1.5e13, -1e25, 1e30, -3e38, 3e38, 1e-45, 0.0])])
+    qy = np.concatenate([rng.uniform(0, 4, len(qx) - 6), [1e-38, -1e30, 1e30, 3.9999, 0.0, 4.0]]).astype(np.float32)
+    with np.errstate(all="ignore"):
+        st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, True)
+        got = Interp2D.new_unchecked(gx, gy, data, Bilinear.new().extrapolate(True)).interp_array(qx, qy)
+        assert same(got, ref)
+        d1 = data[:, 1, :].copy()
+        st, ref, _ = O.interp1d_linear(gx, d1, qx, True)
+        assert same(Interp1D.new_unchecked(gx, d1, Linear.new().extrapolate(True)).interp_array(qx), ref)
