@@ -270,6 +270,7 @@ def run_b200(args, wl, name):
         return t
 
     extrap = wl["extrap"]
+    spline_build = None
     if wl["kind"] == "bilinear":
         gx, gy, data = replicated(host["x"]), replicated(host["y"]), replicated(host["data"])
         ip = D.DeviceInterp2D(gx, gy, data)
@@ -308,6 +309,17 @@ def run_b200(args, wl, name):
             else:
                 st, _ = ip.spline_build(L_BC_NATURAL)
                 assert st == 0
+            if world == 1:
+                # K6 on its own: CubicSpline::calc_coefficients for this table (host-synchronous call, wall clock)
+                torch.cuda.synchronize()
+                reps, t0 = 5, time.perf_counter()
+                for _ in range(reps):
+                    st, _ = ip.spline_build(L_BC_NATURAL)
+                build_ms = (time.perf_counter() - t0) / reps * 1e3
+                build_bytes = s * (3 * wl["n"] - 2) * wl["w"]            # y in, a and b out
+                spline_build = {"ms": build_ms, "columns": wl["w"], "rows": wl["n"],
+                                "algorithmic_GBps": build_bytes / build_ms / 1e6,
+                                "note": "ndi_interp1d_spline_build, Natural boundary, includes allocation + final sync"}
         q = torch.from_numpy(host["q"]).to(dev)
         out = torch.empty((wl["q"], wl["w"]), dtype=tdt, device=dev)
         err = D.new_err_word(dev)
@@ -425,6 +437,7 @@ def run_b200(args, wl, name):
                          "traffic": recorded_traffic(name), "algorithmic_bytes": abytes, "peak_source": peak_src,
                          "frac_of_nominal_8000": achieved / 8000.0},
             "cpu_baseline": cpu,
+            "spline_build": spline_build,
             "e2e": e2e,
             "gpu_launches": int(launches) * world,
             "clocks": sampler.summary(),

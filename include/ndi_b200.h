@@ -213,6 +213,11 @@ ndi_status ndi_interp2d_bilinear_dev(const ndi_interp2d* h, const void* qx_dev, 
 ndi_status ndi_selftest_fdiv(uint32_t a_mant_begin, uint32_t a_mant_count, int32_t a_exp, int32_t b_exp,
                              uint64_t* mismatches);
 
+/* f64 counterpart for the spline sweeps (cubic_spline.rs:716 divides by a matrix entry shared by all
+ * columns; csrc/ndi_device.cuh: Hoisted<double>): counts mismatches against the correctly rounded
+ * quotient over about `pairs` pseudo-random operand pairs covering every exponent.  Must report 0. */
+ndi_status ndi_selftest_ddiv(uint64_t seed, uint64_t pairs, uint64_t* mismatches);
+
 #ifdef __cplusplus
 }
 #endif

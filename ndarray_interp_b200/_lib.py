@@ -58,6 +58,7 @@ SIGNATURES = {
     "ndi_interp2d_device_ptrs": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "ndi_interp2d_clone_to_device": (_i32, [_vp, _i32, C.POINTER(_vp)]),
     "ndi_selftest_fdiv": (_i32, [_u32, _u32, _i32, _i32, C.POINTER(_u64)]),
+    "ndi_selftest_ddiv": (_i32, [_u64, _u64, C.POINTER(_u64)]),
     "ndi_interp2d_set_binning": (_i32, [_vp, _i32, _i32]),
     "ndi_interp2d_bilinear": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _pi64, _pi32]),
     "ndi_interp2d_bilinear_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),

@@ -324,6 +324,22 @@ ndi_status ndi_selftest_fdiv(uint32_t a_mant_begin, uint32_t a_mant_count, int32
     return NDI_OK;
 }
 
+ndi_status ndi_selftest_ddiv(uint64_t seed, uint64_t pairs, uint64_t* mismatches) {
+    if (!mismatches) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    int dev = 0; CK(cudaGetDevice(&dev));
+    ndi_status st; Workspace* ws = workspace(dev, &st); if (!ws) return st;
+    const int per_thread = 64;                                   // x 8 numerators each
+    uint64_t blocks = (pairs + 256ull * per_thread * 8 - 1) / (256ull * per_thread * 8);
+    if (blocks < 1) blocks = 1;
+    if (blocks > (1u << 30)) return fail(NDI_INVALID_ARGUMENT, "too many pairs");
+    CK(cudaMemsetAsync(ws->d_err, 0, sizeof(uint64_t), ws->s[0]));
+    CK(launch_selftest_ddiv(seed, (int)blocks, per_thread, ws->d_err, ws->s[0]));
+    CK(cudaMemcpyAsync(ws->h_pin, ws->d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws->s[0]));
+    CK(cudaStreamSynchronize(ws->s[0]));
+    memcpy(mismatches, ws->h_pin, sizeof(uint64_t));
+    return NDI_OK;
+}
+
 const char* ndi_version_string(void) { return "ndarray-interp-b200 0.1 (sm_100a)"; }
 const char* ndi_last_error_message(void) { return g_err; }
 uint64_t ndi_kernel_launch_count(void) { return g_launches.load(); }
@@ -648,26 +664,31 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
         const size_t coef_bytes = (size_t)(h->n - 1) * h->w * sizeof(T);
         T *a = nullptr, *b = nullptr, *scratch = nullptr, *lv = nullptr, *rv = nullptr;
         int32_t *lk = nullptr, *rk = nullptr;
+        // everything comes from the stream-ordered pool (device_info() keeps freed blocks cached), so a
+        // rebuild does not pay cudaMalloc / cudaFree
+        cudaStream_t bs = ws->s[0];
         auto cleanup = [&](bool keep) {
-            cudaFree(scratch); cudaFree(lv); cudaFree(rv); cudaFree(lk); cudaFree(rk);
-            if (!keep) { cudaFree(a); cudaFree(b); }
+            cudaFreeAsync(scratch, bs); cudaFreeAsync(lv, bs); cudaFreeAsync(rv, bs); cudaFreeAsync(lk, bs); cudaFreeAsync(rk, bs);
+            if (!keep) { cudaFreeAsync(a, bs); cudaFreeAsync(b, bs); }
+            cudaGetLastError();
         };
         auto body = [&]() -> ndi_status {
-            CK(cudaMalloc(&a, coef_bytes));
-            CK(cudaMalloc(&b, coef_bytes));
-            CK(cudaMalloc(&scratch, spline_scratch_elems<T>(h->n, h->w, bc_kind) * sizeof(T)));
+            device_info();
+            CK(cudaMallocAsync((void**)&a, coef_bytes, bs));
+            CK(cudaMallocAsync((void**)&b, coef_bytes, bs));
+            CK(cudaMallocAsync((void**)&scratch, spline_scratch_elems<T>(h->n, h->w, bc_kind) * sizeof(T), bs));
             if (bc_kind == NDI_BC_INDIVIDUAL) {
-                CK(cudaMalloc(&lk, h->w * sizeof(int32_t))); CK(cudaMalloc(&rk, h->w * sizeof(int32_t)));
-                CK(cudaMalloc(&lv, h->w * sizeof(T))); CK(cudaMalloc(&rv, h->w * sizeof(T)));
-                CK(cudaMemcpyAsync(lk, left_kind, h->w * sizeof(int32_t), cudaMemcpyHostToDevice, ws->s[0]));
-                CK(cudaMemcpyAsync(rk, right_kind, h->w * sizeof(int32_t), cudaMemcpyHostToDevice, ws->s[0]));
-                CK(cudaMemcpyAsync(lv, left_val, h->w * sizeof(T), cudaMemcpyHostToDevice, ws->s[0]));
-                CK(cudaMemcpyAsync(rv, right_val, h->w * sizeof(T), cudaMemcpyHostToDevice, ws->s[0]));
+                CK(cudaMallocAsync((void**)&lk, h->w * sizeof(int32_t), bs)); CK(cudaMallocAsync((void**)&rk, h->w * sizeof(int32_t), bs));
+                CK(cudaMallocAsync((void**)&lv, h->w * sizeof(T), bs)); CK(cudaMallocAsync((void**)&rv, h->w * sizeof(T), bs));
+                CK(cudaMemcpyAsync(lk, left_kind, h->w * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
+                CK(cudaMemcpyAsync(rk, right_kind, h->w * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
+                CK(cudaMemcpyAsync(lv, left_val, h->w * sizeof(T), cudaMemcpyHostToDevice, bs));
+                CK(cudaMemcpyAsync(rv, right_val, h->w * sizeof(T), cudaMemcpyHostToDevice, bs));
             }
-            CK(cudaMemsetAsync(ws->d_err, 0xff, sizeof(uint64_t), ws->s[0]));
-            CK(launch_spline_build<T>((const T*)h->x, h->n, (const T*)h->data, h->w, bc_kind, lk, lv, rk, rv, a, b, scratch, ws->d_err, ws->s[0]));
-            CK(cudaMemcpyAsync(ws->h_pin, ws->d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws->s[0]));
-            CK(cudaStreamSynchronize(ws->s[0]));
+            CK(cudaMemsetAsync(ws->d_err, 0xff, sizeof(uint64_t), bs));
+            CK(launch_spline_build<T>((const T*)h->x, h->n, (const T*)h->data, h->w, bc_kind, lk, lv, rk, rv, a, b, scratch, ws->d_err, bs));
+            CK(cudaMemcpyAsync(ws->h_pin, ws->d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, bs));
+            CK(cudaStreamSynchronize(bs));
             return NDI_OK;
         };
         ndi_status s2 = body();
@@ -679,7 +700,7 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
             return fail(NDI_PERIODIC_MISMATCH, "for periodic boundary condition the first and last value must be equal (column %lld)", (long long)word);
         }
         cleanup(true);
-        if (h->owns_coeffs) { cudaFree(h->a); cudaFree(h->b); }
+        if (h->owns_coeffs) { cudaFreeAsync(h->a, bs); cudaFreeAsync(h->b, bs); }
         h->a = a; h->b = b; h->owns_coeffs = true;
         return NDI_OK;
     });
@@ -871,12 +892,13 @@ long env_long(const char* name, long dflt) {
     return v && *v ? strtol(v, nullptr, 10) : dflt;
 }
 
-// Is grouping the queries by table band (ndi_bin.cu) worth its extra passes?  Estimated DRAM bytes
-// of the direct kernel (four gathers per query, each at least one 32-byte sector, missing L2 in
-// proportion to the part of the table that cannot stay resident) against the binned path (table
-// once + 28 B (f32) of extra query traffic per query).
+// Is grouping the queries by table band (ndi_bin.cu) worth its two extra passes?  Measured on B200
+// (profiles/r01/binning.md): yes when the table cannot stay in L2 under random gathers AND an
+// output row is at least two sectors (C5a, 128-byte rows: 3.44 -> 2.54 ms); no for 32-byte rows
+// (C4: 0.59 -> 0.62 ms), where the scattered output stores and the binning passes cost what the
+// gathers save and the evaluation is bound by L1 wavefronts either way.
 bool want_binning(const ndi_interp2d* h, int64_t nq, size_t es, BandPlan* bp) {
-    static const long env_mode = env_long("NDI_BIN_MODE", -1), env_band_mb = env_long("NDI_BAND_MB", 32);
+    static const long env_mode = env_long("NDI_BIN_MODE", -1), env_band_mb = env_long("NDI_BAND_MB", 16);
     const int mode = env_mode >= 0 ? (int)env_mode : h->bin_mode;
     if (mode == NDI_BIN_OFF || nq < 2 || nq > 0xffffffffll) return false;
     const double table = (double)h->n * (double)h->m * (double)h->w * (double)es;
@@ -884,8 +906,8 @@ bool want_binning(const ndi_interp2d* h, int64_t nq, size_t es, BandPlan* bp) {
     if (bp->nbands < 2) return false;
     if (mode == NDI_BIN_ON) return true;
     const double resident = 0.4 * (double)device_info().l2_bytes;   // what random gathers keep of L2 (two partitions, output stream)
-    if (table <= resident || nq < (1 << 18)) return false;
-    const double seg = (double)(h->w * es < 32 ? 32 : h->w * es);
+    const double seg = (double)(h->w * es);
+    if (table <= resident || nq < (1 << 18) || seg < 64) return false;
     const double direct = (double)nq * 4.0 * seg * (1.0 - resident / table);
     const double binned = table + (double)nq * (double)(es + 2 * (4 + 2 * es));
     return direct > 1.5 * binned;

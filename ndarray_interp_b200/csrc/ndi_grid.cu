@@ -247,4 +247,39 @@ cudaError_t launch_selftest_fdiv(uint32_t a_mant_begin, uint32_t a_mant_count, i
     return cudaGetLastError();
 }
 
+// ndi_selftest_ddiv: Hoisted<double>::div against __ddiv_rn on pseudo-random operand pairs (splitmix64
+// bit patterns: every exponent, sign and mantissa; plus pairs with equal or nearly equal exponents).
+__device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) selftest_ddiv_kernel(uint64_t seed, int per_thread, unsigned long long* mismatches) {
+    uint64_t st = seed + 0x632BE59BD9B4E019ull * ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1);
+    unsigned long long bad = 0;
+    for (int it = 0; it < per_thread; ++it) {
+        uint64_t ub = splitmix64(st);
+        if (it & 1) ub = (ub & 0x800FFFFFFFFFFFFFull) | ((uint64_t)(1023 - 400 + (int)(splitmix64(st) % 800)) << 52);   // in Hoisted's range
+        const double b = __longlong_as_double((long long)ub);
+        const double r = Hoisted<double>::rcp(b);
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            uint64_t ua = splitmix64(st);
+            if (j & 1) ua = (ua & 0x800FFFFFFFFFFFFFull) | (ub & 0x7FF0000000000000ull);     // same exponent as b
+            const double a = __longlong_as_double((long long)ua);
+            const double q = Hoisted<double>::div(a, b, r), ref = __ddiv_rn(a, b);
+            bad += __double_as_longlong(q) != __double_as_longlong(ref) && !(q != q && ref != ref);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
+}
+cudaError_t launch_selftest_ddiv(uint64_t seed, int blocks, int per_thread, unsigned long long* mismatches_dev, cudaStream_t st) {
+    selftest_ddiv_kernel<<<blocks, 256, 0, st>>>(seed, per_thread, mismatches_dev);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace ndi

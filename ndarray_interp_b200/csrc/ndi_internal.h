@@ -84,6 +84,8 @@ cudaError_t launch_table_fast_div(const float* data, size_t count, int32_t* flag
 cudaError_t launch_selftest_fdiv(uint32_t a_mant_begin, uint32_t a_mant_count, int a_exp, int b_exp,
                                  unsigned long long* mismatches_dev, cudaStream_t st);
 
+cudaError_t launch_selftest_ddiv(uint64_t seed, int blocks, int per_thread, unsigned long long* mismatches_dev, cudaStream_t st);
+
 // ---- grid checks (ndi_grid.cu) -----------------------------------------------------------
 // result[0] = Monotonic enum, result[1] = 1 when the even-spacing guess hits on every cell
 template <class T>

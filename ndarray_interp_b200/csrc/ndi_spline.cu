@@ -11,12 +11,21 @@
 //     eliminated diagonal, :690-692) is therefore done once, by `spline_factor_kernel`, in exactly
 //     the reference's serial order.  For Periodic the second solve (rhs2, :535-550) is the same for
 //     every column too and is also done there.
-//   * `spline_columns_kernel` is the column-parallel Thomas: one thread per trailing column, the
-//     columns of a row are contiguous so every load and store is coalesced.  The forward sweep
-//     builds the right-hand side on the fly from a sliding window of three data rows and parks the
-//     swept values in the `b` output buffer; the backward sweep turns them into k and immediately
-//     into a and b (:354-365), so k is never written to memory: the build reads data twice and
-//     writes a and b once.
+//   * per column only two first-order recurrences are serial in the row index:
+//         forward   r[i] = rhs[i] - w[i] * r[i-1]                 (:698)
+//         backward  k[i] = (r[i] - up[i] * k[i+1]) / mid'[i]      (:716)
+//     Everything else -- the right-hand side (:468, two divisions per element) and a, b from k
+//     (:354-365) -- is independent per element.  The build is therefore three launches:
+//         spline_rhs_kernel     all elements in parallel: rhs into the scratch matrix R (n x w)
+//         spline_sweep_kernel   one thread per column: the two recurrences in place on R, rows streamed
+//                               through shared memory with cp.async so that a step waits for arithmetic
+//                               only; the division by mid'[i] uses the reciprocal formed once per row by
+//                               the factor kernel (ndi_device.cuh, Hoisted) -- same quotient, 3 dependent
+//                               operations instead of ~13
+//         spline_ab_kernel      all elements in parallel: a, b from k and y
+//     (first version: one fused kernel, one thread per column doing all of it serially: 4.3 ms for
+//     4096 x 1024 f64 because 32 warps executed ~150 instructions per row each; profiles/r01.)
+//     `spline_columns_kernel` is that fused version, kept for the 3-point special cases.
 //   * BoundaryCondition::Individual gives every column its own first/last matrix row, hence its
 //     own elimination; `spline_columns_individual_kernel` does the factorisation per column
 //     (scratch: one eliminated diagonal per column).
@@ -121,39 +130,75 @@ __device__ __forceinline__ T rhs_right(const T* __restrict__ x, int n, Side<T> r
     return ADD(MUL(three, SUB(y_1, y_2)), DIV(MUL(r.val, MUL(dx_1, dx_1)), two));     // :666
 }
 
-// ---- shared-matrix factorisation (one thread; serial by definition) ---------------------------
-// fac layout: up[n] | mid[n] (eliminated) | wl[n] | k2[n]
+// ---- shared-matrix factorisation -------------------------------------------------------------------
+// The elimination w[i] = low[i] / mid'[i-1]; mid'[i] = mid[i] - w[i] * up[i-1] (thomas :690-692) is a
+// serial chain by definition (division -> multiply -> subtract, in the reference's order).  One
+// block: all threads form the matrix rows of a tile in shared memory, thread 0 runs the chain over
+// the tile out of shared memory (so its only latency is the arithmetic), all threads write the
+// tile back.  fac layout: up[n] | mid[n] (eliminated) | wl[n] | k2[n]
+constexpr int kFacTile = 1024, kFacBlock = 256;
+template <class T> struct alignas(4 * sizeof(T)) FacRow { T up, mid, wl, rmid; };
 template <class T>
-__global__ void spline_factor_kernel(const T* __restrict__ x, int n, int periodic, int lk, int rk, T* __restrict__ fac) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    T* up = fac; T* mid = fac + n; T* wl = fac + 2 * (size_t)n; T* k2 = fac + 3 * (size_t)n;
+__device__ __forceinline__ FacRow<T> ld_fac(const FacRow<T>* p) {
+    FacRow<T> f;
+    if constexpr (sizeof(T) == 4) { const int4 v = __ldg(reinterpret_cast<const int4*>(p)); f = *reinterpret_cast<const FacRow<T>*>(&v); }
+    else {
+        const int4 v0 = __ldg(reinterpret_cast<const int4*>(p)), v1 = __ldg(reinterpret_cast<const int4*>(p) + 1);
+        int4 t[2] = {v0, v1};
+        f = *reinterpret_cast<const FacRow<T>*>(t);
+    }
+    return f;
+}
+template <class T>
+__global__ void __launch_bounds__(kFacBlock) spline_factor_kernel(const T* __restrict__ x, int n, int periodic, int lk, int rk,
+                                                                  T* __restrict__ fac) {
+    __shared__ T su[kFacTile], sm[kFacTile], sl[kFacTile];
+    __shared__ T carry[2];
+    FacRow<T>* rows = reinterpret_cast<FacRow<T>*>(fac);
+    T* k2 = fac + 4 * (size_t)n;
     const bool nak3 = !periodic && n == 3 && lk == SB_NAK && rk == SB_NAK;
     const int len = periodic ? n - 2 : n;
-    T u, m, l;
-    if (periodic) matrix_row_periodic<T>(x, n, 0, u, m, l); else matrix_row<T>(x, n, 0, lk, rk, nak3, u, m, l);
-    up[0] = u; mid[0] = m; wl[0] = (T)0;
-    T m_prev = m, u_prev = u;
-    for (int i = 1; i < len; ++i) {                                                   // thomas :690-692
-        if (periodic) matrix_row_periodic<T>(x, n, i, u, m, l); else matrix_row<T>(x, n, i, lk, rk, nak3, u, m, l);
-        const T w = DIV(l, m_prev);
-        m = SUB(m, MUL(w, u_prev));
-        up[i] = u; mid[i] = m; wl[i] = w;
-        m_prev = m; u_prev = u;
+    for (int base = 0; base < len; base += kFacTile) {
+        const int cnt = min(kFacTile, len - base);
+        for (int j = threadIdx.x; j < cnt; j += kFacBlock) {
+            T u, m, l;
+            if (periodic) matrix_row_periodic<T>(x, n, base + j, u, m, l); else matrix_row<T>(x, n, base + j, lk, rk, nak3, u, m, l);
+            su[j] = u; sm[j] = m; sl[j] = l;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            T m_prev = base ? carry[0] : (T)0, u_prev = base ? carry[1] : (T)0;
+            for (int j = 0; j < cnt; ++j) {
+                T m = sm[j];
+                T w = (T)0;
+                if (base + j > 0) {
+                    w = DIV(sl[j], m_prev);
+                    m = SUB(m, MUL(w, u_prev));
+                }
+                sm[j] = m; sl[j] = w;
+                m_prev = m; u_prev = su[j];
+            }
+            carry[0] = m_prev; carry[1] = u_prev;
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < cnt; j += kFacBlock) rows[base + j] = FacRow<T>{su[j], sm[j], sl[j], Hoisted<T>::rcp(sm[j])};
+        __syncthreads();
     }
-    if (periodic && n > 3) {                                                          // rhs2 solve :535-550
+    if (periodic && n > 3 && threadIdx.x == 0) {                                      // rhs2 solve :535-550
+        __threadfence_block();
         const T dx0 = SUB(x[1], x[0]), dx_3 = SUB(x[n - 3], x[n - 4]);
         T prev = (T)0;
         for (int i = 0; i < len; ++i) {
             T r = (T)0;
             if (i == 0) r = -dx0;
             if (i == n - 3) r = -dx_3;
-            if (i > 0) r = SUB(r, MUL(wl[i], prev));
+            if (i > 0) r = SUB(r, MUL(rows[i].wl, prev));
             k2[i] = r; prev = r;
         }
-        T kr = DIV(k2[len - 1], mid[len - 1]);
+        T kr = DIV(k2[len - 1], rows[len - 1].mid);
         k2[len - 1] = kr;
         for (int i = len - 2; i >= 0; --i) {
-            kr = DIV(SUB(k2[i], MUL(up[i], kr)), mid[i]);
+            kr = DIV(SUB(k2[i], MUL(rows[i].up, kr)), rows[i].mid);
             k2[i] = kr;
         }
     }
@@ -167,7 +212,11 @@ __global__ void __launch_bounds__(128) spline_columns_kernel(const T* __restrict
                                                              T* __restrict__ b, unsigned long long* err) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= w) return;
-    const T* up = fac; const T* mid = fac + n; const T* wl = fac + 2 * (size_t)n; const T* k2 = fac + 3 * (size_t)n;
+    const FacRow<T>* rows = reinterpret_cast<const FacRow<T>*>(fac);
+    const T* k2 = fac + 4 * (size_t)n;
+    auto up = [&](int i) { return rows[i].up; };
+    auto mid = [&](int i) { return rows[i].mid; };
+    auto wl = [&](int i) { return rows[i].wl; };
     const T one = (T)1, two = (T)2, three = (T)3;
     auto Y = [&](int r) -> T { return __ldg(y + (long long)r * w + c); };
     auto Aat = [&](int r) -> T& { return a[(long long)r * w + c]; };
@@ -201,15 +250,15 @@ __global__ void __launch_bounds__(128) spline_columns_kernel(const T* __restrict
         for (int i = 1; i < len; ++i) {
             const T yr = Y(i + 1);
             const T dxn = SUB(x[i + 1], x[i]), dxn_1 = SUB(x[i], x[i - 1]);
-            const T r = SUB(rhs_interior<T>(yl, ym, yr, dxn, dxn_1), MUL(wl[i], r_prev));
+            const T r = SUB(rhs_interior<T>(yl, ym, yr, dxn, dxn_1), MUL(wl(i), r_prev));
             Aat(i) = r; r_prev = r; yl = ym; ym = yr;
         }
         // back substitution -> k1, parked in a[0..len)
-        T kr = DIV(r_prev, mid[len - 1]);
+        T kr = DIV(r_prev, mid(len - 1));
         const T k1_last = kr;
         Aat(len - 1) = kr;
         for (int i = len - 2; i >= 0; --i) {
-            kr = DIV(SUB(Aat(i), MUL(up[i], kr)), mid[i]);
+            kr = DIV(SUB(Aat(i), MUL(up(i), kr)), mid(i));
             Aat(i) = kr;
         }
         const T k1_0 = kr;
@@ -251,7 +300,7 @@ __global__ void __launch_bounds__(128) spline_columns_kernel(const T* __restrict
             const T dxn = SUB(x[i + 1], x[i]), dxn_1 = SUB(x[i], x[i - 1]);
             rhs = rhs_interior<T>(yl, ym, yr, dxn, dxn_1);
         }
-        const T rr = SUB(rhs, MUL(wl[i], r_prev));                                    // :698
+        const T rr = SUB(rhs, MUL(wl(i), r_prev));                                    // :698
         Bat(i) = rr; r_prev = rr;
         if (i < n - 2) { yl = ym; ym = yr; }
     }
@@ -259,18 +308,287 @@ __global__ void __launch_bounds__(128) spline_columns_kernel(const T* __restrict
     T rhs_n;
     if (nak3) rhs_n = MUL(DIV(SUB(yr, ym), dx1), two);                                // :595
     else rhs_n = rhs_right<T>(x, n, r, yr, ym, yl);
-    const T r_last = SUB(rhs_n, MUL(wl[n - 1], r_prev));
+    const T r_last = SUB(rhs_n, MUL(wl(n - 1), r_prev));
     // back substitution fused with a, b
-    T k_right = DIV(r_last, mid[n - 1]);                                              // :704-708
+    T k_right = DIV(r_last, mid(n - 1));                                              // :704-708
     T y_right = yr;
 #pragma unroll 4
     for (int i = n - 2; i >= 0; --i) {
-        const T k = DIV(SUB(Bat(i), MUL(up[i], k_right)), mid[i]);                    // :716
+        const T k = DIV(SUB(Bat(i), MUL(up(i), k_right)), mid(i));                    // :716
         const T y_i = (i == n - 2) ? ym : Y(i);
         const T dx = SUB(x[i + 1], x[i]), dy = SUB(y_right, y_i);
         Aat(i) = SUB(MUL(k, dx), dy);                                                 // :362
         Bat(i) = SUB(dy, MUL(k_right, dx));                                           // :363
         k_right = k; y_right = y_i;
+    }
+}
+
+// ---- the three-launch build ---------------------------------------------------------------------------
+constexpr int kRows = 8, kRing = 4;       // sweep: kRing batches of kRows rows in flight per thread
+constexpr int kRowGroup = 4;              // rhs / ab: rows per thread, sharing their loads
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <class T>
+__device__ __forceinline__ void cp_async_elem(unsigned smem_addr, const T* gmem_src) {
+    if constexpr (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gmem_src) : "memory");
+}
+template <class T>
+__device__ __forceinline__ T lds_elem(unsigned smem_addr) {
+    T v;
+    // volatile keeps it between the cp.async wait before and the next prefetch after it (both volatile);
+    // no memory clobber, so ordinary loads and stores may be scheduled across it
+    if constexpr (sizeof(T) == 8) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_addr));
+    else asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_addr));
+    return v;
+}
+
+// a block works on (group of kRowGroup rows, chunk of blockDim.x columns) tasks; grid-stride over the tasks
+struct RowTask { int row; long long col; bool live; };
+__device__ __forceinline__ RowTask row_task(long long task, long long chunks, long long w) {
+    const long long g = task / chunks;
+    const long long col = (task - g * chunks) * blockDim.x + threadIdx.x;
+    return RowTask{(int)g * kRowGroup, col, col < w};
+}
+
+// launch 1: right-hand sides.  Non-periodic: R[0] = left boundary row, R[1..n-2] = interior rows (:468),
+// R[n-1] = right boundary row.  Periodic (n > 3): R[0] = condensed first row (:529-530), R[1..n-3] interior,
+// R[n-2] = the last condensed equation's right-hand side (:531-532), kept for k_m1; columns whose first
+// and last value differ are reported through err (:499-507).
+template <class T>
+__global__ void __launch_bounds__(256) spline_rhs_kernel(const T* __restrict__ x, int n, const T* __restrict__ y, long long w,
+                                                         int periodic, Side<T> left, Side<T> right, T* __restrict__ R,
+                                                         unsigned long long* err) {
+    const Side<T> l = specialize(left), r = specialize(right);
+    const T three = (T)3;
+    const long long chunks = (w + blockDim.x - 1) / blockDim.x;
+    const int rows = periodic ? n - 1 : n;
+    const long long ntasks = chunks * ((rows + kRowGroup - 1) / kRowGroup);
+    for (long long task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const RowTask t = row_task(task, chunks, w);
+        if (!t.live) continue;
+        const T* ycol = y + t.col;
+        auto Y = [&](int row) -> T { return __ldg(ycol + (long long)row * w); };
+        // window y[row-1 .. row+kRowGroup] shared by the rows of the group (clamped at the ends, where it is not used)
+        T yv[kRowGroup + 2];
+#pragma unroll
+        for (int j = 0; j < kRowGroup + 2; ++j) yv[j] = Y(min(max(t.row - 1 + j, 0), n - 1));
+#pragma unroll
+        for (int j = 0; j < kRowGroup; ++j) {
+            const int i = t.row + j;
+            if (i >= rows) break;
+            T v;
+            const bool interior = periodic ? (i > 0 && i < n - 2) : (i > 0 && i < n - 1);
+            if (interior) {
+                const T dxn = SUB(x[i + 1], x[i]), dxn_1 = SUB(x[i], x[i - 1]);
+                v = rhs_interior<T>(yv[j], yv[j + 1], yv[j + 2], dxn, dxn_1);
+            } else if (periodic) {
+                const T dx0 = SUB(x[1], x[0]), dx_1 = SUB(x[n - 1], x[n - 2]), dx_2 = SUB(x[n - 2], x[n - 3]);
+                if (i == 0) {
+                    const T y0 = Y(0), yN = Y(n - 1);
+                    if (y0 != yN) atomicMin(err, (unsigned long long)t.col);
+                    const T slope0 = DIV(SUB(Y(1), y0), dx0);                         // :521
+                    const T slope_1 = DIV(SUB(yN, Y(n - 2)), dx_1);                   // :526
+                    v = MUL(ADD(MUL(slope_1, dx0), MUL(slope0, dx_1)), three);        // :529-530
+                } else {
+                    const T yn2 = Y(n - 2);
+                    const T slope_1 = DIV(SUB(Y(n - 1), yn2), dx_1), slope_2 = DIV(SUB(yn2, Y(n - 3)), dx_2);   // :526-527
+                    v = MUL(ADD(MUL(slope_2, dx_1), MUL(slope_1, dx_2)), three);      // :531-532
+                }
+            } else if (i == 0) {
+                v = rhs_left<T>(x, l, Y(0), Y(1), Y(2));
+            } else {
+                v = rhs_right<T>(x, n, r, Y(n - 1), Y(n - 2), Y(n - 3));
+            }
+            R[(long long)i * w + t.col] = v;
+        }
+    }
+}
+
+// launch 2: the two recurrences over rows [0, len) of R, in place (thomas :690-720 with the matrix part
+// already done by the factor kernel).  One thread per column.  A step must wait for arithmetic only,
+// so everything it reads is staged in shared memory ahead of time with cp.async:
+//   * the column's own rows go through a private ring (kRing batches of kRows rows in flight); a thread
+//     reads back only what it copied itself, so cp.async.wait_group is all the synchronisation needed;
+//   * the matrix rows (the same for every column) are staged per warp, 32 rows at a time, one row per
+//     lane, double buffered; __syncwarp makes the other lanes' copies visible.
+// Pointers advance by one row per step and all shared-memory offsets are compile-time constants.
+template <class T>
+__device__ __forceinline__ void cp_async_fac(unsigned smem_addr, const FacRow<T>* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(src) : "memory");
+    if constexpr (sizeof(T) == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr + 16), "l"(reinterpret_cast<const char*>(src) + 16) : "memory");
+}
+
+template <class T, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) spline_sweep_kernel(int len, long long w, const T* __restrict__ fac, T* __restrict__ R) {
+    extern __shared__ __align__(32) unsigned char ring_raw[];
+    constexpr int kSuper = kRing * kRows;                     // rows per outer iteration
+    static_assert(kSuper == 32, "one matrix row per lane and outer iteration");
+    constexpr unsigned kSlot = BLOCK * sizeof(T);
+    constexpr unsigned kFacBytes = sizeof(FacRow<T>);
+    const long long c0 = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = c0 < w;                                 // dead lanes shadow the last column (they stage matrix rows too)
+    const long long c = live ? c0 : w - 1;
+    const int lane = threadIdx.x & 31;
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(ring_raw);
+    const unsigned ring = smem0 + threadIdx.x * (unsigned)sizeof(T);
+    const unsigned facbuf = smem0 + kSuper * kSlot + (threadIdx.x >> 5) * (2 * kSuper * kFacBytes);   // this warp's [2][32] rows
+    const FacRow<T>* rows = reinterpret_cast<const FacRow<T>*>(fac);
+    T* col = R + c;
+
+    T k;                                                      // k[len-1] after the forward sweep, then the running k[i+1]
+    // ---- forward: r[i] = rhs[i] - wl[i] * r[i-1], i = 1 .. len-1
+    {
+        const T* pf = col + w;                                // next row to prefetch
+        int pf_left = len - 1;
+        auto prefetch = [&](int slot0) {
+#pragma unroll
+            for (int j = 0; j < kRows; ++j) {
+                if (j < pf_left) cp_async_elem<T>(ring + (slot0 + j) * kSlot, pf);
+                pf += w;
+            }
+            pf_left -= kRows;
+        };
+        int fac_row = 1 + lane;                               // the matrix row this lane stages next
+        auto stage_fac = [&](int buf) {
+            if (fac_row < len) cp_async_fac<T>(facbuf + (buf * kSuper + lane) * kFacBytes, rows + fac_row);
+            fac_row += kSuper;
+        };
+        stage_fac(0);
+#pragma unroll
+        for (int b = 0; b < kRing - 1; ++b) { prefetch(b * kRows); cp_async_commit(); }
+        T prev = col[0];
+        T* wp = col + w;
+        int buf = 0;
+        for (int left = len - 1; left > 0; buf ^= 1) {
+#pragma unroll
+            for (int bb = 0; bb < kRing; ++bb) {
+                if (bb == 0) stage_fac(buf ^ 1);
+                prefetch(((bb + kRing - 1) % kRing) * kRows);
+                cp_async_commit();
+                cp_async_wait<kRing - 1>();
+                if (bb == 0) __syncwarp();
+#pragma unroll
+                for (int j = 0; j < kRows; ++j) {
+                    if (j < left) {
+                        const T wl = lds_elem<T>(facbuf + (buf * kSuper + bb * kRows + j) * kFacBytes + 2 * sizeof(T));
+                        prev = SUB(lds_elem<T>(ring + (bb * kRows + j) * kSlot), MUL(wl, prev));   // :698
+                        if (live) *wp = prev;
+                    }
+                    wp += w;
+                }
+                left -= kRows;
+            }
+            __syncwarp();                                     // everyone is done with buf before it is staged again
+        }
+        const FacRow<T> flast = ld_fac<T>(rows + len - 1);
+        k = Hoisted<T>::div(prev, flast.mid, flast.rmid);                             // :704-708
+        if (live) col[(long long)(len - 1) * w] = k;
+    }
+    cp_async_wait<0>();
+    __threadfence();                                          // the swept values are read back below
+    __syncwarp();
+
+    // ---- backward: k[i] = (r[i] - up[i] * k[i+1]) / mid[i], i = len-2 .. 0
+    {
+        const T* pf = col + (long long)(len - 2) * w;
+        int pf_left = len - 1;
+        auto prefetch = [&](int slot0) {
+#pragma unroll
+            for (int j = 0; j < kRows; ++j) {
+                if (j < pf_left) cp_async_elem<T>(ring + (slot0 + j) * kSlot, pf);
+                pf -= w;
+            }
+            pf_left -= kRows;
+        };
+        int fac_row = len - 2 - lane;
+        auto stage_fac = [&](int buf) {
+            if (fac_row >= 0) cp_async_fac<T>(facbuf + (buf * kSuper + lane) * kFacBytes, rows + fac_row);
+            fac_row -= kSuper;
+        };
+        stage_fac(0);
+#pragma unroll
+        for (int b = 0; b < kRing - 1; ++b) { prefetch(b * kRows); cp_async_commit(); }
+        T* wp = col + (long long)(len - 2) * w;
+        int buf = 0;
+        for (int left = len - 1; left > 0; buf ^= 1) {
+#pragma unroll
+            for (int bb = 0; bb < kRing; ++bb) {
+                if (bb == 0) stage_fac(buf ^ 1);
+                prefetch(((bb + kRing - 1) % kRing) * kRows);
+                cp_async_commit();
+                cp_async_wait<kRing - 1>();
+                if (bb == 0) __syncwarp();
+#pragma unroll
+                for (int j = 0; j < kRows; ++j) {
+                    if (j < left) {
+                        const unsigned fa = facbuf + (buf * kSuper + bb * kRows + j) * kFacBytes;
+                        const T up = lds_elem<T>(fa), mid = lds_elem<T>(fa + sizeof(T)), rmid = lds_elem<T>(fa + 3 * sizeof(T));
+                        k = Hoisted<T>::div(SUB(lds_elem<T>(ring + (bb * kRows + j) * kSlot), MUL(up, k)), mid, rmid);   // :716
+                        if (live) *wp = k;
+                    }
+                    wp -= w;
+                }
+                left -= kRows;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// periodic only, between launch 2 and 3: k_m1 (:552-557) into R[n-2], k[n-1] = k[0] (:563) into R[n-1]
+template <class T>
+__global__ void __launch_bounds__(256) spline_periodic_close_kernel(const T* __restrict__ x, int n, long long w,
+                                                                    const T* __restrict__ fac, T* __restrict__ R) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= w) return;
+    const T* k2 = fac + 4 * (size_t)n;
+    const int len = n - 2;
+    const T two = (T)2;
+    const T dx_1 = SUB(x[n - 1], x[n - 2]), dx_2 = SUB(x[n - 2], x[n - 3]);
+    const T k1_0 = R[c], k1_last = R[(long long)(len - 1) * w + c], rhs_last = R[(long long)(n - 2) * w + c];
+    const T k_m1 = DIV(SUB(SUB(rhs_last, MUL(k1_0, dx_2)), MUL(k1_last, dx_1)),
+                       ADD(ADD(MUL(k2[0], dx_2), MUL(k2[len - 1], dx_1)), MUL(two, ADD(dx_1, dx_2))));
+    R[(long long)(n - 2) * w + c] = k_m1;
+    R[(long long)(n - 1) * w + c] = ADD(k1_0, MUL(k_m1, k2[0]));
+}
+
+// launch 3: a[i] = k[i] dx - dy, b[i] = dy - k[i+1] dx (:354-365).  Periodic: k[i] = k1[i] + k_m1 k2[i]
+// for i < n-2 (:559-561), rows n-2 and n-1 of R already hold k.
+template <class T>
+__global__ void __launch_bounds__(256) spline_ab_kernel(const T* __restrict__ x, int n, const T* __restrict__ y, long long w,
+                                                        int periodic, const T* __restrict__ fac, const T* __restrict__ R,
+                                                        T* __restrict__ a, T* __restrict__ b) {
+    const T* k2 = fac + 4 * (size_t)n;
+    const long long chunks = (w + blockDim.x - 1) / blockDim.x;
+    const long long ntasks = chunks * ((n - 1 + kRowGroup - 1) / kRowGroup);
+    for (long long task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const RowTask t = row_task(task, chunks, w);
+        if (!t.live) continue;
+        const long long at0 = (long long)t.row * w + t.col;
+        T kv[kRowGroup + 1], yv[kRowGroup + 1];
+#pragma unroll
+        for (int j = 0; j <= kRowGroup; ++j) {
+            const int i = min(t.row + j, n - 1);
+            kv[j] = R[(long long)i * w + t.col];
+            yv[j] = __ldg(y + (long long)i * w + t.col);
+        }
+        if (periodic) {
+            const T k_m1 = R[(long long)(n - 2) * w + t.col];
+#pragma unroll
+            for (int j = 0; j <= kRowGroup; ++j)
+                if (t.row + j < n - 2) kv[j] = ADD(kv[j], MUL(k_m1, k2[t.row + j]));
+        }
+#pragma unroll
+        for (int j = 0; j < kRowGroup; ++j) {
+            const int i = t.row + j;
+            if (i >= n - 1) break;
+            const T dx = SUB(x[i + 1], x[i]), dy = SUB(yv[j + 1], yv[j]);
+            a[at0 + (long long)j * w] = SUB(MUL(kv[j], dx), dy);
+            b[at0 + (long long)j * w] = SUB(dy, MUL(kv[j + 1], dx));
+        }
     }
 }
 
@@ -338,7 +656,7 @@ __global__ void __launch_bounds__(128) spline_columns_individual_kernel(
 
 template <class T>
 size_t spline_scratch_elems(int64_t n, int64_t w, int bc_kind) {
-    return bc_kind == BC_INDIVIDUAL ? (size_t)n * (size_t)w : 4 * (size_t)n;
+    return bc_kind == BC_INDIVIDUAL ? (size_t)n * (size_t)w : 5 * (size_t)n + 4 + (size_t)n * (size_t)w;
 }
 
 template <class T>
@@ -359,10 +677,37 @@ cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w,
     if (bc_kind == BC_CLAMPED) l = r = Side<T>{SB_CLAMPED, (T)0};
     const int periodic = bc_kind == BC_PERIODIC;
     const Side<T> ls = specialize(l), rs = specialize(r);
-    spline_factor_kernel<T><<<1, 32, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, scratch);
+    spline_factor_kernel<T><<<1, kFacBlock, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, scratch);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (n >= 4) {
+        T* R = scratch + ((5 * (size_t)n + 3) & ~(size_t)3);
+        const long long chunks = (w + 255) / 256;
+        const long long cap = (long long)device_info().sm_count * 8;
+        const int rows = periodic ? (int)n - 1 : (int)n;
+        auto grid_for = [&](long long nrows) {
+            const long long tasks = chunks * ((nrows + kRowGroup - 1) / kRowGroup);
+            return (int)(tasks < cap ? tasks : cap);
+        };
+        spline_rhs_kernel<T><<<grid_for(rows), 256, 0, st>>>(x, (int)n, data, (long long)w, periodic, l, r, R, err);
+        count_launch();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        const int len = periodic ? (int)n - 2 : (int)n;
+        const size_t smem = (size_t)kRing * kRows * block * sizeof(T) + (size_t)(block / 32) * 2 * kRing * kRows * sizeof(FacRow<T>);
+        if (block == 32) spline_sweep_kernel<T, 32><<<grid, 32, smem, st>>>(len, (long long)w, scratch, R);
+        else spline_sweep_kernel<T, 128><<<grid, 128, smem, st>>>(len, (long long)w, scratch, R);
+        count_launch();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (periodic) {
+            spline_periodic_close_kernel<T><<<(int)chunks, 256, 0, st>>>(x, (int)n, (long long)w, scratch, R);
+            count_launch();
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+        spline_ab_kernel<T><<<grid_for(n - 1), 256, 0, st>>>(x, (int)n, data, (long long)w, periodic, scratch, R, a, b);
+        count_launch();
+        return cudaGetLastError();
+    }
     spline_columns_kernel<T><<<grid, block, 0, st>>>(x, (int)n, data, (long long)w, periodic, l, r, scratch, a, b, err);
     count_launch();
     return cudaGetLastError();

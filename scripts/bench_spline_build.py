@@ -1,0 +1,43 @@
+#!/usr/bin/env python3
+"""K6 timing: CubicSpline coefficient construction for a few table shapes (one JSON line each)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ndarray_interp_b200 import device as D  # noqa: E402
+
+SHAPES = [("c2", 4096, 1024, torch.float64), ("c5b-shard", 4096, 16384, torch.float32), ("wide", 512, 262144, torch.float32),
+          ("long", 65536, 64, torch.float64)]
+BC = {"NotAKnot": 0, "Natural": 1, "Periodic": 3}
+
+
+def main():
+    D.set_device(0)
+    only = sys.argv[1:]
+    for name, n, w, dt in SHAPES:
+        if only and name not in only:
+            continue
+        g = torch.cumsum(torch.rand(n, dtype=torch.float64, device="cuda") + 0.5, 0).to(dt)
+        y = torch.randn(n, w, dtype=dt, device="cuda")
+        y[-1] = y[0]                                        # so that Periodic is admissible
+        ip = D.DeviceInterp1D(g, y)
+        for bc, code in BC.items():
+            ip.spline_build(code)
+            torch.cuda.synchronize()
+            reps, t0 = 5, time.perf_counter()
+            for _ in range(reps):
+                st, _ = ip.spline_build(code)
+                assert st == 0
+            ms = (time.perf_counter() - t0) / reps * 1e3
+            es = 8 if dt == torch.float64 else 4
+            print(json.dumps({"shape": name, "rows": n, "columns": w, "dtype": str(dt), "boundary": bc, "ms": round(ms, 4),
+                              "algorithmic_GBps": round(es * (3 * n - 2) * w / ms / 1e6, 1)}))
+
+
+if __name__ == "__main__":
+    main()

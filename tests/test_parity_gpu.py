@@ -438,3 +438,12 @@ def test_f32_fast_division_edge_queries():
         d1 = data[:, 1, :].copy()
         st, ref, _ = O.interp1d_linear(gx, d1, qx, True)
         assert same(Interp1D.new_unchecked(gx, d1, Linear.new().extrapolate(True)).interp_array(qx), ref)
+
+
+def test_ddiv_selftest_sample():
+    """Hoisted<double>::div == __ddiv_rn on 2^28 pseudo-random operand pairs (all exponents and signs)"""
+    lib = L.require_device()
+    for seed in (1, 2026):
+        bad = C.c_uint64(123)
+        L.check(lib.ndi_selftest_ddiv(seed, 1 << 27, C.byref(bad)))
+        assert bad.value == 0, (seed, bad.value)
