@@ -387,6 +387,17 @@ def run_b200(args, wl, name):
             hi.interp_array_into(q_pin.numpy(), out_np)
     e2e_step()                                            # warm-up (workspace allocation)
     barrier()
+    # what the PCIe link gives a plain pinned device-to-host copy (the ceiling of any host-buffer API)
+    probe_dev = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
+    probe_pin = torch.empty(1 << 28, dtype=torch.uint8, pin_memory=True)
+    probe_pin.copy_(probe_dev, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        probe_pin.copy_(probe_dev, non_blocking=True)
+    torch.cuda.synchronize()
+    d2h_link_gbs = 4 * (1 << 28) / (time.perf_counter() - t0) / 1e9
+    del probe_dev, probe_pin
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
@@ -399,7 +410,9 @@ def run_b200(args, wl, name):
     c = 2 if wl["kind"] == "bilinear" else 1
     e2e = {"value": world * wl["q"] / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": s * c * wl["q"],
            "d2h_bytes_per_step": s * wl["w"] * wl["q"], "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-           "api": "Interp{1,2}D.interp_array_into -> ndi_interp*_{cubic,linear,bilinear} (host pointers, pinned)"}
+           "api": "Interp{1,2}D.interp_array_into -> ndi_interp*_{cubic,linear,bilinear} (host pointers, pinned)",
+           "d2h_link_GBps": d2h_link_gbs, "d2h_achieved_GBps": s * wl["w"] * wl["q"] / e2e_s / 1e9,
+           "note": "bounded by the PCIe device-to-host copy of the result rows (d2h_achieved vs d2h_link)"}
     # spot-check: the e2e result equals the device-resident result's oracle on a sample
     sampler.stop_flag = True
 
@@ -432,7 +445,9 @@ def run_b200(args, wl, name):
                        "l2": "working set per step (%.2f GB, output streamed once) exceeds the 126 MB L2; no explicit flush"
                              % (abytes / 1e9),
                        "tables": "replicated per GPU by NCCL broadcast; queries sharded, no collective in the timed region",
-                       "search_mode": args.search_mode},
+                       "search_mode": args.search_mode,
+                       "launches_per_step": int(launches) // max(args.steps, 1),
+                       "timed": "whole step (all launches of the step) with CUDA events on the launch stream"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(name), "algorithmic_bytes": abytes, "peak_source": peak_src,
                          "frac_of_nominal_8000": achieved / 8000.0},

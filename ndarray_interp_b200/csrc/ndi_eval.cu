@@ -333,8 +333,12 @@ __global__ void __launch_bounds__(kBlock) interp1d_cubic_kernel(const Eval1<T> p
 // ------------------------------------------------------------------------------------------------
 // K4: Bilinear::interp_into x batch (bilinear.rs:64-99)
 // ------------------------------------------------------------------------------------------------
+// Very thin rows (LPQ <= 2, e.g. C4: 8 f32 columns) are bound by gather latency: five resident blocks
+// (48 registers, a few spilled bytes) beat four (C4 0.589 -> 0.543 ms).  Wider rows are bound by
+// instruction issue and lose from the spills (C5a 2.28 -> 2.75 ms): four blocks (64 registers, no spills).
+// (Asking for one block only lets ptxas take 95 registers: two resident blocks, 3.36 ms.)
 template <class T, int V, int LPQ, bool PERM>
-__global__ void __launch_bounds__(kBlock) interp2d_bilinear_kernel(const Eval2<T> p) {
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (LPQ <= 2 ? 5 : 4) : 3) interp2d_bilinear_kernel(const Eval2<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar[2];
     const GridView<T> gx = make_grid_view<T>(p.gx, p.n, p.scx, smem_raw, &bar[0]);
