@@ -62,10 +62,10 @@ __device__ __forceinline__ void report_bad_unordered(unsigned long long* err, bo
 __device__ __forceinline__ bool shfl_b(bool v, int src) { return __shfl_sync(0xffffffffu, (int)v, src) != 0; }
 template <class T> __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// thin rows: tiles searched in lock step by one warp (TPW) and rounds whose gathers are issued
-// together (RB).  Tunable at build time for measurement.  Measured on B200 (profiles/r01): with the
-// bucket-table search the chains are short, and TPW = RB = 1 wins on every thin workload because
-// the registers saved buy occupancy (C3 0.37 vs 0.41 ms at TPW 2 / RB 4, C5a 3.7 vs 5.2 ms).
+// thin rows: tiles searched in lock step by one warp (TPW), tunable at build time for measurement.
+// Measured on B200 (profiles/r01): with the bucket-table search the chains are short, and one tile
+// per warp with one round of gathers in flight wins on every thin workload because the registers
+// saved buy occupancy (C3 0.37 vs 0.41 ms at 2 tiles / 4 rounds batched, C5a 3.7 vs 5.2 ms).
 #ifndef NDI_TPW_LINEAR
 #define NDI_TPW_LINEAR 1
 #endif
@@ -75,22 +75,16 @@ template <class T> __device__ __forceinline__ T shfl_t(T v, int src) { return __
 #ifndef NDI_TPW_BILINEAR
 #define NDI_TPW_BILINEAR 1
 #endif
-#ifndef NDI_RB_LINEAR
-#define NDI_RB_LINEAR 1
-#endif
-#ifndef NDI_RB_CUBIC
-#define NDI_RB_CUBIC 1
-#endif
-#ifndef NDI_RB_BILINEAR
-#define NDI_RB_BILINEAR 1
-#endif
 constexpr int kTilesLinear = NDI_TPW_LINEAR, kTilesCubic = NDI_TPW_CUBIC, kTilesBilinear = NDI_TPW_BILINEAR;
 
 // ------------------------------------------------------------------------------------------------
 // K3: Linear::interp_into x batch (linear.rs:73-98)
 // ------------------------------------------------------------------------------------------------
+#ifndef NDI_THIN_MINBLOCKS
+#define NDI_THIN_MINBLOCKS 0          // 0: leave the register budget to ptxas
+#endif
 template <class T, int V, int LPQ>
-__global__ void __launch_bounds__(kBlock) interp1d_linear_kernel(const Eval1<T> p) {
+__global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THIN_MINBLOCKS : 0) interp1d_linear_kernel(const Eval1<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     const GridView<T> g = make_grid_view<T>(p.grid, p.n, p.sc, smem_raw, &bar);
@@ -99,7 +93,7 @@ __global__ void __launch_bounds__(kBlock) interp1d_linear_kernel(const Eval1<T> 
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     for (long long task = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < p.ntasks; task += nwarps) {
         if constexpr (LPQ < 32) {
-            constexpr int TPW = kTilesLinear, QPR = 32 / LPQ, RB = LPQ < NDI_RB_LINEAR ? LPQ : NDI_RB_LINEAR;
+            constexpr int TPW = kTilesLinear, QPR = 32 / LPQ;
             const long long qbase0 = task * (32 * TPW);
             T x[TPW]; int idx[TPW]; T dx21[TPW], dxq[TPW]; bool skip[TPW]; Slope<T> slope[TPW];   // dx21/dxq: x1, x2 from the search
 #pragma unroll
@@ -128,28 +122,29 @@ __global__ void __launch_bounds__(kBlock) interp1d_linear_kernel(const Eval1<T> 
             for (int t = 0; t < TPW; ++t) {
                 const long long qbase = qbase0 + t * 32;
                 if (qbase >= p.nq) break;
+                // A tile whose queries all fall into one interval (dense sorted batches) gathers its two
+                // table rows once instead of once per round.
+                const int idx0 = __shfl_sync(0xffffffffu, idx[t], __ffs(__ballot_sync(0xffffffffu, !skip[t]) | 0x80000000u) - 1);
+                const bool one_interval = LPQ > 1 && __all_sync(0xffffffffu, skip[t] || idx[t] == idx0);
+                Vec<T, V> y1, y2;
+                if (one_interval && colok) {
+                    const T* row = p.data + (long long)idx0 * p.w + col;
+                    y1 = ld_table<T, V>(row);
+                    y2 = ld_table<T, V>(row + p.w);
+                }
 #pragma unroll
-                for (int r0 = 0; r0 < LPQ; r0 += RB) {
-                    Vec<T, V> y1[RB], y2[RB]; bool ok[RB]; Slope<T> sl[RB]; T dq[RB];
-#pragma unroll
-                    for (int j = 0; j < RB; ++j) {                                     // issue all gathers of the batch
-                        const int src = (r0 + j) * QPR + qsel;
-                        const int is = __shfl_sync(0xffffffffu, idx[t], src);
-                        sl[j] = slope[t].from_lane(src); dq[j] = shfl_t(dxq[t], src);
-                        ok[j] = !shfl_b(skip[t], src) && colok;
-                        if (ok[j]) {
+                for (int r = 0; r < LPQ; ++r) {
+                    const int src = r * QPR + qsel;
+                    const int is = __shfl_sync(0xffffffffu, idx[t], src);
+                    const Slope<T> sl = slope[t].from_lane(src);
+                    const T dq = shfl_t(dxq[t], src);
+                    if (!shfl_b(skip[t], src) && colok) {
+                        if (!one_interval) {
                             const T* row = p.data + (long long)is * p.w + col;
-                            y1[j] = ld_table<T, V>(row);
-                            y2[j] = ld_table<T, V>(row + p.w);
+                            y1 = ld_table<T, V>(row);
+                            y2 = ld_table<T, V>(row + p.w);
                         }
-                    }
-#pragma unroll
-                    for (int j = 0; j < RB; ++j) {
-                        if (ok[j]) {
-                            const int src = (r0 + j) * QPR + qsel;
-                            const Vec<T, V> res = lerp_vec<T, V>(y1[j], y2[j], sl[j], dq[j]);        // linear.rs:94-96
-                            st_stream<T, V>(p.out + (qbase + src) * p.w + col, res);
-                        }
+                        st_stream<T, V>(p.out + (qbase + src) * p.w + col, lerp_vec<T, V>(y1, y2, sl, dq));   // linear.rs:94-96
                     }
                 }
             }
@@ -219,7 +214,7 @@ __device__ __forceinline__ bool cubic_prepare(T& x, T g0, T gl, int mode) {
 }
 
 template <class T, int V, int LPQ>
-__global__ void __launch_bounds__(kBlock) interp1d_cubic_kernel(const Eval1<T> p) {
+__global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THIN_MINBLOCKS : 0) interp1d_cubic_kernel(const Eval1<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     const GridView<T> g = make_grid_view<T>(p.grid, p.n, p.sc, smem_raw, &bar);
@@ -229,7 +224,7 @@ __global__ void __launch_bounds__(kBlock) interp1d_cubic_kernel(const Eval1<T> p
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     for (long long task = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < p.ntasks; task += nwarps) {
         if constexpr (LPQ < 32) {
-            constexpr int TPW = kTilesCubic, QPR = 32 / LPQ, RB = LPQ < NDI_RB_CUBIC ? LPQ : NDI_RB_CUBIC;
+            constexpr int TPW = kTilesCubic, QPR = 32 / LPQ;
             const long long qbase0 = task * (32 * TPW);
             T x[TPW]; int idx[TPW]; T tq[TPW], omt[TPW], tt[TPW]; bool skip[TPW], bad[TPW];
 #pragma unroll
@@ -257,33 +252,35 @@ __global__ void __launch_bounds__(kBlock) interp1d_cubic_kernel(const Eval1<T> p
             for (int t = 0; t < TPW; ++t) {
                 const long long qbase = qbase0 + t * 32;
                 if (qbase >= p.nq) break;
+                // A tile whose queries all fall into one interval (dense sorted batches: C5b has 8192 queries
+                // per interval) gathers its four table rows once instead of once per round.
+                const int idx0 = __shfl_sync(0xffffffffu, idx[t], __ffs(__ballot_sync(0xffffffffu, !skip[t]) | 0x80000000u) - 1);
+                const bool one_interval = LPQ > 1 && __all_sync(0xffffffffu, skip[t] || idx[t] == idx0);
+                Vec<T, V> yl, yr, al, bl;
+                if (one_interval && colok) {
+                    const long long ro = (long long)idx0 * p.w + col;
+                    yl = ld_table<T, V>(p.data + ro);
+                    yr = ld_table<T, V>(p.data + ro + p.w);
+                    al = ld_table<T, V>(p.a + ro);
+                    bl = ld_table<T, V>(p.b + ro);
+                }
 #pragma unroll
-                for (int r0 = 0; r0 < LPQ; r0 += RB) {
-                    Vec<T, V> yl[RB], yr[RB], al[RB], bl[RB]; bool ok[RB]; T ts[RB], os[RB], tts[RB];
-#pragma unroll
-                    for (int j = 0; j < RB; ++j) {
-                        const int src = (r0 + j) * QPR + qsel;
-                        const int is = __shfl_sync(0xffffffffu, idx[t], src);
-                        ts[j] = shfl_t(tq[t], src); os[j] = shfl_t(omt[t], src); tts[j] = shfl_t(tt[t], src);
-                        ok[j] = !shfl_b(skip[t], src) && colok;
-                        if (ok[j]) {
+                for (int r = 0; r < LPQ; ++r) {
+                    const int src = r * QPR + qsel;
+                    const int is = __shfl_sync(0xffffffffu, idx[t], src);
+                    const T ts = shfl_t(tq[t], src), os = shfl_t(omt[t], src), tts = shfl_t(tt[t], src);
+                    if (!shfl_b(skip[t], src) && colok) {
+                        if (!one_interval) {
                             const long long ro = (long long)is * p.w + col;
-                            yl[j] = ld_table<T, V>(p.data + ro);
-                            yr[j] = ld_table<T, V>(p.data + ro + p.w);
-                            al[j] = ld_table<T, V>(p.a + ro);
-                            bl[j] = ld_table<T, V>(p.b + ro);
+                            yl = ld_table<T, V>(p.data + ro);
+                            yr = ld_table<T, V>(p.data + ro + p.w);
+                            al = ld_table<T, V>(p.a + ro);
+                            bl = ld_table<T, V>(p.b + ro);
                         }
-                    }
+                        Vec<T, V> res;
 #pragma unroll
-                    for (int j = 0; j < RB; ++j) {
-                        if (ok[j]) {
-                            const int src = (r0 + j) * QPR + qsel;
-                            Vec<T, V> res;
-#pragma unroll
-                            for (int e = 0; e < V; ++e)
-                                res.v[e] = cubic_point<T>(yl[j].v[e], yr[j].v[e], al[j].v[e], bl[j].v[e], ts[j], os[j], tts[j]);
-                            st_stream<T, V>(p.out + (qbase + src) * p.w + col, res);
-                        }
+                        for (int e = 0; e < V; ++e) res.v[e] = cubic_point<T>(yl.v[e], yr.v[e], al.v[e], bl.v[e], ts, os, tts);
+                        st_stream<T, V>(p.out + (qbase + src) * p.w + col, res);
                     }
                 }
             }
@@ -349,7 +346,7 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (LPQ <= 2 ? 5 : 4) : 
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     for (long long task = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < p.ntasks; task += nwarps) {
         if constexpr (LPQ < 32) {
-            constexpr int TPW = kTilesBilinear, QPR = 32 / LPQ, RB = LPQ < NDI_RB_BILINEAR ? LPQ : NDI_RB_BILINEAR;
+            constexpr int TPW = kTilesBilinear, QPR = 32 / LPQ;
             const long long qbase0 = task * (32 * TPW);
             T x[TPW], y[TPW]; int ix[TPW], iy[TPW];
             long long cell[TPW]; T ax[TPW], bx[TPW], ay[TPW], by[TPW]; bool skip[TPW];   // ax..by: x1, x2, y1, y2 from the search
@@ -391,32 +388,18 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (LPQ <= 2 ? 5 : 4) : 
                 const long long qbase = qbase0 + t * 32;
                 if (qbase >= p.nq) break;
 #pragma unroll
-                for (int r0 = 0; r0 < LPQ; r0 += RB) {
-                    Vec<T, V> z11[RB], z12[RB], z21[RB], z22[RB]; bool ok[RB]; Slope<T> ssx[RB], ssy[RB]; T sbx[RB], sby[RB];
-                    long long srow[RB];
-#pragma unroll
-                    for (int j = 0; j < RB; ++j) {
-                        const int src = (r0 + j) * QPR + qsel;
-                        const long long cs = __shfl_sync(0xffffffffu, cell[t], src);
-                        if constexpr (PERM) srow[j] = __shfl_sync(0xffffffffu, orow[t], src);
-                        else srow[j] = qbase + src;
-                        ssx[j] = slx[t].from_lane(src); sbx[j] = shfl_t(bx[t], src);
-                        ssy[j] = sly[t].from_lane(src); sby[j] = shfl_t(by[t], src);
-                        ok[j] = !shfl_b(skip[t], src) && colok;
-                        if (ok[j]) {
-                            const T* c0 = p.data + cs + col;
-                            z11[j] = ld_table<T, V>(c0);
-                            z12[j] = ld_table<T, V>(c0 + p.w);
-                            z21[j] = ld_table<T, V>(c0 + rowx);
-                            z22[j] = ld_table<T, V>(c0 + rowx + p.w);
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < RB; ++j) {
-                        if (ok[j]) {
-                            const Vec<T, V> res = bilerp_vec<T, V>(z11[j], z12[j], z21[j], z22[j], ssx[j], sbx[j], ssy[j], sby[j]);
-                            st_stream<T, V>(p.out + srow[j] * p.w + col, res);
-                        }
+                for (int r = 0; r < LPQ; ++r) {
+                    const int src = r * QPR + qsel;
+                    const long long cs = __shfl_sync(0xffffffffu, cell[t], src);
+                    const Slope<T> ssx = slx[t].from_lane(src), ssy = sly[t].from_lane(src);
+                    const T sbx = shfl_t(bx[t], src), sby = shfl_t(by[t], src);
+                    long long srow = qbase + src;
+                    if constexpr (PERM) srow = __shfl_sync(0xffffffffu, orow[t], src);
+                    if (!shfl_b(skip[t], src) && colok) {
+                        const T* c0 = p.data + cs + col;
+                        const Vec<T, V> z11 = ld_table<T, V>(c0), z12 = ld_table<T, V>(c0 + p.w);
+                        const Vec<T, V> z21 = ld_table<T, V>(c0 + rowx), z22 = ld_table<T, V>(c0 + rowx + p.w);
+                        st_stream<T, V>(p.out + srow * p.w + col, bilerp_vec<T, V>(z11, z12, z21, z22, ssx, sbx, ssy, sby));
                     }
                 }
             }
