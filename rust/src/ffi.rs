@@ -39,6 +39,8 @@ extern "C" {
 
     pub fn ndi_interp2d_create(dtype: i32, x: *const c_void, n: i64, y: *const c_void, m: i64, data: *const c_void, w: i64, flags: u32, out: *mut *mut ndi_interp2d) -> ndi_status;
     pub fn ndi_interp2d_destroy(h: *mut ndi_interp2d) -> ndi_status;
+    /// locality binning of query batches by table band: 0 auto, 1 off, 2 on (csrc/ndi_bin.cu)
+    pub fn ndi_interp2d_set_binning(h: *mut ndi_interp2d, mode: i32, band_rows: i32) -> ndi_status;
     pub fn ndi_interp2d_bilinear(h: *const ndi_interp2d, qx: *const c_void, qy: *const c_void, nq: i64, extrapolate: i32, out: *mut c_void, first_bad: *mut i64, bad_axis: *mut i32) -> ndi_status;
 }
 
