@@ -563,7 +563,8 @@ static Shape pick_shape(long long w, long long nq, int v, int tiles_per_warp) {
 
 template <class K>
 static cudaError_t prep_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    // static shared memory (barriers) counts against the 48 KB default as well
+    if (bytes > 40 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     return cudaSuccess;
 }
 
