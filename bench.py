@@ -42,6 +42,8 @@ WORKLOADS = {
                desc="Interp1D CubicSpline natural, x len 4096, data (4096,1024), 2^20 sorted queries, f64"),
     "c3": dict(kind="linear", dtype="f32", n=65536, w=16, q=1 << 24, extrap=True, sorted=False,
                desc="Interp1D Linear extrapolate, query (4096,4096) on non-uniform grid len 65536, data (65536,16), f32"),
+    "c3d": dict(kind="linear", dtype="f64", n=65536, w=16, q=1 << 24, extrap=True, sorted=False,
+                desc="as c3 with f64 tables (the reference's default element type)"),
     "c4": dict(kind="bilinear", dtype="f32", n=2048, m=2048, w=8, q=1 << 24, extrap=False, sorted=False,
                desc="Interp2D Bilinear, 2048x2048 grid, data (2048,2048,8), 16M random queries, f32, no extrapolation"),
     "c4x": dict(kind="bilinear", dtype="f32", n=2048, m=2048, w=8, q=1 << 24, extrap=True, sorted=False,

@@ -297,6 +297,7 @@ static ndi_status classify_grid(ndi_dtype dtype, const void* x_dev, int64_t n, W
 static ndi_status scan_fast_tables(ndi_dtype dtype, const void* data_dev, size_t count, Workspace* ws, int* fast) {
     *fast = 0;
     static const bool disabled = getenv("NDI_NO_FAST_DIV") != nullptr;
+    if (dtype == NDI_F64) { *fast = !disabled; return NDI_OK; }   // f64 checks every quotient itself (div_ok): no scan needed
     if (dtype != NDI_F32 || disabled) return NDI_OK;
     const int32_t one = 1;
     CK(cudaMemcpyAsync(ws->d_res, &one, sizeof(one), cudaMemcpyHostToDevice, ws->s[0]));
