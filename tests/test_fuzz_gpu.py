@@ -1,0 +1,68 @@
+"""Randomised shapes through every kernel of the path, bit for bit against the CPU oracle: table and
+batch sizes around the kernels' internal tile sizes (32 queries per tile, 2048 per binning chunk,
+8-row batches and 32-row matrix-row staging in the spline sweeps, 128/256-thread blocks, 4-row groups)
+where off-by-one mistakes in tails would live."""
+import numpy as np
+import pytest
+
+from ndarray_interp_b200 import _lib as L
+from ndarray_interp_b200.interp1d import BoundaryCondition, CubicSpline, Interp1D, Interp1DBuilder, Linear
+from ndarray_interp_b200.interp2d import Bilinear, Interp2D
+from oracle import oracle_py as O
+from test_parity_gpu import make_data, make_grid, make_queries, same
+
+pytestmark = pytest.mark.gpu
+
+EDGE_N = [2, 3, 4, 5, 8, 9, 31, 32, 33, 34, 40, 41, 63, 64, 65, 66, 97, 129, 257, 1025]
+EDGE_W = [1, 2, 3, 4, 5, 7, 8, 12, 16, 31, 32, 33, 63, 64, 100, 127, 128, 129, 255, 256, 257, 300]
+EDGE_Q = [1, 2, 31, 32, 33, 63, 64, 65, 255, 1000, 2047, 2048, 2049, 4097, 10000]
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_linear_and_bilinear(seed):
+    rng = np.random.default_rng(9000 + seed)
+    dt = [np.float32, np.float64, np.int32][seed % 3]
+    n, m = int(rng.choice(EDGE_N)), int(rng.choice(EDGE_N[:14]))
+    w, nq = int(rng.choice(EDGE_W)), int(rng.choice(EDGE_Q))
+    extrap = bool(seed & 1)
+    g = make_grid(rng, n, dt, ["uniform", "random", "exp"][seed % 3])
+    d1 = make_data(rng, (n, w), dt)
+    q = make_queries(rng, g, nq, dt, extrap)
+    st, ref, _ = O.interp1d_linear(g, d1, q, extrap)
+    assert st == O.ST_OK
+    assert same(Interp1D.new_unchecked(g, d1, Linear.new().extrapolate(extrap)).interp_array(q), ref)
+    gy = make_grid(rng, m, dt, ["random", "exp", "uniform"][seed % 3])
+    w2 = min(w, 64)
+    d2 = make_data(rng, (n, m, w2), dt)
+    qx, qy = make_queries(rng, g, nq, dt, extrap), make_queries(rng, gy, nq, dt, extrap)
+    st, ref, _, _ = O.interp2d_bilinear(g, gy, d2, qx, qy, extrap)
+    assert st == O.ST_OK
+    for mode, rows in [(L.BIN_OFF, 0), (L.BIN_ON, int(rng.choice([1, 2, 8])))]:
+        ip = Interp2D.new_unchecked(g, gy, d2, Bilinear.new().extrapolate(extrap))
+        L.check(L.load().ndi_interp2d_set_binning(ip._handle(), mode, rows))
+        assert same(ip.interp_array(qx, qy), ref), (mode, rows)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_spline_build_and_eval(seed):
+    rng = np.random.default_rng(7000 + seed)
+    dt = [np.float32, np.float64][seed % 2]
+    n = int(rng.choice([3, 4, 5, 6, 7, 8, 9, 10, 11, 32, 33, 34, 35, 36, 64, 65, 66, 67, 130, 259, 1030]))
+    w, nq = int(rng.choice(EDGE_W)), int(rng.choice(EDGE_Q))
+    bc = ["NotAKnot", "Natural", "Clamped", "Periodic"][seed % 4]
+    g = np.cumsum(rng.uniform(0.5, 1.5, n)).astype(dt)
+    y = rng.normal(size=(n, w)).astype(dt)
+    if bc == "Periodic":
+        y[-1] = y[0]
+    st, a_ref, b_ref = O.spline_build(g, y, {"kind": bc})
+    assert st == O.ST_OK
+    extrap = bool((seed >> 2) & 1)
+    strat = CubicSpline.new().extrapolate(extrap).boundary(getattr(BoundaryCondition, bc))
+    ip = Interp1DBuilder.new(y).x(g).strategy(strat).build()
+    a, b = ip.strategy.coefficients(ip)
+    assert same(a, a_ref) and same(b, b_ref)
+    q = np.sort(make_queries(rng, g, nq, dt, extrap)) if seed % 3 else make_queries(rng, g, nq, dt, extrap)
+    mode = 0 if not extrap else (2 if bc == "Periodic" else 1)
+    st, ref, _ = O.interp1d_cubic(g, y, a_ref, b_ref, q, mode)
+    assert st == O.ST_OK
+    assert same(ip.interp_array(q), ref)
