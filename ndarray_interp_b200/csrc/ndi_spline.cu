@@ -470,11 +470,17 @@ __global__ void __launch_bounds__(BLOCK) spline_sweep_kernel(int len, long long 
                 cp_async_commit();
                 cp_async_wait<kRing - 1>();
                 if (bb == 0) __syncwarp();
+                // all shared-memory reads of the batch first, then the chain: a step waits for its predecessor only
+                T rv[kRows], wv[kRows];
+#pragma unroll
+                for (int j = 0; j < kRows; ++j) {
+                    wv[j] = lds_elem<T>(facbuf + (buf * kSuper + bb * kRows + j) * kFacBytes + 2 * sizeof(T));
+                    rv[j] = lds_elem<T>(ring + (bb * kRows + j) * kSlot);
+                }
 #pragma unroll
                 for (int j = 0; j < kRows; ++j) {
                     if (j < left) {
-                        const T wl = lds_elem<T>(facbuf + (buf * kSuper + bb * kRows + j) * kFacBytes + 2 * sizeof(T));
-                        prev = SUB(lds_elem<T>(ring + (bb * kRows + j) * kSlot), MUL(wl, prev));   // :698
+                        prev = SUB(rv[j], MUL(wv[j], prev));                          // :698
                         if (live) *wp = prev;
                     }
                     wp += w;
@@ -521,12 +527,17 @@ __global__ void __launch_bounds__(BLOCK) spline_sweep_kernel(int len, long long 
                 cp_async_commit();
                 cp_async_wait<kRing - 1>();
                 if (bb == 0) __syncwarp();
+                T rv[kRows], uv[kRows], mv[kRows], iv[kRows];
+#pragma unroll
+                for (int j = 0; j < kRows; ++j) {
+                    const unsigned fa = facbuf + (buf * kSuper + bb * kRows + j) * kFacBytes;
+                    uv[j] = lds_elem<T>(fa); mv[j] = lds_elem<T>(fa + sizeof(T)); iv[j] = lds_elem<T>(fa + 3 * sizeof(T));
+                    rv[j] = lds_elem<T>(ring + (bb * kRows + j) * kSlot);
+                }
 #pragma unroll
                 for (int j = 0; j < kRows; ++j) {
                     if (j < left) {
-                        const unsigned fa = facbuf + (buf * kSuper + bb * kRows + j) * kFacBytes;
-                        const T up = lds_elem<T>(fa), mid = lds_elem<T>(fa + sizeof(T)), rmid = lds_elem<T>(fa + 3 * sizeof(T));
-                        k = Hoisted<T>::div(SUB(lds_elem<T>(ring + (bb * kRows + j) * kSlot), MUL(up, k)), mid, rmid);   // :716
+                        k = Hoisted<T>::div(SUB(rv[j], MUL(uv[j], k)), mv[j], iv[j]);  // :716
                         if (live) *wp = k;
                     }
                     wp -= w;
