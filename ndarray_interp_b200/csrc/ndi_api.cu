@@ -664,12 +664,24 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
         using T = decltype(tag);
         const size_t coef_bytes = (size_t)(h->n - 1) * h->w * sizeof(T);
         T *a = nullptr, *b = nullptr, *scratch = nullptr, *lv = nullptr, *rv = nullptr;
-        int32_t *lk = nullptr, *rk = nullptr;
+        int32_t *lk = nullptr, *rk = nullptr, *pos = nullptr;
+        // Individual: group the columns by the kinds of their two boundary rows (what decides the matrix)
+        std::vector<int32_t> pos_host;
+        int64_t group_count[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (bc_kind == NDI_BC_INDIVIDUAL) {
+            auto variant = [](int32_t k) { return k == NDI_SB_NOT_A_KNOT ? 0 : ((k == NDI_SB_FIRST_DERIV || k == NDI_SB_CLAMPED) ? 1 : 2); };
+            pos_host.resize((size_t)h->w);
+            for (int64_t c = 0; c < h->w; ++c) ++group_count[3 * variant(left_kind[c]) + variant(right_kind[c])];
+            int64_t next[9], acc = 0;
+            for (int g = 0; g < 9; ++g) { next[g] = acc; acc += group_count[g]; }
+            for (int64_t c = 0; c < h->w; ++c) pos_host[(size_t)c] = (int32_t)next[3 * variant(left_kind[c]) + variant(right_kind[c])]++;
+        }
         // everything comes from the stream-ordered pool (device_info() keeps freed blocks cached), so a
         // rebuild does not pay cudaMalloc / cudaFree
         cudaStream_t bs = ws->s[0];
         auto cleanup = [&](bool keep) {
             cudaFreeAsync(scratch, bs); cudaFreeAsync(lv, bs); cudaFreeAsync(rv, bs); cudaFreeAsync(lk, bs); cudaFreeAsync(rk, bs);
+            cudaFreeAsync(pos, bs);
             if (!keep) { cudaFreeAsync(a, bs); cudaFreeAsync(b, bs); }
             cudaGetLastError();
         };
@@ -685,9 +697,11 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
                 CK(cudaMemcpyAsync(rk, right_kind, h->w * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
                 CK(cudaMemcpyAsync(lv, left_val, h->w * sizeof(T), cudaMemcpyHostToDevice, bs));
                 CK(cudaMemcpyAsync(rv, right_val, h->w * sizeof(T), cudaMemcpyHostToDevice, bs));
+                CK(cudaMallocAsync((void**)&pos, h->w * sizeof(int32_t), bs));
+                CK(cudaMemcpyAsync(pos, pos_host.data(), h->w * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
             }
             CK(cudaMemsetAsync(ws->d_err, 0xff, sizeof(uint64_t), bs));
-            CK(launch_spline_build<T>((const T*)h->x, h->n, (const T*)h->data, h->w, bc_kind, lk, lv, rk, rv, a, b, scratch, ws->d_err, bs));
+            CK(launch_spline_build<T>((const T*)h->x, h->n, (const T*)h->data, h->w, bc_kind, lk, lv, rk, rv, pos, group_count, a, b, scratch, ws->d_err, bs));
             CK(cudaMemcpyAsync(ws->h_pin, ws->d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, bs));
             CK(cudaStreamSynchronize(bs));
             return NDI_OK;

@@ -98,13 +98,16 @@ template <class T>
 cudaError_t launch_build_lut(const T* x, int64_t n, double g0d, double scale, int nb, void* lut_dev, cudaStream_t st);
 
 // ---- spline construction (ndi_spline.cu) -----------------------------------------------------
-// Builds a, b ((n-1) x w each) on the device.  For bc_kind == INDIVIDUAL the four arrays are
-// device arrays of w entries.  scratch: n*w elements for INDIVIDUAL, else 4*n elements.
+// Builds a, b ((n-1) x w each) on the device.  For bc_kind == INDIVIDUAL the four boundary arrays are
+// device arrays of w entries; pos (device, w entries) gives every column its position when the
+// columns are grouped by (left kind, right kind) after specialisation, group_count (host, 9
+// entries, group = 3 * variant(left) + variant(right), variant: NotAKnot 0, FirstDeriv 1,
+// SecondDeriv 2) the size of each group.  scratch: spline_scratch_elems() elements.
 // err: device word, set to the first column with a periodic mismatch.
 template <class T>
 cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w, int bc_kind, const int32_t* lk,
-                                const T* lv, const int32_t* rk, const T* rv, T* a, T* b, T* scratch,
-                                unsigned long long* err, cudaStream_t st);
+                                const T* lv, const int32_t* rk, const T* rv, const int32_t* pos, const int64_t* group_count,
+                                T* a, T* b, T* scratch, unsigned long long* err, cudaStream_t st);
 template <class T>
 size_t spline_scratch_elems(int64_t n, int64_t w, int bc_kind);
 

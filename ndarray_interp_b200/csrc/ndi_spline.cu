@@ -149,11 +149,18 @@ __device__ __forceinline__ FacRow<T> ld_fac(const FacRow<T>* p) {
     }
     return f;
 }
+// Individual boundaries: the matrix differs between columns only through the KIND of the two boundary
+// rows (three kinds each after specialize()), so there are at most nine matrices.  Block g = 3*l + r
+// factorises the one with left kind kIndKinds[l] and right kind kIndKinds[r] into fac + g * fac_stride.
+__constant__ int kIndKinds[3] = {SB_NAK, SB_FIRST, SB_SECOND};
+__host__ __device__ inline int ind_variant(int specialized_kind) { return specialized_kind == SB_NAK ? 0 : (specialized_kind == SB_FIRST ? 1 : 2); }
+
 template <class T>
 __global__ void __launch_bounds__(kFacBlock) spline_factor_kernel(const T* __restrict__ x, int n, int periodic, int lk, int rk,
-                                                                  T* __restrict__ fac) {
+                                                                  T* __restrict__ fac, size_t fac_stride) {
     __shared__ T su[kFacTile], sm[kFacTile], sl[kFacTile];
     __shared__ T carry[2];
+    if (gridDim.x > 1) { lk = kIndKinds[blockIdx.x / 3]; rk = kIndKinds[blockIdx.x % 3]; fac += blockIdx.x * fac_stride; }
     FacRow<T>* rows = reinterpret_cast<FacRow<T>*>(fac);
     T* k2 = fac + 4 * (size_t)n;
     const bool nak3 = !periodic && n == 3 && lk == SB_NAK && rk == SB_NAK;
@@ -359,8 +366,10 @@ __device__ __forceinline__ RowTask row_task(long long task, long long chunks, lo
 template <class T>
 __global__ void __launch_bounds__(256) spline_rhs_kernel(const T* __restrict__ x, int n, const T* __restrict__ y, long long w,
                                                          int periodic, Side<T> left, Side<T> right, T* __restrict__ R,
-                                                         unsigned long long* err) {
-    const Side<T> l = specialize(left), r = specialize(right);
+                                                         unsigned long long* err, const int32_t* __restrict__ lks = nullptr,
+                                                         const T* __restrict__ lvs = nullptr, const int32_t* __restrict__ rks = nullptr,
+                                                         const T* __restrict__ rvs = nullptr, const int32_t* __restrict__ pos = nullptr) {
+    Side<T> l = specialize(left), r = specialize(right);
     const T three = (T)3;
     const long long chunks = (w + blockDim.x - 1) / blockDim.x;
     const int rows = periodic ? n - 1 : n;
@@ -397,11 +406,13 @@ __global__ void __launch_bounds__(256) spline_rhs_kernel(const T* __restrict__ x
                     v = MUL(ADD(MUL(slope_2, dx_1), MUL(slope_1, dx_2)), three);      // :531-532
                 }
             } else if (i == 0) {
+                if (lks) l = specialize(Side<T>{lks[t.col], lvs[t.col]});             // Individual: this column's own boundary
                 v = rhs_left<T>(x, l, Y(0), Y(1), Y(2));
             } else {
+                if (rks) r = specialize(Side<T>{rks[t.col], rvs[t.col]});
                 v = rhs_right<T>(x, n, r, Y(n - 1), Y(n - 2), Y(n - 3));
             }
-            R[(long long)i * w + t.col] = v;
+            R[(long long)i * w + (pos ? pos[t.col] : t.col)] = v;                     // Individual: columns grouped by matrix
         }
     }
 }
@@ -421,16 +432,33 @@ __device__ __forceinline__ void cp_async_fac(unsigned smem_addr, const FacRow<T>
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr + 16), "l"(reinterpret_cast<const char*>(src) + 16) : "memory");
 }
 
+// Individual boundaries sweep all (up to nine) groups of columns in ONE launch: the groups are
+// independent and each is bound by its chain latency, not by throughput.
+struct SweepGroups {
+    int ngroups;                 // 0: one group = all ncols columns, factorisation at fac
+    int first_block[10];         // blocks [first_block[g], first_block[g+1]) sweep group g
+    long long col_off[9], count[9];
+    unsigned long long fac_stride;
+};
+
 template <class T, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) spline_sweep_kernel(int len, long long w, const T* __restrict__ fac, T* __restrict__ R) {
+__global__ void __launch_bounds__(BLOCK) spline_sweep_kernel(int len, long long w, long long ncols, const T* __restrict__ fac,
+                                                             T* __restrict__ R, const SweepGroups groups) {
     extern __shared__ __align__(32) unsigned char ring_raw[];
     constexpr int kSuper = kRing * kRows;                     // rows per outer iteration
     static_assert(kSuper == 32, "one matrix row per lane and outer iteration");
     constexpr unsigned kSlot = BLOCK * sizeof(T);
     constexpr unsigned kFacBytes = sizeof(FacRow<T>);
-    const long long c0 = (long long)blockIdx.x * BLOCK + threadIdx.x;
-    const bool live = c0 < w;                                 // dead lanes shadow the last column (they stage matrix rows too)
-    const long long c = live ? c0 : w - 1;
+    int block = blockIdx.x;
+    if (groups.ngroups) {
+        int g = 0;
+        while (g + 1 < groups.ngroups && block >= groups.first_block[g + 1]) ++g;
+        block -= groups.first_block[g];
+        ncols = groups.count[g]; R += groups.col_off[g]; fac += g * groups.fac_stride;
+    }
+    const long long c0 = (long long)block * BLOCK + threadIdx.x;
+    const bool live = c0 < ncols;                             // dead lanes shadow the last column (they stage matrix rows too)
+    const long long c = live ? c0 : ncols - 1;                // w: row stride of R, ncols: columns this launch sweeps
     const int lane = threadIdx.x & 31;
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(ring_raw);
     const unsigned ring = smem0 + threadIdx.x * (unsigned)sizeof(T);
@@ -571,7 +599,7 @@ __global__ void __launch_bounds__(256) spline_periodic_close_kernel(const T* __r
 template <class T>
 __global__ void __launch_bounds__(256) spline_ab_kernel(const T* __restrict__ x, int n, const T* __restrict__ y, long long w,
                                                         int periodic, const T* __restrict__ fac, const T* __restrict__ R,
-                                                        T* __restrict__ a, T* __restrict__ b) {
+                                                        T* __restrict__ a, T* __restrict__ b, const int32_t* __restrict__ pos = nullptr) {
     const T* k2 = fac + 4 * (size_t)n;
     const long long chunks = (w + blockDim.x - 1) / blockDim.x;
     const long long ntasks = chunks * ((n - 1 + kRowGroup - 1) / kRowGroup);
@@ -583,7 +611,7 @@ __global__ void __launch_bounds__(256) spline_ab_kernel(const T* __restrict__ x,
 #pragma unroll
         for (int j = 0; j <= kRowGroup; ++j) {
             const int i = min(t.row + j, n - 1);
-            kv[j] = R[(long long)i * w + t.col];
+            kv[j] = R[(long long)i * w + (pos ? pos[t.col] : t.col)];
             yv[j] = __ldg(y + (long long)i * w + t.col);
         }
         if (periodic) {
@@ -667,19 +695,66 @@ __global__ void __launch_bounds__(128) spline_columns_individual_kernel(
 
 template <class T>
 size_t spline_scratch_elems(int64_t n, int64_t w, int bc_kind) {
-    return bc_kind == BC_INDIVIDUAL ? (size_t)n * (size_t)w : 5 * (size_t)n + 4 + (size_t)n * (size_t)w;
+    // factorisation(s) (FacRow[n] + k2[n], padded) + the matrix R; Individual: nine factorisations (n < 4: a diagonal per column)
+    const size_t fac = (5 * (size_t)n + 3) & ~(size_t)3;
+    if (bc_kind == BC_INDIVIDUAL) return n < 4 ? (size_t)n * (size_t)w : 9 * fac + (size_t)n * (size_t)w;
+    return fac + (size_t)n * (size_t)w;
 }
 
 template <class T>
 cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w, int bc_kind, const int32_t* lk,
-                                const T* lv, const int32_t* rk, const T* rv, T* a, T* b, T* scratch,
-                                unsigned long long* err, cudaStream_t st) {
+                                const T* lv, const int32_t* rk, const T* rv, const int32_t* pos, const int64_t* group_count,
+                                T* a, T* b, T* scratch, unsigned long long* err, cudaStream_t st) {
     if (w <= 0) return cudaSuccess;
     // few columns: small blocks so that more SMs take part; many columns: 128-thread blocks
     const int block = (w <= 32ll * 2 * device_info().sm_count) ? 32 : 128;
     const int grid = (int)((w + block - 1) / block);
+    const size_t fac_elems = (5 * (size_t)n + 3) & ~(size_t)3;
+    const long long chunks = (w + 255) / 256;
+    const long long cap = (long long)device_info().sm_count * 8;
+    auto grid_for = [&](long long nrows) {
+        const long long tasks = chunks * ((nrows + kRowGroup - 1) / kRowGroup);
+        return (int)(tasks < cap ? tasks : cap);
+    };
+    auto sweep = [&](int len, const T* fac, T* Rm, const int64_t* counts) -> cudaError_t {
+        // few columns: small blocks so that more SMs take part; many columns: 128-thread blocks
+        const int blk = (w <= 32ll * 2 * device_info().sm_count) ? 32 : 128;
+        SweepGroups sg = {};
+        int nblocks = (int)((w + blk - 1) / blk);
+        if (counts) {
+            sg.ngroups = 9; sg.fac_stride = fac_elems;
+            long long off = 0; int first = 0;
+            for (int g = 0; g < 9; ++g) {
+                sg.first_block[g] = first; sg.col_off[g] = off; sg.count[g] = counts[g];
+                first += (int)((counts[g] + blk - 1) / blk); off += counts[g];
+            }
+            sg.first_block[9] = first;
+            nblocks = first;
+        }
+        const size_t smem = (size_t)kRing * kRows * blk * sizeof(T) + (size_t)(blk / 32) * 2 * kRing * kRows * sizeof(FacRow<T>);
+        if (blk == 32) spline_sweep_kernel<T, 32><<<nblocks, 32, smem, st>>>(len, (long long)w, (long long)w, fac, Rm, sg);
+        else spline_sweep_kernel<T, 128><<<nblocks, 128, smem, st>>>(len, (long long)w, (long long)w, fac, Rm, sg);
+        count_launch();
+        return cudaGetLastError();
+    };
     if (bc_kind == BC_INDIVIDUAL) {
-        spline_columns_individual_kernel<T><<<grid, block, 0, st>>>(x, (int)n, data, (long long)w, lk, lv, rk, rv, a, b, scratch);
+        if (n < 4 || !pos || !group_count) {                 // the 3-point special cases: one factorisation per column
+            spline_columns_individual_kernel<T><<<grid, block, 0, st>>>(x, (int)n, data, (long long)w, lk, lv, rk, rv, a, b, scratch);
+            count_launch();
+            return cudaGetLastError();
+        }
+        // columns grouped by (left kind, right kind): nine shared-matrix builds in the same three launches
+        T* R = scratch + 9 * fac_elems;
+        spline_factor_kernel<T><<<9, kFacBlock, 0, st>>>(x, (int)n, 0, 0, 0, scratch, fac_elems);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        spline_rhs_kernel<T><<<grid_for(n), 256, 0, st>>>(x, (int)n, data, (long long)w, 0, Side<T>{SB_NAK, (T)0}, Side<T>{SB_NAK, (T)0}, R, err,
+                                                          lk, lv, rk, rv, pos);
+        count_launch();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = sweep((int)n, scratch, R, group_count)) != cudaSuccess) return e;
+        spline_ab_kernel<T><<<grid_for(n - 1), 256, 0, st>>>(x, (int)n, data, (long long)w, 0, scratch, R, a, b, pos);
         count_launch();
         return cudaGetLastError();
     }
@@ -688,28 +763,17 @@ cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w,
     if (bc_kind == BC_CLAMPED) l = r = Side<T>{SB_CLAMPED, (T)0};
     const int periodic = bc_kind == BC_PERIODIC;
     const Side<T> ls = specialize(l), rs = specialize(r);
-    spline_factor_kernel<T><<<1, kFacBlock, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, scratch);
+    spline_factor_kernel<T><<<1, kFacBlock, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, scratch, 0);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (n >= 4) {
-        T* R = scratch + ((5 * (size_t)n + 3) & ~(size_t)3);
-        const long long chunks = (w + 255) / 256;
-        const long long cap = (long long)device_info().sm_count * 8;
+        T* R = scratch + fac_elems;
         const int rows = periodic ? (int)n - 1 : (int)n;
-        auto grid_for = [&](long long nrows) {
-            const long long tasks = chunks * ((nrows + kRowGroup - 1) / kRowGroup);
-            return (int)(tasks < cap ? tasks : cap);
-        };
         spline_rhs_kernel<T><<<grid_for(rows), 256, 0, st>>>(x, (int)n, data, (long long)w, periodic, l, r, R, err);
         count_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        const int len = periodic ? (int)n - 2 : (int)n;
-        const size_t smem = (size_t)kRing * kRows * block * sizeof(T) + (size_t)(block / 32) * 2 * kRing * kRows * sizeof(FacRow<T>);
-        if (block == 32) spline_sweep_kernel<T, 32><<<grid, 32, smem, st>>>(len, (long long)w, scratch, R);
-        else spline_sweep_kernel<T, 128><<<grid, 128, smem, st>>>(len, (long long)w, scratch, R);
-        count_launch();
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = sweep(periodic ? (int)n - 2 : (int)n, scratch, R, nullptr)) != cudaSuccess) return e;
         if (periodic) {
             spline_periodic_close_kernel<T><<<(int)chunks, 256, 0, st>>>(x, (int)n, (long long)w, scratch, R);
             count_launch();
@@ -725,11 +789,11 @@ cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w,
 }
 
 template cudaError_t launch_spline_build<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*,
-                                                const float*, const int32_t*, const float*, float*, float*, float*,
-                                                unsigned long long*, cudaStream_t);
+                                                const float*, const int32_t*, const float*, const int32_t*, const int64_t*,
+                                                float*, float*, float*, unsigned long long*, cudaStream_t);
 template cudaError_t launch_spline_build<double>(const double*, int64_t, const double*, int64_t, int, const int32_t*,
-                                                 const double*, const int32_t*, const double*, double*, double*,
-                                                 double*, unsigned long long*, cudaStream_t);
+                                                 const double*, const int32_t*, const double*, const int32_t*, const int64_t*,
+                                                 double*, double*, double*, unsigned long long*, cudaStream_t);
 template size_t spline_scratch_elems<float>(int64_t, int64_t, int);
 template size_t spline_scratch_elems<double>(int64_t, int64_t, int);
 

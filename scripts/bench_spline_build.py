@@ -6,6 +6,7 @@ import sys
 import time
 
 import numpy as np
+import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,7 +14,7 @@ from ndarray_interp_b200 import device as D  # noqa: E402
 
 SHAPES = [("c2", 4096, 1024, torch.float64), ("c5b-shard", 4096, 16384, torch.float32), ("wide", 512, 262144, torch.float32),
           ("long", 65536, 64, torch.float64)]
-BC = {"NotAKnot": 0, "Natural": 1, "Periodic": 3}
+BC = {"NotAKnot": 0, "Natural": 1, "Periodic": 3, "Individual": 4}
 
 
 def main():
@@ -26,12 +27,17 @@ def main():
         y = torch.randn(n, w, dtype=dt, device="cuda")
         y[-1] = y[0]                                        # so that Periodic is admissible
         ip = D.DeviceInterp1D(g, y)
+        rng = np.random.default_rng(0)
+        ndt = np.float64 if dt == torch.float64 else np.float32
+        ind = (rng.integers(0, 5, w).astype(np.int32), rng.normal(size=w).astype(ndt),
+               rng.integers(0, 5, w).astype(np.int32), rng.normal(size=w).astype(ndt))
         for bc, code in BC.items():
-            ip.spline_build(code)
+            extra = ind if bc == "Individual" else ()
+            ip.spline_build(code, *extra)
             torch.cuda.synchronize()
             reps, t0 = 5, time.perf_counter()
             for _ in range(reps):
-                st, _ = ip.spline_build(code)
+                st, _ = ip.spline_build(code, *extra)
                 assert st == 0
             ms = (time.perf_counter() - t0) / reps * 1e3
             es = 8 if dt == torch.float64 else 4

@@ -2,7 +2,7 @@
 # round-1 evidence run: tests, every workload's bench line, the reference arm, launch list and ncu captures
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/final_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/final_pytest.log
-for WL in c2 c1 c3 c4 c4x c5a c5b; do
+for WL in c2 c1 c3 c3d c4 c4x c5a c5b; do
   timeout 900 python bench.py --workload $WL --steps 30 --warmup 5 > gpurun_out/final_$WL.json 2> gpurun_out/final_$WL.err || tail -c 300 gpurun_out/final_$WL.err
   python -c "
 import json
@@ -27,4 +27,5 @@ cap c4_bilinear c4 interp2d_bilinear 4 X=1
 cap c5a_bilinear_binned c5a interp2d_bilinear 4 X=1
 cap c5a_bin_scatter c5a bin_scatter 4 X=1
 cap c5b_cubic c5b interp1d_cubic 4 X=1
+timeout 300 python scripts/bench_spline_build.py > gpurun_out/final_spline_build.jsonl 2>&1
 ls -la gpurun_out/ncu_*.txt

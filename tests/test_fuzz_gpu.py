@@ -66,3 +66,33 @@ def test_fuzz_spline_build_and_eval(seed):
     st, ref, _ = O.interp1d_cubic(g, y, a_ref, b_ref, q, mode)
     assert st == O.ST_OK
     assert same(ip.interp_array(q), ref)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_individual_boundaries(seed):
+    """per-column boundaries: columns are grouped by the kinds of their boundary rows (nine shared
+    matrices); group sizes from empty to all columns, around the block sizes of the sweeps"""
+    from ndarray_interp_b200.interp1d import RowBoundary, SingleBoundary
+    rng = np.random.default_rng(5000 + seed)
+    dt = [np.float32, np.float64][seed % 2]
+    n = int(rng.choice([4, 5, 9, 33, 34, 65, 259]))
+    w = int(rng.choice([1, 2, 9, 31, 32, 33, 129, 300, 1000]))
+    kinds = ["NotAKnot", "Natural", "Clamped", "FirstDeriv", "SecondDeriv"]
+    allowed = kinds if seed % 3 else kinds[: 1 + seed % 5]          # some runs use few kinds: large and empty groups
+    g = np.cumsum(rng.uniform(0.5, 1.5, n)).astype(dt)
+    y = rng.normal(size=(n, w)).astype(dt)
+
+    def sb(k, v):
+        return (SingleBoundary.FirstDeriv(v) if k == "FirstDeriv" else SingleBoundary.SecondDeriv(v)
+                if k == "SecondDeriv" else getattr(SingleBoundary, k))
+    rows, spec = [], []
+    for c in range(w):
+        lk, rk = allowed[rng.integers(0, len(allowed))], allowed[rng.integers(0, len(allowed))]
+        lv, rv = float(rng.normal()), float(rng.normal())
+        rows.append(RowBoundary.Mixed(sb(lk, lv), sb(rk, rv)))
+        spec.append({"kind": "Mixed", "left": {"kind": lk, "value": lv}, "right": {"kind": rk, "value": rv}})
+    st, a_ref, b_ref = O.spline_build(g, y, {"kind": "Individual", "rows": spec})
+    assert st == O.ST_OK
+    ip = Interp1DBuilder.new(y).x(g).strategy(CubicSpline.new().boundary(BoundaryCondition.Individual([rows]))).build()
+    a, b = ip.strategy.coefficients(ip)
+    assert same(a, a_ref) and same(b, b_ref)
