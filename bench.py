@@ -389,6 +389,15 @@ def run_b200(args, wl, name):
     ms_max = float(t.item())
     ms_per_step = ms_max / args.steps
     value = world * wl["q"] / (ms_per_step * 1e-3)
+    # per-step distribution (median and best), outside the headline region
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(min(args.steps, 50) + 1)]
+    evs[0].record()
+    for i in range(1, len(evs)):
+        step()
+        evs[i].record()
+    torch.cuda.synchronize()
+    per_step = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1))
+    step_stats = {"median_ms": per_step[len(per_step) // 2], "best_ms": per_step[0], "worst_ms": per_step[-1], "n": len(per_step)}
 
     # ---- end to end through the host-array API (pinned host buffers, H2D + D2H in the timed region) ----
     ndt = np.float32 if wl["dtype"] == "f32" else np.float64
@@ -488,6 +497,7 @@ def run_b200(args, wl, name):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(name), "algorithmic_bytes": abytes, "peak_source": peak_src,
                          "frac_of_nominal_8000": achieved / 8000.0},
+            "per_step": step_stats,
             "cpu_baseline": cpu,
             "spline_build": spline_build,
             "e2e": e2e,
