@@ -282,4 +282,22 @@ cudaError_t launch_selftest_ddiv(uint64_t seed, int blocks, int per_thread, unsi
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tail of the scalar / tiny-batch latency path: hands the error word to the host through mapped pinned
+// memory, re-arms it, and raises the completion flag the host is spinning on (no driver synchronisation).
+// ------------------------------------------------------------------------------------------------
+__global__ void publish_kernel(unsigned long long* d_err, volatile unsigned long long* h_err,
+                               volatile unsigned long long* h_flag, unsigned long long seq) {
+    *h_err = *d_err;
+    *d_err = ~0ull;
+    __threadfence_system();
+    *h_flag = seq;
+}
+cudaError_t launch_publish(unsigned long long* d_err, void* h_err, void* h_flag, unsigned long long seq, cudaStream_t st) {
+    publish_kernel<<<1, 1, 0, st>>>(d_err, static_cast<volatile unsigned long long*>(h_err),
+                                    static_cast<volatile unsigned long long*>(h_flag), seq);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace ndi

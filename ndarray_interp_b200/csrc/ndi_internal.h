@@ -86,6 +86,8 @@ cudaError_t launch_selftest_fdiv(uint32_t a_mant_begin, uint32_t a_mant_count, i
 
 cudaError_t launch_selftest_ddiv(uint64_t seed, int blocks, int per_thread, unsigned long long* mismatches_dev, cudaStream_t st);
 
+cudaError_t launch_publish(unsigned long long* d_err, void* h_err, void* h_flag, unsigned long long seq, cudaStream_t st);
+
 // ---- grid checks (ndi_grid.cu) -----------------------------------------------------------
 // result[0] = Monotonic enum, result[1] = 1 when the even-spacing guess hits on every cell
 template <class T>
