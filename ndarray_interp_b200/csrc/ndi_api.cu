@@ -103,9 +103,12 @@ static ndi_status dispatch_float(ndi_dtype d, F&& f) {
 
 // ---- thread-local workspace --------------------------------------------------------------------------
 constexpr size_t kChunkBytes = 64ull << 20;    // output bytes per pipeline chunk
+#ifndef NDI_TINY_KB
+#define NDI_TINY_KB 256
+#endif
 constexpr size_t kSmallBytes = 256ull << 10;   // outputs up to this size take the single-sync path
-constexpr size_t kTinyBytes = 16ull << 10;     // ... and up to this size the kernel reads / writes pinned host memory directly
-constexpr size_t kTinyQueryBytes = 4ull << 10;
+constexpr size_t kTinyBytes = NDI_TINY_KB * 1024ull;     // ... and up to this size the kernel reads / writes pinned host memory directly
+constexpr size_t kTinyQueryBytes = NDI_TINY_KB * 1024ull;
 
 struct Workspace {
     bool ready = false;
