@@ -13,6 +13,10 @@
 // All per-call state lives in a thread-local workspace, so one handle can be used from many
 // threads at once (the reference's &self methods are called from rayon workers).
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <thread>
+#include <unordered_map>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -120,6 +124,8 @@ struct Workspace {
     int32_t* d_res = nullptr;                 // 2 words (grid classify result)
     uint32_t* d_scr = nullptr;                // grid classify scratch
     unsigned char* h_pin = nullptr; size_t h_pin_cap = 0;   // pinned: [err word, flag | small outputs | tiny queries]
+    unsigned char* h_stage[3] = {nullptr, nullptr, nullptr};   // pinned staging for pageable outputs (lazy)
+    cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};
     unsigned long long seq = 0;               // completion counter of the tiny-batch path
     bool err_armed = false;                   // d_err[1] holds ~0 (re-armed by publish_kernel)
 };
@@ -150,6 +156,69 @@ static ndi_status grow(void** p, size_t* cap, size_t need) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
     *cap = want;
     return NDI_OK;
+}
+
+// ---- host-side copy pool -------------------------------------------------------------------------------
+// Results for ordinary (pageable) host arrays are copied device -> pinned staging -> caller memory; the
+// second hop is a plain memcpy, which one core cannot do at PCIe speed, so a few worker threads share it.
+// One pool per process, created on first use and never destroyed (workers block on a condition variable).
+constexpr size_t kStageBytes = 16ull << 20;
+class CopyPool {
+public:
+    static CopyPool& get() { static CopyPool* p = new CopyPool(); return *p; }
+    // copy asynchronously; returns a ticket for wait()
+    uint64_t submit(void* dst, const void* src, size_t bytes) {
+        std::unique_lock<std::mutex> lk(mu_);
+        const uint64_t t = ++last_ticket_;
+        const size_t parts = bytes >= (1u << 20) ? nthreads_ : 1;
+        const size_t slice = ((bytes + parts - 1) / parts + 63) & ~(size_t)63;
+        int n = 0;
+        for (size_t off = 0; off < bytes; off += slice, ++n)
+            tasks_.push_back(Task{(unsigned char*)dst + off, (const unsigned char*)src + off, bytes - off < slice ? bytes - off : slice, t});
+        if (n == 0) return 0;
+        pending_[t] = n;
+        lk.unlock();
+        work_.notify_all();
+        return t;
+    }
+    void wait(uint64_t ticket) {
+        if (!ticket) return;
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_.find(ticket) == pending_.end(); });
+    }
+private:
+    struct Task { unsigned char* dst; const unsigned char* src; size_t bytes; uint64_t ticket; };
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        nthreads_ = hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1);
+        if (const char* e = getenv("NDI_COPY_THREADS")) { long v = strtol(e, nullptr, 10); if (v >= 1 && v <= 64) nthreads_ = (size_t)v; }
+        for (size_t i = 0; i < nthreads_; ++i) std::thread([this] { run(); }).detach();
+    }
+    void run() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                work_.wait(lk, [&] { return !tasks_.empty(); });
+                t = tasks_.front(); tasks_.pop_front();
+            }
+            memcpy(t.dst, t.src, t.bytes);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                auto it = pending_.find(t.ticket);
+                if (it != pending_.end() && --it->second == 0) { pending_.erase(it); done_.notify_all(); }
+            }
+        }
+    }
+    std::mutex mu_; std::condition_variable work_, done_;
+    std::deque<Task> tasks_; std::unordered_map<uint64_t, int> pending_;
+    uint64_t last_ticket_ = 0; size_t nthreads_ = 1;
+};
+
+static bool is_pageable_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
 }
 
 // ---- search configuration ----------------------------------------------------------------------------
@@ -610,6 +679,43 @@ ndi_status run_host_eval(const HostEval& he, Launch&& launch, Validate&& validat
     int64_t nvalid = he.nq;
     if (*err_word != NDI_ERR_WORD_NONE) nvalid = (int64_t)(he.ncoord > 1 ? *err_word >> 1 : *err_word);
 
+    static const bool stage_pageable = [] { const char* e = getenv("NDI_STAGE_PAGEABLE"); return !(e && *e == '0'); }();
+    if (stage_pageable && row <= kStageBytes / 32 && is_pageable_host(he.out)) {
+        // pageable output: device -> pinned staging (three buffers in flight) -> caller memory by the copy pool
+        int64_t per = (int64_t)(kStageBytes / row) & ~31ll;
+        for (int k = 0; k < 3; ++k) {
+            if (!ws->h_stage[k]) CK(cudaMallocHost(&ws->h_stage[k], kStageBytes));
+            if (!ws->stage_ev[k]) CK(cudaEventCreateWithFlags(&ws->stage_ev[k], cudaEventDisableTiming));
+        }
+        CopyPool& pool = CopyPool::get();
+        uint64_t ticket[3] = {0, 0, 0};
+        const int64_t nch = (nvalid + per - 1) / per;
+        auto finish = [&](int64_t j) -> ndi_status {           // chunk j has landed in its staging buffer: hand it to the pool
+            const int k = (int)(j % 3);
+            CK(cudaEventSynchronize(ws->stage_ev[k]));
+            const int64_t lo = j * per, cnt = nvalid - lo < per ? nvalid - lo : per;
+            ticket[k] = pool.submit((unsigned char*)he.out + (size_t)lo * row, ws->h_stage[k], (size_t)cnt * row);
+            return NDI_OK;
+        };
+        ndi_status pst = NDI_OK;
+        for (int64_t i = 0; i < nch && pst == NDI_OK; ++i) {
+            const int k = (int)(i % 3), sl = (int)(i & 1);
+            const int64_t lo = i * per, cnt = nvalid - lo < per ? nvalid - lo : per;
+            pool.wait(ticket[k]);                                // the host copy that last used this staging buffer is done
+            if ((pst = grow(&ws->d_out[sl], &ws->d_out_cap[sl], (size_t)per * row)) != NDI_OK) break;
+            const void* c0 = (const unsigned char*)dq0 + (size_t)lo * he.es;
+            const void* c1 = dq1 ? (const unsigned char*)dq1 + (size_t)lo * he.es : nullptr;
+            if ((pst = launch(c0, c1, cnt, ws->d_out[sl], nullptr, ws->s[sl])) != NDI_OK) break;
+            cudaError_t ce = cudaMemcpyAsync(ws->h_stage[k], ws->d_out[sl], (size_t)cnt * row, cudaMemcpyDeviceToHost, ws->s[sl]);
+            if (ce == cudaSuccess) ce = cudaEventRecord(ws->stage_ev[k], ws->s[sl]);
+            if (ce != cudaSuccess) { pst = cuda_fail(ce, "staged copy"); break; }
+            if (i >= 1) pst = finish(i - 1);
+        }
+        if (pst == NDI_OK && nch >= 1) pst = finish(nch - 1);
+        for (int k = 0; k < 3; ++k) pool.wait(ticket[k]);      // never leave with copies into the caller's memory in flight
+        if (pst != NDI_OK) { cudaStreamSynchronize(ws->s[0]); cudaStreamSynchronize(ws->s[1]); }
+        return pst;
+    }
     int64_t per_chunk = (int64_t)(kChunkBytes / row);
     per_chunk = per_chunk < 32 ? 32 : (per_chunk & ~31ll);
     const size_t chunk_bytes = (size_t)per_chunk * row;
