@@ -123,3 +123,68 @@ def test_c4_bilinear_f32_full_size(D, extrapolate):
         err = D.new_err_word()
         ip.bilinear(dev(qx2), dev(qy2), False, out=out, err=err)
         assert D.err_word_value(err) == 2 * 555 + 1
+
+
+def test_c5a_bilinear_f32_at_scale_binned_equals_direct(D):
+    """C5a: 2.1 GB table, 2^25 random queries -- AUTO bins the batch by table band.  Binning changes the
+    order of evaluation only: every output row equals the direct kernel's, and a sample equals the oracle."""
+    rng = np.random.default_rng(55)
+    n = m = 4096
+    w, nq = 32, 1 << 25
+    gx = torch.linspace(0.0, 1.0, n, dtype=torch.float32, device="cuda")
+    gy_h = (np.cumsum(rng.uniform(0.5, 1.5, m)) / m).astype(np.float32)
+    data = torch.randn((n, m, w), dtype=torch.float32, device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    qx = torch.rand(nq, dtype=torch.float32, device="cuda", generator=gen)
+    qy = (torch.rand(nq, dtype=torch.float32, device="cuda", generator=gen) * float(gy_h[-1] - gy_h[0]) + float(gy_h[0]))
+    qy = qy.clamp(float(gy_h[0]), float(gy_h[-1]))
+    ip = D.DeviceInterp2D(gx, dev(gy_h), data)
+    launches0 = D.kernel_launch_count()
+    err = D.new_err_word()
+    out_auto = ip.bilinear(qx, qy, False, err=err)
+    assert D.err_word_value(err) == D.ERR_NONE
+    assert D.kernel_launch_count() - launches0 == 3                       # count pass, scatter pass, evaluation
+    ip.set_binning(L.BIN_OFF)
+    out_direct = ip.bilinear(qx, qy, False)
+    assert torch.equal(out_auto, out_direct)
+    idx = np.sort(rng.choice(nq, 4096, replace=False))
+    rows = np.unique(np.concatenate([np.searchsorted(np.linspace(0, 1, n, dtype=np.float32), qx[idx].cpu().numpy(), "right") - 1]))
+    # the oracle needs the table on the host: take the x-rows the sample touches (and their successors) only
+    need = np.unique(np.clip(np.concatenate([rows, rows + 1]), 0, n - 1))
+    sub = data[torch.from_numpy(need).cuda()].cpu().numpy()
+    gx_h = gx.cpu().numpy()
+    # evaluate the sample row by row on the two x-rows it needs (a 2-row table is a valid bilinear table)
+    got = sample_rows(out_auto, idx)
+    qxs, qys = qx[idx].cpu().numpy(), qy[idx].cpu().numpy()
+    pos = {r: k for k, r in enumerate(need)}
+    for k in range(0, len(idx), 64):                                      # 64 oracle calls: enough to pin the bits
+        i = int(min(max(np.searchsorted(gx_h, qxs[k], "right") - 1, 0), n - 2))
+        tbl = np.stack([sub[pos[i]], sub[pos[i + 1]]])
+        st, ref, _, _ = O.interp2d_bilinear(gx_h[i:i + 2], gy_h, tbl, qxs[k:k + 1], qys[k:k + 1], False)
+        assert st == O.ST_OK and np.array_equal(got[k:k + 1], ref)
+
+
+def test_c5b_cubic_f32_at_scale_sorted(D):
+    """C5b: 2^25 sorted queries on a (4096, 32) f32 spline: 8192 queries per interval, so nearly every
+    32-query tile takes the one-interval path (rows gathered once per tile); sampled bit-exact parity
+    and equality with the same queries in shuffled order (which take the per-round path)."""
+    rng = np.random.default_rng(56)
+    n, w, nq = 4096, 32, 1 << 25
+    g = np.cumsum(rng.uniform(0.5, 1.5, n)).astype(np.float32)
+    y = rng.standard_normal((n, w), dtype=np.float32)
+    ip = D.DeviceInterp1D(dev(g), dev(y))
+    st, _ = ip.spline_build(1)
+    assert st == 0
+    a, b = ip.coeffs_to_host()
+    st, a_ref, b_ref = O.spline_build(g, y, {"kind": "Natural"})
+    assert np.array_equal(a, a_ref) and np.array_equal(b, b_ref)
+    q = torch.sort(torch.rand(nq, dtype=torch.float32, device="cuda") * float(g[-1] - g[0]) + float(g[0]))[0].clamp(float(g[0]), float(g[-1]))
+    err = D.new_err_word()
+    out = ip.cubic(q, 0, err=err)
+    assert D.err_word_value(err) == D.ERR_NONE
+    idx = np.sort(rng.choice(nq, 8192, replace=False))
+    st, ref, _ = O.interp1d_cubic(g, y, a_ref, b_ref, q[torch.from_numpy(idx).cuda()].cpu().numpy(), 0)
+    assert st == O.ST_OK and np.array_equal(sample_rows(out, idx), ref)
+    perm = torch.randperm(1 << 22, device="cuda")
+    sub = q[: 1 << 22].contiguous()
+    assert torch.equal(ip.cubic(sub[perm].contiguous(), 0), out[: 1 << 22][perm])
