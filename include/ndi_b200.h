@@ -95,7 +95,9 @@ typedef int32_t ndi_dtype;
 #define NDI_ASSUME_VALID 1u    /* skip the strict-rising check: Interp1D::new_unchecked (interp1d/mod.rs:363) */
 #define NDI_DEVICE_POINTERS 2u /* x / y / data are device pointers on the current device (copied D2D) */
 #define NDI_BORROW 4u          /* with NDI_DEVICE_POINTERS: keep the caller's buffers instead of copying
-                                  (the Interp1DView / ViewRepr case, interp1d/aliases.rs); caller keeps them alive */
+                                  (the Interp1DView / ViewRepr case, interp1d/aliases.rs); caller keeps them alive
+                                  AND unchanged: create() derives search tables from the grid and classifies the
+                                  value range of the data (which division sequence the kernels may use) */
 
 /* lower-index search strategy, for measurement; NDI_SEARCH_AUTO is what production uses */
 #define NDI_SEARCH_AUTO 0
