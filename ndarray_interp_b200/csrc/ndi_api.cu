@@ -2,14 +2,15 @@
 // host-buffer pipeline around the kernels.  No interpolation arithmetic happens on the host.
 //
 // Host entry points (no _dev suffix):
-//   small batches : one fused launch (evaluation + first-error word), results staged through a
-//                   pinned buffer and copied out with a single synchronisation -- this is the
-//                   latency path of interp_scalar / interp / interp_into.
-//   large batches : (1) queries uploaded once, (2) K7 pre-pass finds the first query the reference
+//   results <= 256 KB : the latency path of interp_scalar / interp / interp_into: queries and rows live in the
+//                   thread's pinned workspace, which the kernel reads and writes directly; completion is a flag
+//                   in that workspace (profiles/r01/latency.md).
+//   larger batches : (1) queries uploaded once, (2) K7 pre-pass finds the first query the reference
 //                   would fail on, (3) only the rows before it are evaluated, in chunks alternating
 //                   between two streams so the D2H copy of one chunk overlaps the kernel of the
 //                   next.  Rows at and after the failing query stay untouched, like the reference
-//                   (interp1d/mod.rs:321,336-340).
+//                   (interp1d/mod.rs:321,336-340).  Page-locked output arrays receive the chunks directly;
+//                   ordinary pageable ones through three pinned staging buffers and a pool of copy threads.
 // All per-call state lives in a thread-local workspace, so one handle can be used from many
 // threads at once (the reference's &self methods are called from rayon workers).
 #include <atomic>
@@ -619,7 +620,8 @@ ndi_status run_host_eval(const HostEval& he, Launch&& launch, Validate&& validat
     if ((size_t)he.nq * row <= kTinyBytes && qbytes <= kTinyQueryBytes) {
         // scalar / tiny-batch latency path (interp_scalar, interp, interp_into: interp1d/mod.rs:108-175): the
         // pinned workspace is mapped into the device's address space, so the kernel reads the queries from
-        // it and writes the rows into it over PCIe: one launch, one 8-byte copy, one synchronisation
+        // it and writes the rows into it over PCIe; publish_kernel hands over the error word and raises the
+        // flag this thread spins on: two launches, no copy call, no driver synchronisation
         unsigned char* hq0 = ws->h_pin + 64 + kSmallBytes;
         unsigned char* hq1 = hq0 + kTinyQueryBytes;
         memcpy(hq0, he.q[0], qbytes);
