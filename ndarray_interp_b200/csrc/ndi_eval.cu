@@ -91,15 +91,26 @@ __global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THI
     const T g0 = g.g0, gl = g.gl;
     const int lane = threadIdx.x & 31;
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
-    for (long long task = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < p.ntasks; task += nwarps) {
+    const long long task0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    // thin rows: the query of the NEXT tile is loaded while this one is processed, so a tile does not start
+    // with a DRAM round trip (with ~40 resident warps per SM the kernel is bound by per-tile latency)
+    T x_ahead = g0;
+    if (LPQ < 32 && kTilesLinear == 1 && task0 < p.ntasks && task0 * 32 + lane < p.nq) x_ahead = ld_query(p.q + task0 * 32 + lane);
+    for (long long task = task0; task < p.ntasks; task += nwarps) {
         if constexpr (LPQ < 32) {
             constexpr int TPW = kTilesLinear, QPR = 32 / LPQ;
             const long long qbase0 = task * (32 * TPW);
             T x[TPW]; int idx[TPW]; T dx21[TPW], dxq[TPW]; bool skip[TPW]; Slope<T> slope[TPW];   // dx21/dxq: x1, x2 from the search
+            if constexpr (TPW == 1) {
+                x[0] = x_ahead;
+                const long long qn = (task + nwarps) * 32 + lane;
+                x_ahead = (task + nwarps < p.ntasks && qn < p.nq) ? ld_query(p.q + qn) : g0;
+            } else {
 #pragma unroll
-            for (int t = 0; t < TPW; ++t) {
-                const long long qi = qbase0 + t * 32 + lane;
-                x[t] = qi < p.nq ? ld_query(p.q + qi) : g0;
+                for (int t = 0; t < TPW; ++t) {
+                    const long long qi = qbase0 + t * 32 + lane;
+                    x[t] = qi < p.nq ? ld_query(p.q + qi) : g0;
+                }
             }
             search_multi<T, TPW>(g, x, idx, dx21, dxq);                               // linear.rs:87, :90-91 (x1, x2)
 #pragma unroll
@@ -222,17 +233,27 @@ __global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THI
     const T one = (T)1;
     const int lane = threadIdx.x & 31;
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
-    for (long long task = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < p.ntasks; task += nwarps) {
+    const long long task0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    T x_ahead = g0;                                           // thin rows: the next tile's query, loaded one tile ahead
+    if (LPQ < 32 && kTilesCubic == 1 && task0 < p.ntasks && task0 * 32 + lane < p.nq) x_ahead = ld_query(p.q + task0 * 32 + lane);
+    for (long long task = task0; task < p.ntasks; task += nwarps) {
         if constexpr (LPQ < 32) {
             constexpr int TPW = kTilesCubic, QPR = 32 / LPQ;
             const long long qbase0 = task * (32 * TPW);
             T x[TPW]; int idx[TPW]; T tq[TPW], omt[TPW], tt[TPW]; bool skip[TPW], bad[TPW];
+            if constexpr (TPW == 1) {
+                x[0] = x_ahead;
+                const long long qn = (task + nwarps) * 32 + lane;
+                x_ahead = (task + nwarps < p.ntasks && qn < p.nq) ? ld_query(p.q + qn) : g0;
+                bad[0] = cubic_prepare<T>(x[0], g0, gl, p.mode) && qbase0 + lane < p.nq;
+            } else {
 #pragma unroll
-            for (int t = 0; t < TPW; ++t) {
-                const long long qi = qbase0 + t * 32 + lane;
-                const bool live = qi < p.nq;
-                x[t] = live ? ld_query(p.q + qi) : g0;
-                bad[t] = cubic_prepare<T>(x[t], g0, gl, p.mode) && live;
+                for (int t = 0; t < TPW; ++t) {
+                    const long long qi = qbase0 + t * 32 + lane;
+                    const bool live = qi < p.nq;
+                    x[t] = live ? ld_query(p.q + qi) : g0;
+                    bad[t] = cubic_prepare<T>(x[t], g0, gl, p.mode) && live;
+                }
             }
             search_multi<T, TPW>(g, x, idx, tq, omt);                                 // :811 (+ x_left, x_right)
 #pragma unroll
@@ -344,7 +365,13 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (LPQ <= 2 ? 5 : 4) : 
     const int lane = threadIdx.x & 31;
     const long long rowx = (long long)p.m * p.w;      // elements between x-rows
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
-    for (long long task = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < p.ntasks; task += nwarps) {
+    const long long task0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    T x_ahead = gx0, y_ahead = gy0; unsigned row_ahead = 0;   // thin rows: the next tile's query, loaded one tile ahead
+    if (LPQ < 32 && kTilesBilinear == 1 && task0 < p.ntasks && task0 * 32 + lane < p.nq) {
+        x_ahead = ld_query(p.qx + task0 * 32 + lane); y_ahead = ld_query(p.qy + task0 * 32 + lane);
+        if constexpr (PERM) row_ahead = __ldcs(p.perm + task0 * 32 + lane);
+    }
+    for (long long task = task0; task < p.ntasks; task += nwarps) {
         if constexpr (LPQ < 32) {
             constexpr int TPW = kTilesBilinear, QPR = 32 / LPQ;
             const long long qbase0 = task * (32 * TPW);
@@ -352,13 +379,22 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (LPQ <= 2 ? 5 : 4) : 
             long long cell[TPW]; T ax[TPW], bx[TPW], ay[TPW], by[TPW]; bool skip[TPW];   // ax..by: x1, x2, y1, y2 from the search
             Slope<T> slx[TPW], sly[TPW];
             unsigned orow[TPW];                                                        // output row (PERM only)
+            if constexpr (TPW == 1) {
+                x[0] = x_ahead; y[0] = y_ahead; orow[0] = row_ahead;
+                const long long qn = (task + nwarps) * 32 + lane;
+                const bool more = task + nwarps < p.ntasks && qn < p.nq;
+                x_ahead = more ? ld_query(p.qx + qn) : gx0;
+                y_ahead = more ? ld_query(p.qy + qn) : gy0;
+                if constexpr (PERM) row_ahead = more ? __ldcs(p.perm + qn) : 0u;
+            } else {
 #pragma unroll
-            for (int t = 0; t < TPW; ++t) {
-                const long long qi = qbase0 + t * 32 + lane;
-                const bool live = qi < p.nq;
-                x[t] = live ? ld_query(p.qx + qi) : gx0;
-                y[t] = live ? ld_query(p.qy + qi) : gy0;
-                if constexpr (PERM) orow[t] = live ? __ldcs(p.perm + qi) : 0u;
+                for (int t = 0; t < TPW; ++t) {
+                    const long long qi = qbase0 + t * 32 + lane;
+                    const bool live = qi < p.nq;
+                    x[t] = live ? ld_query(p.qx + qi) : gx0;
+                    y[t] = live ? ld_query(p.qy + qi) : gy0;
+                    if constexpr (PERM) orow[t] = live ? __ldcs(p.perm + qi) : 0u;
+                }
             }
             search_multi<T, TPW>(gx, x, ix, ax, bx);                                  // bilinear.rs:82 (+ x1, x2)
             search_multi<T, TPW>(gy, y, iy, ay, by);
