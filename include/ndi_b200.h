@@ -64,6 +64,7 @@ typedef int32_t ndi_dtype;
 #define NDI_F32 0
 #define NDI_F64 1
 #define NDI_I32 2 /* everything except splines (SplineNum is float-only, cubic_spline.rs:34-49) */
+#define NDI_I64 3 /* as NDI_I32: wrapping arithmetic, truncating division (Linear / Bilinear are generic over Num) */
 
 /* enum Monotonic (src/vector_extensions.rs:24-29) */
 #define NDI_MONO_NOT_MONOTONIC 0

@@ -15,14 +15,15 @@ SO_PATH = os.environ.get("NDI_B200_LIB") or os.path.join(_HERE, "libndi_b200.so"
 OK, OUT_OF_BOUNDS, NAN_QUERY, PERIODIC_MISMATCH, INVALID_ARGUMENT, NOT_MONOTONIC, NO_SPLINE, UNSUPPORTED_DTYPE, \
     NO_DEVICE = range(9)
 CUDA_ERROR = 100
-F32, F64, I32 = 0, 1, 2
+F32, F64, I32, I64 = 0, 1, 2, 3
 ASSUME_VALID, DEVICE_POINTERS, BORROW = 1, 2, 4
 SEARCH_AUTO, SEARCH_BINARY_GLOBAL, SEARCH_BINARY_SMEM, SEARCH_UNIFORM_GUESS, SEARCH_BUCKET_LUT = 0, 1, 2, 3, 4
 EXTRAP_NO, EXTRAP_YES, EXTRAP_PERIODIC = 0, 1, 2
 BIN_AUTO, BIN_OFF, BIN_ON = 0, 1, 2
 ERR_WORD_NONE = 2 ** 64 - 1
 
-DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32}
+DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32,
+          np.dtype(np.int64): I64}
 
 _vp, _i64, _i32, _u32, _u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_uint64
 _pi64, _pi32 = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
@@ -124,4 +125,4 @@ def dtype_code(dt):
         return DTYPES[np.dtype(dt)]
     except KeyError:
         raise TypeError(f"element type {np.dtype(dt)} is not supported on the device path "
-                        "(f32, f64 and i32 are)") from None
+                        "(f32, f64, i32 and i64 are)") from None

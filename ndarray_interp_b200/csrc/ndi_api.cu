@@ -85,8 +85,8 @@ struct DeviceGuard {
     ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
 };
 
-static size_t elem_size(ndi_dtype d) { return d == NDI_F64 ? 8 : 4; }
-static bool dtype_ok(ndi_dtype d) { return d == NDI_F32 || d == NDI_F64 || d == NDI_I32; }
+static size_t elem_size(ndi_dtype d) { return (d == NDI_F64 || d == NDI_I64) ? 8 : 4; }
+static bool dtype_ok(ndi_dtype d) { return d == NDI_F32 || d == NDI_F64 || d == NDI_I32 || d == NDI_I64; }
 
 template <class F>
 static ndi_status dispatch(ndi_dtype d, F&& f) {
@@ -94,6 +94,7 @@ static ndi_status dispatch(ndi_dtype d, F&& f) {
     case NDI_F32: return f(float{});
     case NDI_F64: return f(double{});
     case NDI_I32: return f(int32_t{});
+    case NDI_I64: return f(int64_t{});
     default: return fail(NDI_UNSUPPORTED_DTYPE, "unsupported dtype %d", (int)d);
     }
 }
@@ -277,7 +278,7 @@ static SearchCfg make_search(const GridMeta& gm, int mode, int64_t nq, size_t ot
 //  - coarse table for a grid too large to stage whole (strided device-to-device copy)
 //  - bucket table for the O(1) search
 static ndi_status build_aids(ndi_dtype dtype, const void* grid, int64_t n, cudaStream_t st, GridAids* aids) {
-    const size_t elem = dtype == NDI_F64 ? 8 : 4;
+    const size_t elem = elem_size(dtype);
     *aids = GridAids{};
     if ((size_t)n * elem > kFullStageBytes) {
         int sh = 1;
@@ -303,6 +304,9 @@ static ndi_status build_aids(ndi_dtype dtype, const void* grid, int64_t n, cudaS
     } else if (dtype == NDI_F64) {
         double a, b; memcpy(&a, ends, 8); memcpy(&b, ends + 8, 8);
         g0d = a; scale = (double)nb / (b - a);
+    } else if (dtype == NDI_I64) {
+        int64_t a, b; memcpy(&a, ends, 8); memcpy(&b, ends + 8, 8);
+        g0d = (double)a; scale = (double)nb / ((double)b - (double)a);
     } else {
         int32_t a, b; memcpy(&a, ends, 4); memcpy(&b, ends + 8, 4);
         g0d = a; scale = (double)nb / ((double)b - (double)a);
@@ -333,7 +337,7 @@ struct ndi_interp1d {
     int uniform_hint; int search_mode;
     int fast_tables = 0;             // f32: every data value is 0 or in [2^-56, 2^30] (hoisted-reciprocal division allowed)
     GridAids aids;
-    GridMeta meta() const { return aids.meta(x, n, dtype == NDI_F64 ? (size_t)8 : (size_t)4, uniform_hint); }
+    GridMeta meta() const { return aids.meta(x, n, elem_size(dtype), uniform_hint); }
 };
 struct ndi_interp2d {
     ndi_dtype dtype; int device; int64_t n, m, w;
@@ -343,8 +347,8 @@ struct ndi_interp2d {
     int bin_mode = NDI_BIN_AUTO; int band_rows = 0;   // locality binning of query batches (ndi_bin.cu)
     int fast_tables = 0;
     GridAids aids_x, aids_y;
-    GridMeta meta_x() const { return aids_x.meta(x, n, dtype == NDI_F64 ? (size_t)8 : (size_t)4, hint_x); }
-    GridMeta meta_y() const { return aids_y.meta(y, m, dtype == NDI_F64 ? (size_t)8 : (size_t)4, hint_y); }
+    GridMeta meta_x() const { return aids_x.meta(x, n, elem_size(dtype), hint_x); }
+    GridMeta meta_y() const { return aids_y.meta(y, m, elem_size(dtype), hint_y); }
 };
 
 // upload or adopt one table
@@ -878,7 +882,7 @@ ndi_status ndi_interp1d_spline_coeffs(const ndi_interp1d* h, void* a, void* b) {
 
 ndi_status ndi_interp1d_spline_set_coeffs(ndi_interp1d* h, const void* a, const void* b, uint32_t flags) {
     if (!h || !a || !b) return fail(NDI_INVALID_ARGUMENT, "null pointer");
-    if (h->dtype == NDI_I32) return fail(NDI_UNSUPPORTED_DTYPE, "cubic splines need a float dtype");
+    if (h->dtype == NDI_I32 || h->dtype == NDI_I64) return fail(NDI_UNSUPPORTED_DTYPE, "cubic splines need a float dtype");
     DeviceGuard g(h->device);
     const size_t bytes = (size_t)(h->n - 1) * h->w * elem_size(h->dtype);
     void *na = nullptr, *nb = nullptr; bool oa = false, ob = false;

@@ -235,5 +235,6 @@ cudaError_t launch_bin_queries(const T* gx, int64_t n, SearchCfg scx, const T* q
 NDI_INST_BIN(float)
 NDI_INST_BIN(double)
 NDI_INST_BIN(int32_t)
+NDI_INST_BIN(int64_t)
 
 }  // namespace ndi

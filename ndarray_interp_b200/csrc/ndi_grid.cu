@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(kGridBlock) grid_classify_kernel(const T* __re
                 T mid;
                 if constexpr (std::is_same_v<T, double>) mid = 0.5 * (a + b);
                 else if constexpr (std::is_same_v<T, float>) mid = 0.5f * (a + b);
+                else if constexpr (sizeof(T) == 8) mid = a < b ? (T)(a + (T)(((unsigned long long)b - (unsigned long long)a) / 2)) : a;   // a + b may overflow
                 else mid = (T)(((long long)a + (long long)b) / 2);
                 if (a <= mid && mid < b) {
                     T g0 = x[0], gl = x[n - 1];
@@ -188,10 +189,12 @@ cudaError_t launch_build_lut(const T* x, int64_t n, double g0d, double scale, in
 template cudaError_t launch_build_lut<float>(const float*, int64_t, double, double, int, void*, cudaStream_t);
 template cudaError_t launch_build_lut<double>(const double*, int64_t, double, double, int, void*, cudaStream_t);
 template cudaError_t launch_build_lut<int32_t>(const int32_t*, int64_t, double, double, int, void*, cudaStream_t);
+template cudaError_t launch_build_lut<int64_t>(const int64_t*, int64_t, double, double, int, void*, cudaStream_t);
 
 template cudaError_t launch_grid_classify<float>(const float*, int64_t, int32_t*, uint32_t*, cudaStream_t);
 template cudaError_t launch_grid_classify<double>(const double*, int64_t, int32_t*, uint32_t*, cudaStream_t);
 template cudaError_t launch_grid_classify<int32_t>(const int32_t*, int64_t, int32_t*, uint32_t*, cudaStream_t);
+template cudaError_t launch_grid_classify<int64_t>(const int64_t*, int64_t, int32_t*, uint32_t*, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
 // May the evaluation kernels divide with a per-query reciprocal (ndi_device.cuh, div_by)?  Yes when

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib as L
 
-_TORCH_DT = {torch.float32: L.F32, torch.float64: L.F64, torch.int32: L.I32}
+_TORCH_DT = {torch.float32: L.F32, torch.float64: L.F64, torch.int32: L.I32, torch.int64: L.I64}
 ERR_NONE = L.ERR_WORD_NONE
 
 
@@ -21,7 +21,7 @@ def _code(t):
     try:
         return _TORCH_DT[t.dtype]
     except KeyError:
-        raise TypeError(f"dtype {t.dtype} is not supported (f32, f64, i32)") from None
+        raise TypeError(f"dtype {t.dtype} is not supported (f32, f64, i32, i64)") from None
 
 
 def _p(t):

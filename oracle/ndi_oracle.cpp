@@ -19,13 +19,14 @@
 //
 // Reference citations are relative to /root/reference/.
 //
-// Element types: f32, f64 (all entry points) and i32 (everything except splines, which
+// Element types: f32, f64 (all entry points) and i32 / i64 (everything except splines, which
 // the reference restricts to float types through SplineNum, cubic_spline.rs:34-49).
 // Integer arithmetic wraps on overflow like a Rust release build.
 
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <thread>
 #include <type_traits>
 #include <vector>
@@ -57,18 +58,18 @@ inline bool is_nan(T v) {
 
 // wrapping integer arithmetic / plain float arithmetic --------------------------------------
 template <class T> inline T t_add(T a, T b) {
-    if constexpr (std::is_integral_v<T>) return (T)((uint32_t)a + (uint32_t)b); else return a + b;
+    if constexpr (std::is_integral_v<T>) { using U = std::make_unsigned_t<T>; return (T)((U)a + (U)b); } else return a + b;
 }
 template <class T> inline T t_sub(T a, T b) {
-    if constexpr (std::is_integral_v<T>) return (T)((uint32_t)a - (uint32_t)b); else return a - b;
+    if constexpr (std::is_integral_v<T>) { using U = std::make_unsigned_t<T>; return (T)((U)a - (U)b); } else return a - b;
 }
 template <class T> inline T t_mul(T a, T b) {
-    if constexpr (std::is_integral_v<T>) return (T)((uint32_t)a * (uint32_t)b); else return a * b;
+    if constexpr (std::is_integral_v<T>) { using U = std::make_unsigned_t<T>; return (T)((U)a * (U)b); } else return a * b;
 }
 template <class T> inline T t_div(T a, T b) {
     if constexpr (std::is_integral_v<T>) {
         if (b == 0) return 0;              // Rust panics; unreachable on a strictly rising grid
-        if (a == INT32_MIN && b == -1) return a;
+        if (a == std::numeric_limits<T>::min() && b == -1) return a;
         return a / b;                      // truncating, like Rust
     } else return a / b;
 }
@@ -539,6 +540,7 @@ int32_t shard_queries(int64_t nq, int32_t nthreads, int64_t* first_bad, F&& fn) 
 ORA_COMMON(f32, float)
 ORA_COMMON(f64, double)
 ORA_COMMON(i32, int32_t)
+ORA_COMMON(i64, int64_t)
 ORA_SPLINE(f32, float)
 ORA_SPLINE(f64, double)
 

@@ -99,6 +99,11 @@ static void linear_errors() {
     // integer element type: truncating division like the reference's generic Num path
     auto ii = Interp1D<int32_t>::builder(I{10, 20, 40}).build();
     CHECK(ii.interp_array(I{0, 1, 2}) == (I{10, 20, 40}));
+    using I8 = Array<int64_t>;
+    const int64_t big = (int64_t)1 << 60;
+    auto i8 = Interp1D<int64_t>::builder(I8{big, big + 20, big + 50}).x(I8{0, 10, 40}).build();
+    CHECK(i8.interp_array(I8{0, 5, 10, 25, 40}) == (I8{big, big + 10, big + 20, big + 35, big + 50}));
+    CHECK(throws<InterpolateError>([&] { i8.interp_scalar(41); }));
 }
 
 // src/vector_extensions.rs unit tests: borders, exact hits, +-inf, NaN panic, monotonic classification

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.json")
-DT = {"f32": np.float32, "f64": np.float64, "i32": np.int32}
+DT = {"f32": np.float32, "f64": np.float64, "i32": np.int32, "i64": np.int64}
 
 
 def load(kind=None):

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from ndarray_interp_b200 import InterpolateError, Panic, _lib as L
+from ndarray_interp_b200 import BuilderError, InterpolateError, Panic, _lib as L
 from ndarray_interp_b200.interp1d import Interp1D, Linear
 from ndarray_interp_b200.interp2d import Bilinear, Interp2D
 from ndarray_interp_b200.vector_extensions import Monotonic, get_lower_index, monotonic_prop
@@ -17,7 +17,7 @@ from oracle import oracle_py as O
 
 pytestmark = pytest.mark.gpu
 
-DTS = [np.float32, np.float64, np.int32]
+DTS = [np.float32, np.float64, np.int32, np.int64]
 
 
 def same(a, b):
@@ -447,3 +447,46 @@ def test_ddiv_selftest_sample():
         bad = C.c_uint64(123)
         L.check(lib.ndi_selftest_ddiv(seed, 1 << 27, C.byref(bad)))
         assert bad.value == 0, (seed, bad.value)
+
+
+# ---- i64 (Linear / Bilinear are generic over Num) -----------------------
+@pytest.mark.parametrize("mode", [L.SEARCH_AUTO, L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS,
+                                  L.SEARCH_BUCKET_LUT])
+def test_i64_values_beyond_2_pow_53_and_wrapping(mode):
+    """grid / data values that no double represents exactly (the bucket function rounds them, the search must
+    not) and products that wrap like a Rust release build"""
+    rng = np.random.default_rng(64)
+    for n, w in ((2, 1), (50, 3), (5000, 8), (70001, 2)):
+        g = (1 << 60) + np.cumsum(rng.integers(1, 9, n)).astype(np.int64)
+        data = rng.integers(-(1 << 62), 1 << 62, (n, w)).astype(np.int64)
+        q = rng.integers(int(g[0]) - 50, int(g[-1]) + 50, 20000).astype(np.int64)
+        q[:4] = [g[0], g[-1], g[0] - 1, g[-1] + 1]
+        st, ref_idx, _ = O.lower_index(g, q)
+        assert st == O.ST_OK and np.array_equal(get_lower_index(g, q), ref_idx)
+        interp = Interp1D.new_unchecked(g, data, Linear.new().extrapolate(True))
+        L.check(L.load().ndi_interp1d_set_search_mode(interp._handle(), mode))
+        st, ref, _ = O.interp1d_linear(g, data, q, True)
+        assert st == O.ST_OK
+        got = interp.interp_array(q)
+        assert got.dtype == np.int64 and same(got, ref)
+    gx = np.cumsum(rng.integers(1, 1000, 300)).astype(np.int64) - (1 << 40)
+    gy = np.arange(40, dtype=np.int64) * 7 + (1 << 55)
+    d2 = rng.integers(-(1 << 40), 1 << 40, (300, 40, 5)).astype(np.int64)
+    qx = rng.integers(int(gx[0]), int(gx[-1]) + 1, 30000).astype(np.int64)
+    qy = rng.integers(int(gy[0]), int(gy[-1]) + 1, 30000).astype(np.int64)
+    ip = Interp2D.new_unchecked(gx, gy, d2, Bilinear.new())
+    L.check(L.load().ndi_interp2d_set_search_mode(ip._handle(), mode))
+    st, ref, _, _ = O.interp2d_bilinear(gx, gy, d2, qx, qy, False)
+    assert st == O.ST_OK and same(ip.interp_array(qx, qy), ref)
+
+
+def test_i64_builder_checks_and_errors():
+    """the same builder / OutOfBounds behaviour as i32 (tests/interp1d.rs:93-127)"""
+    i = np.int64
+    with pytest.raises(BuilderError.Monotonic):
+        Interp1D.builder(np.array([1, 2, 3], i)).x(np.array([1, 2, 2], i)).build()
+    interp = Interp1D.builder(np.array([10, 20, 40], i)).build()
+    assert interp.interp_scalar(i(1)) == 20 and interp.interp_scalar(i(2)).dtype == np.int64
+    with pytest.raises(InterpolateError.OutOfBounds):
+        interp.interp_scalar(i(3))
+    assert monotonic_prop(np.array([1 << 62, (1 << 62) + 1, (1 << 62) + 1], i)) == Monotonic.Rising(False)
