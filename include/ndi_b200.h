@@ -144,6 +144,15 @@ ndi_status ndi_lower_index_dev(ndi_dtype dtype, const void* grid_dev, int64_t n,
  * host logic of the caller (see the host mirrors), not data-parallel work. */
 ndi_status ndi_interp1d_create(ndi_dtype dtype, const void* x, int64_t n, const void* data, int64_t w,
                                uint32_t flags, ndi_interp1d** out);
+/* The same for ndarray VIEWS (interp1d/aliases.rs: Interp1DView; any strides, negative included --
+ * tests/interp1d.rs:143-155): x is n elements `x_stride` apart, data has `ndim` (1..8) dimensions
+ * with shape[0] == n and `strides` per dimension, all strides in ELEMENTS as ndarray reports them;
+ * both pointers address the view's first logical element.  The view's memory is uploaded as it lies
+ * and made dense on the device (a view that touches less than half of its span is gathered by the
+ * library on the host instead); the handle owns the dense copy.  NDI_BORROW is rejected. */
+ndi_status ndi_interp1d_create_strided(ndi_dtype dtype, const void* x, int64_t n, int64_t x_stride, const void* data,
+                                       int32_t ndim, const int64_t* shape, const int64_t* strides, uint32_t flags,
+                                       ndi_interp1d** out);
 ndi_status ndi_interp1d_destroy(ndi_interp1d* h);
 ndi_status ndi_interp1d_info(const ndi_interp1d* h, ndi_dtype* dtype, int64_t* n, int64_t* w, int32_t* has_spline,
                              int32_t* device);
@@ -185,6 +194,10 @@ ndi_status ndi_interp1d_cubic_dev(const ndi_interp1d* h, const void* q_dev, int6
  * NDI_NOT_MONOTONIC reports the failing axis in the message ("x-axis" before "y-axis"). */
 ndi_status ndi_interp2d_create(ndi_dtype dtype, const void* x, int64_t n, const void* y, int64_t m, const void* data,
                                int64_t w, uint32_t flags, ndi_interp2d** out);
+/* strided views, as ndi_interp1d_create_strided: shape[0] == n, shape[1] == m, ndim in 2..8 */
+ndi_status ndi_interp2d_create_strided(ndi_dtype dtype, const void* x, int64_t n, int64_t x_stride, const void* y,
+                                       int64_t m, int64_t y_stride, const void* data, int32_t ndim, const int64_t* shape,
+                                       const int64_t* strides, uint32_t flags, ndi_interp2d** out);
 ndi_status ndi_interp2d_destroy(ndi_interp2d* h);
 ndi_status ndi_interp2d_info(const ndi_interp2d* h, ndi_dtype* dtype, int64_t* n, int64_t* m, int64_t* w,
                              int32_t* device);

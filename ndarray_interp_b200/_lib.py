@@ -40,6 +40,7 @@ SIGNATURES = {
     "ndi_lower_index": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp, _pi64]),
     "ndi_lower_index_dev": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp]),
     "ndi_interp1d_create": (_i32, [_i32, _vp, _i64, _vp, _i64, _u32, C.POINTER(_vp)]),
+    "ndi_interp1d_create_strided": (_i32, [_i32, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _u32, C.POINTER(_vp)]),
     "ndi_interp1d_destroy": (_i32, [_vp]),
     "ndi_interp1d_info": (_i32, [_vp, _pi32, _pi64, _pi64, _pi32, _pi32]),
     "ndi_interp1d_set_search_mode": (_i32, [_vp, _i32]),
@@ -53,6 +54,8 @@ SIGNATURES = {
     "ndi_interp1d_cubic": (_i32, [_vp, _vp, _i64, _i32, _vp, _pi64]),
     "ndi_interp1d_cubic_dev": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "ndi_interp2d_create": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _u32, C.POINTER(_vp)]),
+    "ndi_interp2d_create_strided": (_i32, [_i32, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _u32,
+                                           C.POINTER(_vp)]),
     "ndi_interp2d_destroy": (_i32, [_vp]),
     "ndi_interp2d_info": (_i32, [_vp, _pi32, _pi64, _pi64, _pi64, _pi32]),
     "ndi_interp2d_set_search_mode": (_i32, [_vp, _i32]),
@@ -118,6 +121,22 @@ def check(st):
 
 def ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def view_args(a):
+    """an ndarray view as the C ABI takes it: (array kept alive, pointer to the first logical element, shape,
+    strides in elements).  numpy reports strides in bytes; a view whose byte strides are not multiples of the
+    item size (never produced by slicing) is copied."""
+    a = np.asarray(a)
+    if any(s % a.itemsize for s in a.strides):
+        a = np.ascontiguousarray(a)
+    shape = (C.c_int64 * max(a.ndim, 1))(*a.shape)
+    strides = (C.c_int64 * max(a.ndim, 1))(*(s // a.itemsize for s in a.strides))
+    return a, C.c_void_p(a.ctypes.data), shape, strides
+
+
+def is_dense(a):
+    return a.flags.c_contiguous
 
 
 def dtype_code(dt):

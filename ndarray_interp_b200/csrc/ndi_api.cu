@@ -390,6 +390,67 @@ static ndi_status scan_fast_tables(ndi_dtype dtype, const void* data_dev, size_t
     return NDI_OK;
 }
 
+// Dense device copy of a strided view (views and negative strides without a
+// host-side copy).  `base` addresses the view's FIRST logical element; strides are in elements.  A host view
+// whose memory span is at most twice its element count is uploaded as it lies and gathered on the device
+// (launch_pack_strided); a sparser one is gathered by the host into a staging buffer first, because moving
+// the whole span over PCIe would cost more than the gather.
+static ndi_status pack_view(const void* base, size_t es, int ndim, const int64_t* shape, const int64_t* strides,
+                            bool device_src, cudaStream_t st, void** dense) {
+    *dense = nullptr;
+    if (ndim < 1 || ndim > kMaxDims || !shape || !strides) return fail(NDI_INVALID_ARGUMENT, "views need 1..%d dimensions", kMaxDims);
+    StridedDesc d; d.ndim = ndim;
+    long long count = 1, lo = 0, hi = 0, dense_stride = 1;
+    bool is_dense = true;
+    for (int k = ndim - 1; k >= 0; --k) {
+        if (shape[k] < 1) return fail(NDI_INVALID_ARGUMENT, "empty view (shape[%d] = %lld)", k, (long long)shape[k]);
+        d.shape[k] = shape[k]; d.stride[k] = strides[k];
+        const long long reach = (long long)(shape[k] - 1) * strides[k];
+        if (reach < 0) lo += reach; else hi += reach;
+        if (shape[k] > 1 && strides[k] != dense_stride) is_dense = false;
+        dense_stride *= shape[k];
+        count *= shape[k];
+    }
+    const size_t bytes = (size_t)count * es;
+    CK(cudaMalloc(dense, bytes));
+    auto bail = [&](ndi_status s) { cudaFree(*dense); *dense = nullptr; return s; };
+#define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(cuda_fail(e_, #call)); } while (0)
+    if (is_dense) {
+        CKP(cudaMemcpyAsync(*dense, base, bytes, device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        return NDI_OK;
+    }
+    const long long span = hi - lo + 1;
+    const unsigned char* first = (const unsigned char*)base + lo * (long long)es;     // lowest address the view touches
+    if (device_src) {
+        CKP(launch_pack_strided(first, -lo, d, es, count, *dense, st));
+        return NDI_OK;
+    }
+    if (span <= 2 * count + 4096) {
+        void* raw = nullptr;
+        CKP(cudaMallocAsync(&raw, (size_t)span * es, st));
+        cudaError_t e = cudaMemcpyAsync(raw, first, (size_t)span * es, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = launch_pack_strided(raw, -lo, d, es, count, *dense, st);
+        cudaFreeAsync(raw, st);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "strided upload"));
+        return NDI_OK;
+    }
+    std::vector<unsigned char> stage(bytes);
+    std::vector<long long> idx((size_t)ndim, 0);
+    long long off = 0;
+    for (long long i = 0; i < count; ++i) {
+        memcpy(stage.data() + (size_t)i * es, (const unsigned char*)base + off * (long long)es, es);
+        for (int k = ndim - 1; k >= 0; --k) {                      // odometer over the logical index
+            off += strides[k];
+            if (++idx[(size_t)k] < shape[k]) break;
+            off -= strides[k] * shape[k]; idx[(size_t)k] = 0;
+        }
+    }
+    CKP(cudaMemcpyAsync(*dense, stage.data(), bytes, cudaMemcpyHostToDevice, st));
+    CKP(cudaStreamSynchronize(st));                                // the staging buffer goes away
+#undef CKP
+    return NDI_OK;
+}
+
 extern "C" {
 
 ndi_status ndi_selftest_fdiv(uint32_t a_mant_begin, uint32_t a_mant_count, int32_t a_exp, int32_t b_exp, uint64_t* mismatches) {
@@ -541,6 +602,31 @@ ndi_status ndi_interp1d_create(ndi_dtype dtype, const void* x, int64_t n, const 
     }
     if ((st = scan_fast_tables(dtype, h->data, (size_t)n * (size_t)w, ws, &h->fast_tables)) != NDI_OK) { ndi_interp1d_destroy(h); return st; }
     *out = h;
+    return NDI_OK;
+}
+
+ndi_status ndi_interp1d_create_strided(ndi_dtype dtype, const void* x, int64_t n, int64_t x_stride, const void* data,
+                                       int32_t ndim, const int64_t* shape, const int64_t* strides, uint32_t flags,
+                                       ndi_interp1d** out) {
+    if (!out) return fail(NDI_INVALID_ARGUMENT, "null handle pointer");
+    *out = nullptr;
+    if (!dtype_ok(dtype)) return fail(NDI_UNSUPPORTED_DTYPE, "unsupported dtype %d", (int)dtype);
+    if (!x || !data || !shape || !strides) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    if (flags & NDI_BORROW) return fail(NDI_INVALID_ARGUMENT, "a strided view cannot be borrowed: the kernels read dense tables");
+    if (ndim < 1 || ndim > kMaxDims) return fail(NDI_INVALID_ARGUMENT, "data needs 1..%d dimensions", kMaxDims);
+    if (shape[0] != n) return fail(NDI_INVALID_ARGUMENT, "data.shape[0] = %lld but x has %lld elements", (long long)shape[0], (long long)n);
+    int dev = 0; CK(cudaGetDevice(&dev));
+    ndi_status st; Workspace* ws = workspace(dev, &st); if (!ws) return st;
+    const size_t es = elem_size(dtype);
+    const bool dsrc = (flags & NDI_DEVICE_POINTERS) != 0;
+    int64_t w = 1;
+    for (int k = 1; k < ndim; ++k) w *= shape[k];
+    void *xd = nullptr, *dd = nullptr;
+    if ((st = pack_view(x, es, 1, &n, &x_stride, dsrc, ws->s[0], &xd)) != NDI_OK) return st;
+    if ((st = pack_view(data, es, ndim, shape, strides, dsrc, ws->s[0], &dd)) != NDI_OK) { cudaFree(xd); return st; }
+    st = ndi_interp1d_create(dtype, xd, n, dd, w, (flags & NDI_ASSUME_VALID) | NDI_DEVICE_POINTERS | NDI_BORROW, out);
+    if (st != NDI_OK) { cudaFree(xd); cudaFree(dd); return st; }
+    (*out)->owns_tables = true;                            // the dense copies belong to the handle
     return NDI_OK;
 }
 
@@ -980,6 +1066,34 @@ ndi_status ndi_interp2d_create(ndi_dtype dtype, const void* x, int64_t n, const 
     if (st == NDI_OK) st = scan_fast_tables(dtype, h->data, (size_t)n * (size_t)m * (size_t)w, ws, &h->fast_tables);
     if (st != NDI_OK) { ndi_interp2d_destroy(h); return st; }
     *out = h;
+    return NDI_OK;
+}
+
+ndi_status ndi_interp2d_create_strided(ndi_dtype dtype, const void* x, int64_t n, int64_t x_stride, const void* y,
+                                       int64_t m, int64_t y_stride, const void* data, int32_t ndim, const int64_t* shape,
+                                       const int64_t* strides, uint32_t flags, ndi_interp2d** out) {
+    if (!out) return fail(NDI_INVALID_ARGUMENT, "null handle pointer");
+    *out = nullptr;
+    if (!dtype_ok(dtype)) return fail(NDI_UNSUPPORTED_DTYPE, "unsupported dtype %d", (int)dtype);
+    if (!x || !y || !data || !shape || !strides) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    if (flags & NDI_BORROW) return fail(NDI_INVALID_ARGUMENT, "a strided view cannot be borrowed: the kernels read dense tables");
+    if (ndim < 2 || ndim > kMaxDims) return fail(NDI_INVALID_ARGUMENT, "data needs 2..%d dimensions", kMaxDims);
+    if (shape[0] != n || shape[1] != m)
+        return fail(NDI_INVALID_ARGUMENT, "data.shape[0..2] = (%lld, %lld) but the axes have (%lld, %lld) elements",
+                    (long long)shape[0], (long long)shape[1], (long long)n, (long long)m);
+    int dev = 0; CK(cudaGetDevice(&dev));
+    ndi_status st; Workspace* ws = workspace(dev, &st); if (!ws) return st;
+    const size_t es = elem_size(dtype);
+    const bool dsrc = (flags & NDI_DEVICE_POINTERS) != 0;
+    int64_t w = 1;
+    for (int k = 2; k < ndim; ++k) w *= shape[k];
+    void *xd = nullptr, *yd = nullptr, *dd = nullptr;
+    st = pack_view(x, es, 1, &n, &x_stride, dsrc, ws->s[0], &xd);
+    if (st == NDI_OK) st = pack_view(y, es, 1, &m, &y_stride, dsrc, ws->s[0], &yd);
+    if (st == NDI_OK) st = pack_view(data, es, ndim, shape, strides, dsrc, ws->s[0], &dd);
+    if (st == NDI_OK) st = ndi_interp2d_create(dtype, xd, n, yd, m, dd, w, (flags & NDI_ASSUME_VALID) | NDI_DEVICE_POINTERS | NDI_BORROW, out);
+    if (st != NDI_OK) { cudaFree(xd); cudaFree(yd); cudaFree(dd); return st; }
+    (*out)->owns_tables = true;
     return NDI_OK;
 }
 

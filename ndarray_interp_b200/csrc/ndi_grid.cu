@@ -197,6 +197,37 @@ template cudaError_t launch_grid_classify<int32_t>(const int32_t*, int64_t, int3
 template cudaError_t launch_grid_classify<int64_t>(const int64_t*, int64_t, int32_t*, uint32_t*, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
+// Dense copy of a strided view (ndi_interp*_create_strided): one thread per destination element,
+// destination writes coalesced, source reads as coalesced as the view's innermost stride allows.
+// ------------------------------------------------------------------------------------------------
+template <class U>
+__global__ void __launch_bounds__(256) pack_strided_kernel(const U* __restrict__ src, long long origin, StridedDesc d,
+                                                           long long count, U* __restrict__ dst) {
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += step) {
+        long long rest = i, off = origin;
+#pragma unroll 1
+        for (int k = d.ndim - 1; k >= 0; --k) {
+            const long long q = rest / d.shape[k];
+            off += (rest - q * d.shape[k]) * d.stride[k];
+            rest = q;
+        }
+        dst[i] = src[off];
+    }
+}
+
+cudaError_t launch_pack_strided(const void* src_dev, long long origin, const StridedDesc& d, size_t elem,
+                                long long count, void* dst_dev, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    const long long want = (count + 255) / 256, cap = (long long)device_info().sm_count * 16;
+    const int blocks = (int)(want < cap ? want : cap);
+    if (elem == 8) pack_strided_kernel<unsigned long long><<<blocks, 256, 0, st>>>((const unsigned long long*)src_dev, origin, d, count, (unsigned long long*)dst_dev);
+    else pack_strided_kernel<unsigned><<<blocks, 256, 0, st>>>((const unsigned*)src_dev, origin, d, count, (unsigned*)dst_dev);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // May the evaluation kernels divide with a per-query reciprocal (ndi_device.cuh, div_by)?  Yes when
 // every table value is finite and either 0 or of magnitude in [2^-56, 2^30].  *flag must be 1 on entry.
 // ------------------------------------------------------------------------------------------------

@@ -99,6 +99,14 @@ size_t lut_entry_bytes(size_t elem);
 template <class T>
 cudaError_t launch_build_lut(const T* x, int64_t n, double g0d, double scale, int nb, void* lut_dev, cudaStream_t st);
 
+// ---- strided views -> dense tables (ndi_grid.cu) ----------------------------------------------
+// dst[row-major index] = src[origin + sum(idx[d] * stride[d])], elements of `elem` bytes (4 or 8);
+// strides are in elements and may be negative or zero (ndarray views, interp1d/aliases.rs).
+constexpr int kMaxDims = 8;
+struct StridedDesc { int ndim; long long shape[kMaxDims]; long long stride[kMaxDims]; };
+cudaError_t launch_pack_strided(const void* src_dev, long long origin, const StridedDesc& d, size_t elem,
+                                long long count, void* dst_dev, cudaStream_t st);
+
 // ---- spline construction (ndi_spline.cu) -----------------------------------------------------
 // Builds a, b ((n-1) x w each) on the device.  For bc_kind == INDIVIDUAL the four boundary arrays are
 // device arrays of w entries; pos (device, w entries) gives every column its position when the

@@ -304,8 +304,16 @@ class _Handle1D:
         lib = L.require_device()
         self.ptr = C.c_void_p()
         w = int(np.prod(data.shape[1:], dtype=np.int64))
-        self.status = L.check(lib.ndi_interp1d_create(L.dtype_code(data.dtype), L.ptr(x), len(x), L.ptr(data), w, flags,
-                                                      C.byref(self.ptr)))
+        if L.is_dense(x) and L.is_dense(data):
+            self.status = L.check(lib.ndi_interp1d_create(L.dtype_code(data.dtype), L.ptr(x), len(x), L.ptr(data), w, flags,
+                                                          C.byref(self.ptr)))
+        else:
+            # views (any strides, negative included -- tests/interp1d.rs:143-155) go up as they lie in memory
+            # and are made dense on the device
+            xk, xp, _, xs = L.view_args(x)
+            dk, dp, shape, strides = L.view_args(data)
+            self.status = L.check(lib.ndi_interp1d_create_strided(L.dtype_code(data.dtype), xp, len(x), xs[0], dp, dk.ndim,
+                                                                  shape, strides, flags, C.byref(self.ptr)))
 
     def __del__(self):
         try:
@@ -423,9 +431,11 @@ def _is_builtin(strategy):
 
 
 def _prepare(x, data):
-    data = np.ascontiguousarray(data)                      # views / negative strides: one contiguous copy
+    data = np.asarray(data)                                # views / negative strides stay views (_Handle1D)
     L.dtype_code(data.dtype)
-    x = np.ascontiguousarray(x, dtype=data.dtype)
+    x = np.asarray(x)
+    if x.dtype != data.dtype:
+        x = x.astype(data.dtype)
     return x, data
 
 

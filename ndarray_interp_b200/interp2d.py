@@ -81,8 +81,15 @@ class _Handle2D:
         lib = L.require_device()
         self.ptr = C.c_void_p()
         w = int(np.prod(data.shape[2:], dtype=np.int64))
-        L.check(lib.ndi_interp2d_create(L.dtype_code(data.dtype), L.ptr(x), len(x), L.ptr(y), len(y), L.ptr(data), w,
-                                        flags, C.byref(self.ptr)))
+        if L.is_dense(x) and L.is_dense(y) and L.is_dense(data):
+            L.check(lib.ndi_interp2d_create(L.dtype_code(data.dtype), L.ptr(x), len(x), L.ptr(y), len(y), L.ptr(data), w,
+                                            flags, C.byref(self.ptr)))
+        else:                                              # views: uploaded as they lie, made dense on the device
+            xk, xp, _, xs = L.view_args(x)
+            yk, yp, _, ys = L.view_args(y)
+            dk, dp, shape, strides = L.view_args(data)
+            L.check(lib.ndi_interp2d_create_strided(L.dtype_code(data.dtype), xp, len(x), xs[0], yp, len(y), ys[0], dp,
+                                                    dk.ndim, shape, strides, flags, C.byref(self.ptr)))
 
     def __del__(self):
         try:
@@ -184,9 +191,10 @@ class Interp2D:
 
 
 def _prepare(x, y, data):
-    data = np.ascontiguousarray(data)
+    data = np.asarray(data)                                # views stay views (_Handle2D)
     L.dtype_code(data.dtype)
-    return np.ascontiguousarray(x, dtype=data.dtype), np.ascontiguousarray(y, dtype=data.dtype), data
+    x, y = np.asarray(x), np.asarray(y)
+    return (x if x.dtype == data.dtype else x.astype(data.dtype)), (y if y.dtype == data.dtype else y.astype(data.dtype)), data
 
 
 class Interp2DBuilder:

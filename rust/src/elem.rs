@@ -3,7 +3,7 @@ use std::fmt::Debug;
 
 use num_traits::{Num, NumCast};
 
-/// f32, f64 and i32 -- the types the reference's tests exercise.
+/// f32, f64, i32 (the types the reference's tests exercise) and i64.
 pub trait NdiElem: Num + NumCast + PartialOrd + Copy + Debug + Send + 'static {
     /// `ndi_dtype` code of `include/ndi_b200.h`
     const DTYPE: i32;
@@ -16,4 +16,7 @@ impl NdiElem for f64 {
 }
 impl NdiElem for i32 {
     const DTYPE: i32 = crate::ffi::NDI_I32;
+}
+impl NdiElem for i64 {
+    const DTYPE: i32 = crate::ffi::NDI_I64;
 }

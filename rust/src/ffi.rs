@@ -12,6 +12,7 @@ pub const NDI_NOT_MONOTONIC: ndi_status = 5;
 pub const NDI_F32: i32 = 0;
 pub const NDI_F64: i32 = 1;
 pub const NDI_I32: i32 = 2;
+pub const NDI_I64: i32 = 3;
 
 pub const NDI_ASSUME_VALID: u32 = 1;
 
@@ -37,6 +38,8 @@ extern "C" {
     pub fn ndi_interp1d_spline_coeffs(h: *const ndi_interp1d, a: *mut c_void, b: *mut c_void) -> ndi_status;
     pub fn ndi_interp1d_cubic(h: *const ndi_interp1d, q: *const c_void, nq: i64, extrap_mode: i32, out: *mut c_void, first_bad: *mut i64) -> ndi_status;
 
+    pub fn ndi_interp1d_create_strided(dtype: i32, x: *const c_void, n: i64, x_stride: i64, data: *const c_void, ndim: i32, shape: *const i64, strides: *const i64, flags: u32, out: *mut *mut ndi_interp1d) -> ndi_status;
+    pub fn ndi_interp2d_create_strided(dtype: i32, x: *const c_void, n: i64, x_stride: i64, y: *const c_void, m: i64, y_stride: i64, data: *const c_void, ndim: i32, shape: *const i64, strides: *const i64, flags: u32, out: *mut *mut ndi_interp2d) -> ndi_status;
     pub fn ndi_interp2d_create(dtype: i32, x: *const c_void, n: i64, y: *const c_void, m: i64, data: *const c_void, w: i64, flags: u32, out: *mut *mut ndi_interp2d) -> ndi_status;
     pub fn ndi_interp2d_destroy(h: *mut ndi_interp2d) -> ndi_status;
     /// locality binning of query batches by table band: 0 auto, 1 off, 2 on (csrc/ndi_bin.cu)

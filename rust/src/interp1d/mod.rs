@@ -241,7 +241,8 @@ where
     }
 }
 
-/// contiguous copy + upload of `(x, data)`; the strict-rising check runs on the device unless skipped
+/// upload of `(x, data)` as the views lie in memory (any strides: the library makes them dense on the device,
+/// no `as_standard_layout()` copy on the host); the strict-rising check runs on the device unless skipped
 pub(crate) fn upload<Sd, Sx, D>(x: &ArrayBase<Sx, Ix1>, data: &ArrayBase<Sd, D>, flags: u32) -> Result<DeviceTable1D, BuilderError>
 where
     Sd: Data,
@@ -249,16 +250,19 @@ where
     Sx: Data<Elem = Sd::Elem>,
     D: Dimension,
 {
-    let (xc, dc) = (x.as_standard_layout(), data.as_standard_layout());
-    let w: usize = data.shape()[1..].iter().product();
+    let shape: Vec<i64> = data.shape().iter().map(|&s| s as i64).collect();
+    let strides: Vec<i64> = data.strides().iter().map(|&s| s as i64).collect();   // ndarray strides are in elements
     let mut handle = std::ptr::null_mut();
     let st = unsafe {
-        ffi::ndi_interp1d_create(
+        ffi::ndi_interp1d_create_strided(
             <Sd::Elem as NdiElem>::DTYPE,
-            xc.as_ptr() as *const c_void,
-            xc.len() as i64,
-            dc.as_ptr() as *const c_void,
-            w as i64,
+            x.as_ptr() as *const c_void,          // first logical element, also for negative strides
+            x.len() as i64,
+            x.strides()[0] as i64,
+            data.as_ptr() as *const c_void,
+            shape.len() as i32,
+            shape.as_ptr(),
+            strides.as_ptr(),
             flags,
             &mut handle,
         )

@@ -297,18 +297,23 @@ where
     Sy: Data<Elem = Sd::Elem>,
     D: Dimension,
 {
-    let (xc, yc, dc) = (x.as_standard_layout(), y.as_standard_layout(), data.as_standard_layout());
-    let w: usize = data.shape()[2..].iter().product();
+    // views go up as they lie in memory; the library makes them dense on the device
+    let shape: Vec<i64> = data.shape().iter().map(|&s| s as i64).collect();
+    let strides: Vec<i64> = data.strides().iter().map(|&s| s as i64).collect();
     let mut handle = std::ptr::null_mut();
     let st = unsafe {
-        ffi::ndi_interp2d_create(
+        ffi::ndi_interp2d_create_strided(
             <Sd::Elem as NdiElem>::DTYPE,
-            xc.as_ptr() as *const c_void,
-            xc.len() as i64,
-            yc.as_ptr() as *const c_void,
-            yc.len() as i64,
-            dc.as_ptr() as *const c_void,
-            w as i64,
+            x.as_ptr() as *const c_void,
+            x.len() as i64,
+            x.strides()[0] as i64,
+            y.as_ptr() as *const c_void,
+            y.len() as i64,
+            y.strides()[0] as i64,
+            data.as_ptr() as *const c_void,
+            shape.len() as i32,
+            shape.as_ptr(),
+            strides.as_ptr(),
             flags,
             &mut handle,
         )

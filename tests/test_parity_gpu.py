@@ -490,3 +490,78 @@ def test_i64_builder_checks_and_errors():
     with pytest.raises(InterpolateError.OutOfBounds):
         interp.interp_scalar(i(3))
     assert monotonic_prop(np.array([1 << 62, (1 << 62) + 1, (1 << 62) + 1], i)) == Monotonic.Rising(False)
+
+
+# ---- strided views (tests/interp1d.rs:143-155 builds from negative strides) ---
+def _views_1d(rng, dt):
+    base = make_data(rng, (64, 12, 10), dt)
+    g = make_grid(rng, 64, dt, "random")
+    gpad = np.zeros(64 * 3, dt); gpad[::3] = g
+    yield "negative axis 0 + reversed grid", g[::-1][::-1], base[::-1]
+    yield "grid with stride 3", gpad[::3], base
+    yield "trailing step", g, base[:, ::2, 1:9:3]
+    yield "transposed trailing axes", g, base.transpose(0, 2, 1)
+    yield "negative trailing", g, base[:, ::-1, ::-1]
+    yield "sparse (host gather path)", g[::7][:9], base[::7, ::5, ::6][:9]
+    yield "broadcast (zero stride)", g, np.broadcast_to(base[:, :1, :], base.shape)
+    yield "1-d data view", g[::2], base[::2, 3, 4]
+    yield "fortran order", g, np.asfortranarray(base)
+
+
+@pytest.mark.parametrize("dt", DTS, ids=lambda d: np.dtype(d).name)
+def test_strided_views_build_without_a_host_copy_1d(dt):
+    rng = np.random.default_rng(77)
+    for name, g, d in _views_1d(rng, dt):
+        assert not (g.flags.c_contiguous and d.flags.c_contiguous), name
+        q = make_queries(rng, np.ascontiguousarray(g), 3000, dt, outside=True)
+        st, ref, _ = O.interp1d_linear(np.ascontiguousarray(g), np.ascontiguousarray(d), q, True)
+        assert st == O.ST_OK
+        ip = Interp1D.builder(d).x(g).strategy(Linear.new().extrapolate(True)).build()
+        assert ip.data is d                                # the view itself is kept: no host-side copy
+        assert same(ip.interp_array(q), ref), name
+    # the monotonic check sees the view, not its memory order
+    with pytest.raises(BuilderError.Monotonic):
+        Interp1D.builder(np.zeros(10, dt)).x(np.arange(10).astype(dt)[::-1]).build()
+
+
+def test_strided_views_2d_and_splines():
+    rng = np.random.default_rng(78)
+    base = rng.normal(size=(40, 30, 6))
+    gx, gy = np.cumsum(rng.uniform(0.5, 1.5, 40)), np.cumsum(rng.uniform(0.5, 1.5, 30))
+    for d, x, y in [(base[::-1, :, ::2], gx, gy), (base.transpose(1, 0, 2), gy, gx),
+                    (base[::2, ::3], gx[::2], gy[::3]), (np.asfortranarray(base), gx[::-1][::-1], gy)]:
+        qx = rng.uniform(x[0], x[-1], 5000); qy = rng.uniform(y[0], y[-1], 5000)
+        st, ref, _, _ = O.interp2d_bilinear(np.ascontiguousarray(x), np.ascontiguousarray(y), np.ascontiguousarray(d), qx, qy, False)
+        assert st == O.ST_OK
+        assert same(Interp2D.builder(d).x(x).y(y).build().interp_array(qx, qy), ref)
+    from ndarray_interp_b200.interp1d import CubicSpline
+    d = base[:, ::-2, 1]
+    q = rng.uniform(gx[0], gx[-1], 4000)
+    got = Interp1D.builder(d).x(gx).strategy(CubicSpline.new()).build().interp_array(q)
+    want = Interp1D.builder(np.ascontiguousarray(d)).x(gx).strategy(CubicSpline.new()).build().interp_array(q)
+    assert same(got, want)
+
+
+def test_strided_create_c_abi_rejects_bad_arguments_and_takes_device_views():
+    import torch
+    lib = L.require_device()
+    h = C.c_void_p()
+    x = np.arange(5.0); d = np.arange(10.0).reshape(5, 2)
+    shape = (C.c_int64 * 2)(5, 2); strides = (C.c_int64 * 2)(2, 1)
+    call = lambda n, ndim, flags: lib.ndi_interp1d_create_strided(L.F64, L.ptr(x), n, 1, L.ptr(d), ndim, shape, strides, flags, C.byref(h))
+    assert call(4, 2, 0) == L.INVALID_ARGUMENT            # x length != shape[0]
+    assert call(5, 9, 0) == L.INVALID_ARGUMENT            # too many dimensions
+    assert call(5, 2, 4) == L.INVALID_ARGUMENT            # NDI_BORROW
+    # device views: a transposed torch tensor is packed on the device
+    t = torch.arange(24, dtype=torch.float64, device="cuda").reshape(4, 6).t()          # shape (6, 4), strides (1, 6)
+    xs = torch.arange(6, dtype=torch.float64, device="cuda")
+    shape = (C.c_int64 * 2)(6, 4); strides = (C.c_int64 * 2)(*t.stride())
+    torch.cuda.synchronize()
+    st = lib.ndi_interp1d_create_strided(L.F64, C.c_void_p(xs.data_ptr()), 6, 1, C.c_void_p(t.data_ptr()), 2, shape, strides,
+                                         2, C.byref(h))
+    assert st == L.OK
+    q = np.array([0.5, 4.25]); out = np.zeros((2, 4)); bad = C.c_int64(-1)
+    assert lib.ndi_interp1d_linear(h, L.ptr(q), 2, 0, L.ptr(out), C.byref(bad)) == L.OK
+    tn = t.cpu().numpy()
+    assert np.array_equal(out[0], tn[0] + 0.5 * (tn[1] - tn[0])) and np.array_equal(out[1], tn[4] + 0.25 * (tn[5] - tn[4]))
+    lib.ndi_interp1d_destroy(h)
