@@ -146,10 +146,16 @@ __global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THI
 #pragma unroll
                 for (int r = 0; r < LPQ; ++r) {
                     const int src = r * QPR + qsel;
+#if NDI_PACK_SHFL >= 1
+                    const int is = __shfl_sync(0xffffffffu, skip[t] ? -1 : idx[t], src);
+                    const bool live_s = is >= 0;
+#else
                     const int is = __shfl_sync(0xffffffffu, idx[t], src);
-                    const Slope<T> sl = slope[t].from_lane(src);
+                    const bool live_s = !shfl_b(skip[t], src);
+#endif
                     const T dq = shfl_t(dxq[t], src);
-                    if (!shfl_b(skip[t], src) && colok) {
+                    const Slope<T> sl = slope[t].from_lane(src, dq, p.fast_tables != 0);
+                    if (live_s && colok) {
                         if (!one_interval) {
                             const T* row = p.data + (long long)is * p.w + col;
                             y1 = ld_table<T, V>(row);
@@ -288,9 +294,20 @@ __global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THI
 #pragma unroll
                 for (int r = 0; r < LPQ; ++r) {
                     const int src = r * QPR + qsel;
+#if NDI_PACK_SHFL >= 1
+                    const int is = __shfl_sync(0xffffffffu, skip[t] ? -1 : idx[t], src);
+                    const bool live_s = is >= 0;
+#else
                     const int is = __shfl_sync(0xffffffffu, idx[t], src);
+                    const bool live_s = !shfl_b(skip[t], src);
+#endif
+#if NDI_PACK_CUBIC >= 2
+                    const T ts = shfl_t(tq[t], src);
+                    const T os = Ar<T>::sub(one, ts), tts = Ar<T>::mul(ts, os);       // the operations of :818-827 again
+#else
                     const T ts = shfl_t(tq[t], src), os = shfl_t(omt[t], src), tts = shfl_t(tt[t], src);
-                    if (!shfl_b(skip[t], src) && colok) {
+#endif
+                    if (live_s && colok) {
                         if (!one_interval) {
                             const long long ro = (long long)is * p.w + col;
                             yl = ld_table<T, V>(p.data + ro);
@@ -426,12 +443,18 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (LPQ <= 2 ? 5 : 4) : 
 #pragma unroll
                 for (int r = 0; r < LPQ; ++r) {
                     const int src = r * QPR + qsel;
+#if NDI_PACK_SHFL >= 1
+                    const long long cs = __shfl_sync(0xffffffffu, skip[t] ? -1ll : cell[t], src);
+                    const bool live_s = cs >= 0;
+#else
                     const long long cs = __shfl_sync(0xffffffffu, cell[t], src);
-                    const Slope<T> ssx = slx[t].from_lane(src), ssy = sly[t].from_lane(src);
+                    const bool live_s = !shfl_b(skip[t], src);
+#endif
                     const T sbx = shfl_t(bx[t], src), sby = shfl_t(by[t], src);
+                    const Slope<T> ssx = slx[t].from_lane(src, sbx, p.fast_tables != 0), ssy = sly[t].from_lane(src, sby, p.fast_tables != 0);
                     long long srow = qbase + src;
                     if constexpr (PERM) srow = __shfl_sync(0xffffffffu, orow[t], src);
-                    if (!shfl_b(skip[t], src) && colok) {
+                    if (live_s && colok) {
                         const T* c0 = p.data + cs + col;
                         const Vec<T, V> z11 = ld_table<T, V>(c0), z12 = ld_table<T, V>(c0 + p.w);
                         const Vec<T, V> z21 = ld_table<T, V>(c0 + rowx), z22 = ld_table<T, V>(c0 + rowx + p.w);
