@@ -296,6 +296,7 @@ static ndi_status build_aids(ndi_dtype dtype, const void* grid, int64_t n, cudaS
     CK(cudaStreamSynchronize(st));
     int nb = 16;
     while (nb < (int64_t)NDI_LUT_PER_POINT * n && nb < (1 << 24)) nb <<= 1;
+    while ((size_t)nb * lut_entry_bytes(elem) > ((size_t)128 << 20) && nb > 16) nb >>= 1;   // keep the table well inside L2
     double g0d, scale;
     if (dtype == NDI_F32) {
         float a, b; memcpy(&a, ends, 4); memcpy(&b, ends + 8, 4);

@@ -57,14 +57,9 @@ __device__ __forceinline__ void bands_of(const GridView<T>& g, const T (&x)[K], 
             band[k] = f > (F)0 ? (f < (F)(g.n - 2) ? (int)f : g.n - 2) : 0;      // NaN -> 0
         }
     } else if (g.mode == SEARCH_LUT) {
-        typedef typename LutEntry<T>::type Entry;
-        const Entry* lut = static_cast<const Entry*>(g.lut);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const Entry e = __ldg(lut + bucket_of<T>(x[k], g.g0d, g.scale, g.nb));
-            if constexpr (sizeof(Entry) == 16) band[k] = e.x >= 0 ? e.x : -e.x - 1;
-            else band[k] = e.x;
-        }
+        for (int k = 0; k < K; ++k)
+            band[k] = lut_tag_index(LutEntry<T>::load_tag(g.lut, bucket_of<T>(x[k], g.g0d, g.scale, g.nb)));
     } else {
         T vlo[K], vhi[K];
         search_multi<T, K>(g, x, band, vlo, vhi);

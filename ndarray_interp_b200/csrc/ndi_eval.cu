@@ -83,6 +83,9 @@ constexpr int kTilesLinear = NDI_TPW_LINEAR, kTilesCubic = NDI_TPW_CUBIC, kTiles
 #ifndef NDI_THIN_MINBLOCKS
 #define NDI_THIN_MINBLOCKS 0          // 0: leave the register budget to ptxas
 #endif
+// (Measured and dropped: issuing the NEXT tile's bucket-table probe before this tile's gathers -- C3 0.3110 ->
+// 0.3090 ms, C3d 0.634 -> 0.627: these kernels are bound by L1TEX / L2 throughput, not by the length of the
+// dependent chain; profiles/r01/gather_ceiling.md.)
 template <class T, int V, int LPQ>
 __global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THIN_MINBLOCKS : 0) interp1d_linear_kernel(const Eval1<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

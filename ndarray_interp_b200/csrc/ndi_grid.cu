@@ -153,7 +153,8 @@ cudaError_t launch_grid_classify(const T* x, int64_t n, int32_t* result_dev, uin
 template <class T>
 __global__ void __launch_bounds__(256) build_lut_kernel(const T* __restrict__ x, int n, double g0d, double scale, int nb,
                                                         typename LutEntry<T>::type* __restrict__ lut) {
-    typedef typename LutEntry<T>::type Entry;
+    typedef LutEntry<T> L;
+    typedef typename L::type Entry;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     auto count_below = [&](int bb) {
@@ -165,19 +166,24 @@ __global__ void __launch_bounds__(256) build_lut_kernel(const T* __restrict__ x,
         return lo;
     };
     const int c0 = count_below(b), c1 = count_below(b + 1);
-    if constexpr (sizeof(Entry) == 16) {
-        Entry e;
-        if (c0 == c1 && c0 >= 1 && c0 <= n - 1) {      // no grid point in this bucket: one interval for all of it
-            const T lo = x[c0 - 1], hi = x[c0];
-            e.x = c0 - 1; e.y = *reinterpret_cast<const int*>(&lo); e.z = *reinterpret_cast<const int*>(&hi); e.w = 0;
-        } else { e.x = -(c0 + 1); e.y = c1; e.z = 0; e.w = 0; }
-        lut[b] = e;
-    } else {
-        lut[b] = make_int2(c0, c1);
+    Entry e;
+    // the index every query of this bucket gets when the bucket holds no grid point, or only g[0] / g[n-1]
+    // (get_lower_index clamps to 0 and n-2 on both sides of those two, vector_extensions.rs:61-66)
+    int flat = -1;
+    if (c0 == c1) flat = min(max(c0 - 1, 0), n - 2);
+    else if (c1 == c0 + 1 && c0 == 0) flat = 0;
+    else if (c1 == c0 + 1 && c0 == n - 1) flat = n - 2;
+    if (flat >= 0 && flat < kLutOnePoint) {                                   // kind A
+        e.tag = flat; e.v0 = x[flat]; e.v1 = x[flat + 1]; e.v2 = x[flat + 1];
+    } else if (c1 == c0 + 1 && c0 < kLutOnePoint) {                           // kind B: 1 <= c0 <= n-2 here
+        e.tag = c0 | kLutOnePoint; e.v0 = x[c0 - 1]; e.v1 = x[c0]; e.v2 = x[c0 + 1];
+    } else {                                                                  // kind C
+        e.tag = -(c0 + 1); e.v0 = L::as_count(c1); e.v1 = e.v0; e.v2 = e.v0;
     }
+    lut[b] = e;
 }
 
-size_t lut_entry_bytes(size_t elem) { return elem == 4 ? 16 : 8; }
+size_t lut_entry_bytes(size_t elem) { return elem == 4 ? 16 : 32; }
 
 template <class T>
 cudaError_t launch_build_lut(const T* x, int64_t n, double g0d, double scale, int nb, void* lut_dev, cudaStream_t st) {
