@@ -122,6 +122,7 @@ struct Workspace {
     cudaEvent_t ev = nullptr;
     void* d_q[2] = {nullptr, nullptr}; size_t d_q_cap[2] = {0, 0};
     void* d_out[2] = {nullptr, nullptr}; size_t d_out_cap[2] = {0, 0};
+    void* d_build = nullptr; size_t d_build_cap = 0;       // spline-build scratch, kept between builds (up to kBuildKeepBytes)
     unsigned long long* d_err = nullptr;      // 4 words
     int32_t* d_res = nullptr;                 // 2 words (grid classify result)
     uint32_t* d_scr = nullptr;                // grid classify scratch
@@ -912,28 +913,38 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
             for (int g = 0; g < 9; ++g) { next[g] = acc; acc += group_count[g]; }
             for (int64_t c = 0; c < h->w; ++c) pos_host[(size_t)c] = (int32_t)next[3 * variant(left_kind[c]) + variant(right_kind[c])]++;
         }
-        // everything comes from the stream-ordered pool (device_info() keeps freed blocks cached), so a
-        // rebuild does not pay cudaMalloc / cudaFree
+        // The scratch matrix and the per-column boundary arrays live in one per-thread buffer that is kept between
+        // builds: taken from the stream-ordered pool instead, the wall time of a build depended on the pool's
+        // history (scripts/probe_spline_calls.py: the first four calls on a new handle 2 - 10 x slower, 61 ms
+        // outliers when consecutive builds asked for different sizes).  a / b come from the pool: they outlive
+        // the call, and the previous pair must stay valid until this build has succeeded.
         cudaStream_t bs = ws->s[0];
+        constexpr size_t kBuildKeepBytes = (size_t)1 << 30;
         auto cleanup = [&](bool keep) {
-            cudaFreeAsync(scratch, bs); cudaFreeAsync(lv, bs); cudaFreeAsync(rv, bs); cudaFreeAsync(lk, bs); cudaFreeAsync(rk, bs);
-            cudaFreeAsync(pos, bs);
+            if (ws->d_build_cap > kBuildKeepBytes) { cudaFree(ws->d_build); ws->d_build = nullptr; ws->d_build_cap = 0; }
             if (!keep) { cudaFreeAsync(a, bs); cudaFreeAsync(b, bs); }
             cudaGetLastError();
         };
         auto body = [&]() -> ndi_status {
             device_info();
+            auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+            const size_t scratch_bytes = up(spline_scratch_elems<T>(h->n, h->w, bc_kind) * sizeof(T));
+            const size_t col_i = up((size_t)h->w * sizeof(int32_t)), col_t = up((size_t)h->w * sizeof(T));
+            const size_t need = scratch_bytes + (bc_kind == NDI_BC_INDIVIDUAL ? 3 * col_i + 2 * col_t : 0);
+            ndi_status gs = grow(&ws->d_build, &ws->d_build_cap, need);
+            if (gs != NDI_OK) return gs;
+            unsigned char* base = static_cast<unsigned char*>(ws->d_build);
+            scratch = reinterpret_cast<T*>(base);
             CK(cudaMallocAsync((void**)&a, coef_bytes, bs));
             CK(cudaMallocAsync((void**)&b, coef_bytes, bs));
-            CK(cudaMallocAsync((void**)&scratch, spline_scratch_elems<T>(h->n, h->w, bc_kind) * sizeof(T), bs));
             if (bc_kind == NDI_BC_INDIVIDUAL) {
-                CK(cudaMallocAsync((void**)&lk, h->w * sizeof(int32_t), bs)); CK(cudaMallocAsync((void**)&rk, h->w * sizeof(int32_t), bs));
-                CK(cudaMallocAsync((void**)&lv, h->w * sizeof(T), bs)); CK(cudaMallocAsync((void**)&rv, h->w * sizeof(T), bs));
+                lk = reinterpret_cast<int32_t*>(base + scratch_bytes); rk = reinterpret_cast<int32_t*>(base + scratch_bytes + col_i);
+                pos = reinterpret_cast<int32_t*>(base + scratch_bytes + 2 * col_i);
+                lv = reinterpret_cast<T*>(base + scratch_bytes + 3 * col_i); rv = reinterpret_cast<T*>(base + scratch_bytes + 3 * col_i + col_t);
                 CK(cudaMemcpyAsync(lk, left_kind, h->w * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
                 CK(cudaMemcpyAsync(rk, right_kind, h->w * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
                 CK(cudaMemcpyAsync(lv, left_val, h->w * sizeof(T), cudaMemcpyHostToDevice, bs));
                 CK(cudaMemcpyAsync(rv, right_val, h->w * sizeof(T), cudaMemcpyHostToDevice, bs));
-                CK(cudaMallocAsync((void**)&pos, h->w * sizeof(int32_t), bs));
                 CK(cudaMemcpyAsync(pos, pos_host.data(), h->w * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
             }
             CK(cudaMemsetAsync(ws->d_err, 0xff, sizeof(uint64_t), bs));

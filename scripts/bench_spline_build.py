@@ -6,7 +6,6 @@ import sys
 import time
 
 import numpy as np
-import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -33,7 +32,8 @@ def main():
                rng.integers(0, 5, w).astype(np.int32), rng.normal(size=w).astype(ndt))
         for bc, code in BC.items():
             extra = ind if bc == "Individual" else ()
-            ip.spline_build(code, *extra)
+            for _ in range(6):                              # the first calls on a new handle grow the stream-ordered
+                ip.spline_build(code, *extra)               # pool (scripts/probe_spline_calls.py: 4 slow calls, then steady)
             torch.cuda.synchronize()
             reps, t0 = 5, time.perf_counter()
             for _ in range(reps):
