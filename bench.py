@@ -88,6 +88,23 @@ def recorded_traffic(name):
         return None
 
 
+def recorded_pattern_ceiling(name):
+    """ms the workload's ACCESS PATTERN alone takes on a B200 (random segment gathers + streaming stores, no search,
+    no arithmetic: scripts/gather_ceiling.cu, recorded in profiles/r01/gather_ceiling.jsonl), if measured"""
+    key = {"c3": "c3:", "c4": "c4:", "c4x": "c4:"}.get(name)
+    p = os.path.join(ROOT, "profiles", "r01", "gather_ceiling.jsonl")
+    if not key or not os.path.exists(p):
+        return None
+    try:
+        for ln in open(p):
+            d = json.loads(ln)
+            if d["shape"].startswith(key):
+                return d["ms_mean"]
+    except Exception:
+        pass
+    return None
+
+
 # ---- synthetic inputs (seeded; numpy on the host so the CPU leg sees the very same arrays) ----------
 def make_host_inputs(wl, rank):
     dt = np.float32 if wl["dtype"] == "f32" else np.float64
@@ -512,7 +529,10 @@ def run_b200(args, wl, name):
                        "timed": "whole step (all launches of the step) with CUDA events on the launch stream"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(name), "algorithmic_bytes": abytes, "peak_source": peak_src,
-                         "frac_of_nominal_8000": achieved / 8000.0},
+                         "frac_of_nominal_8000": achieved / 8000.0,
+                         # thin rows: a random gather out of L2 / DRAM cannot run at the HBM streaming rate; what the
+                         # memory system gives the access pattern alone was measured separately (a recorded number)
+                         "access_pattern_ceiling_ms": recorded_pattern_ceiling(name)},
             "per_step": step_stats,
             "cpu_baseline": cpu,
             "spline_build": spline_build,

@@ -1,6 +1,7 @@
 #!/bin/bash
 # access-pattern ceiling of the thin-row kernels (scripts/gather_ceiling.cu) + SM<->L2 traffic of C3's kernel beside it
 mkdir -p gpurun_out
+[ -x scripts/gather_ceiling.bin ] || nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o scripts/gather_ceiling.bin scripts/gather_ceiling.cu
 M=gpu__time_duration.sum,lts__t_sectors.sum,lts__t_sectors_srcunit_tex.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_write.sum,l1tex__m_xbar2l1tex_read_bytes.sum,l1tex__m_l1tex2xbar_write_bytes.sum,l1tex__data_pipe_lsu_wavefronts.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,sm__cycles_elapsed.max
 scripts/gather_ceiling.bin > gpurun_out/gather_ceiling.jsonl 2> gpurun_out/gather_ceiling.err; echo "ceiling rc=$?"; cat gpurun_out/gather_ceiling.jsonl
 ncu --metrics $M --clock-control none -c 4 --csv --log-file gpurun_out/gather_ceiling_ncu.csv scripts/gather_ceiling.bin > /dev/null 2>&1
