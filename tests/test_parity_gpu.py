@@ -565,3 +565,35 @@ def test_strided_create_c_abi_rejects_bad_arguments_and_takes_device_views():
     tn = t.cpu().numpy()
     assert np.array_equal(out[0], tn[0] + 0.5 * (tn[1] - tn[0])) and np.array_equal(out[1], tn[4] + 0.25 * (tn[5] - tn[4]))
     lib.ndi_interp1d_destroy(h)
+
+
+# ---- empty and 0-d query arrays (ndarray accepts both; the batch loops of interp1d/mod.rs:300-343 then run 0 / 1 times)
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32])
+def test_empty_and_zero_dimensional_queries(dt):
+    from ndarray_interp_b200.interp1d import CubicSpline
+    rng = np.random.default_rng(11)
+    g = make_grid(rng, 30, dt, "random")
+    d1 = make_data(rng, (30, 4, 3), dt)
+    strategies = [Linear.new(), Linear.new().extrapolate(True)]
+    if np.issubdtype(dt, np.floating):
+        strategies.append(CubicSpline.new())
+    for strat in strategies:
+        ip = Interp1D.builder(d1).x(g).strategy(strat).build()
+        for shape in [(0,), (0, 5), (3, 0, 2)]:
+            out = ip.interp_array(np.zeros(shape, dt))
+            assert out.shape == shape + (4, 3) and out.dtype == dt
+        x0 = g[7]                                                  # a knot: the result is the data row itself
+        out = ip.interp_array(np.array(x0))                        # Ix0 query -> data.shape[1:]
+        assert out.shape == (4, 3) and same(out, d1[7])
+        buf = np.full((0, 4, 3), 9, dt)
+        ip.interp_array_into(np.zeros(0, dt), buf)                 # nothing to write, nothing to fail
+    gy = make_grid(rng, 12, dt, "uniform")
+    d2 = make_data(rng, (30, 12, 2), dt)
+    ip2 = Interp2D.builder(d2).x(g).y(gy).build()
+    assert ip2.interp_array(np.zeros((0, 4), dt), np.zeros((0, 4), dt)).shape == (0, 4, 2)
+    assert same(ip2.interp_array(np.array(g[3]), np.array(gy[5])), d2[3, 5])
+    # the C ABI itself: nq = 0 is a no-op with any pointers, nq < 0 is an argument error
+    lib = L.require_device()
+    bad = C.c_int64(-1)
+    assert lib.ndi_interp1d_linear(ip._handle(), None, 0, 0, None, C.byref(bad)) == L.OK and bad.value == -1
+    assert lib.ndi_interp1d_linear(ip._handle(), None, -1, 0, None, C.byref(bad)) == L.INVALID_ARGUMENT
