@@ -22,6 +22,8 @@ tables are replicated by NCCL (spline built column-sharded, coefficients all-gat
 rank evaluates its own 2^20-query shard (weak scaling), no collective on the timed path.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import sys
@@ -571,9 +573,26 @@ def main():
                     help="lower-index search strategy for measurement (0 auto, 1 global bisect, 2 smem bisect, 3 guess, 4 bucket table)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
-        return run_reference(args, wl, args.workload)
-    return run_b200(args, wl, args.workload)
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." at the
+    # first communicator, seen on the GPU boxes), so everything but the final line goes to stderr: file
+    # descriptor 1 points at stderr while the run is in progress and is restored for the JSON line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(out):
+            rc = run_reference(args, wl, args.workload) if args.impl == "reference" else run_b200(args, wl, args.workload)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    lines = [ln for ln in out.getvalue().splitlines() if ln.strip()]
+    for ln in lines[:-1]:
+        print(ln, file=sys.stderr)
+    if lines:
+        print(lines[-1], flush=True)
+    return rc
 
 
 if __name__ == "__main__":
