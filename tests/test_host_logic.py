@@ -84,3 +84,23 @@ def test_boundary_enums():
     assert RowBoundary.Mixed(SingleBoundary.NotAKnot, SingleBoundary.FirstDeriv(0.5)).kind == "Mixed"
     assert Linear.new().extrapolate(True)._extrapolate is True
     assert repr(Monotonic.Rising(True)) == "Rising { strict: true }"
+
+
+def test_view_args_describe_an_ndarray_view_the_way_the_c_abi_takes_it():
+    """pointer to the FIRST LOGICAL element, shape, strides in elements (ndarray's convention; numpy reports bytes)"""
+    from ndarray_interp_b200 import _lib as L
+    base = np.arange(4 * 6 * 5, dtype=np.float64).reshape(4, 6, 5)
+    v = base[::-1, 1::2, ::-2]
+    keep, ptr, shape, strides = L.view_args(v)
+    assert keep is v and list(shape) == [4, 3, 3] and list(strides) == [-30, 10, -2]
+    assert ptr.value == base.ctypes.data + base[3, 1, 4:].ctypes.data - base.ctypes.data     # element [3, 1, 4] of base
+    assert not L.is_dense(v) and L.is_dense(base) and L.is_dense(base[1]) and not L.is_dense(base[:, 0])
+    one = np.arange(10, dtype=np.int64)[::-3]
+    keep, ptr, shape, strides = L.view_args(one)
+    assert list(shape) == [4] and list(strides) == [-3] and ptr.value == one.ctypes.data
+    # broadcast views have zero strides; a byte-misaligned view (structured field) is copied
+    b = np.broadcast_to(np.arange(3.0)[:, None], (3, 4))
+    assert list(L.view_args(b)[3]) == [1, 0]
+    rec = np.zeros(5, dtype=[("pad", "u1"), ("v", "<f8")])["v"]
+    keep, _, _, strides = L.view_args(rec)
+    assert keep is not rec and list(strides) == [1]
