@@ -203,3 +203,28 @@ def test_fma_would_break_parity():
     got = np.array([O.calc_frac(float(a), float(b), float(c), float(d), float(e), np.float32)
                     for a, b, c, d, e in zip(x1, y1, x2, y2, x)], dtype=np.float32)
     assert np.array_equal(got, ref)
+
+
+def test_row_split_study_solves_the_same_system_as_the_oracle():
+    """scripts/pcr_accuracy_study.py (groundwork for a row-split spline build): its sequential
+    solve must be the oracle's, bit for bit, and PCR + Thomas must stay far inside north_star's bars"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "pcr_accuracy_study", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "pcr_accuracy_study.py"))
+    P = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(P)
+    rng = np.random.default_rng(5)
+    for dt, bar in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        x = np.cumsum(rng.uniform(0.5, 1.5, 300)).astype(dt)
+        y = rng.normal(size=(300, 3)).astype(dt)
+        low, mid, up, rhs = P.system_natural(x, y)
+        a, b = P.coefficients(x, y, P.thomas(low, mid, up, rhs))
+        st, ra, rb = O.spline_build(x, y, {"kind": "Natural"})
+        assert st == O.ST_OK and np.array_equal(a, ra) and np.array_equal(b, rb)
+        q = np.sort(rng.uniform(x[0], x[-1], 2000)).astype(dt)
+        ref = P.evaluate(x, y, a, b, q)
+        for levels in (1, 2, 4):
+            val = P.evaluate(x, y, *P.coefficients(x, y, P.pcr_then_thomas(low, mid, up, rhs, levels)), q)
+            scale = np.maximum(np.abs(ref), np.abs(y).max(axis=0)[None, :])
+            assert float((np.abs(val - ref) / scale).max()) < bar / 10
