@@ -19,6 +19,10 @@
 //
 // Reference citations are relative to /root/reference/.
 //
+// One function here is NOT a restatement of the reference: rowsplit_thomas (ora_spline_build_rowsplit_*), the
+// operation-by-operation specification of a row-split (PCR + Thomas) solve that is not built yet (DESIGN.md section
+// 7); it is checked against the sequential solve at north_star's tolerances and never used for parity of shipped code.
+//
 // Element types: f32, f64 (all entry points) and i32 / i64 (everything except splines, which
 // the reference restricts to float types through SplineNum, cubic_spline.rs:34-49).
 // Integer arithmetic wraps on overflow like a Rust release build.
@@ -217,6 +221,56 @@ void thomas(T* k, const T* a_up, T* a_mid, const T* a_low, T* rhs, int64_t len, 
     }
 }
 
+// Row-split variant of the solve (NOT the reference's order): `levels` steps of
+// parallel cyclic reduction, then thomas() on each of the 2^levels interleaved systems (rows j, j+S, j+2S, ...).
+// It exists so that a future row-split build kernel has an operation-by-operation specification to be compared
+// with, the way every shipped kernel is compared with the functions above.  One reduction step with stride s:
+//     alpha = -(low[i] / mid[i-s])   (0 when i-s < 0)        gamma = -(up[i] / mid[i+s])   (0 when i+s > len-1)
+//     low'[i] = alpha * low[i-s]     up'[i] = gamma * up[i+s]
+//     mid'[i] = (mid[i] + alpha * up[i-s]) + gamma * low[i+s]
+//     rhs'[i] = (rhs[i] + alpha * rhs[i-s]) + gamma * rhs[i+s]          (per column)
+// every product and sum rounded on its own (no FMA), the i-s term before the i+s term.
+template <class T>
+void rowsplit_thomas(T* k, const T* a_up, const T* a_mid, const T* a_low, const T* rhs, int64_t len, int64_t w,
+                     int32_t levels) {
+    std::vector<T> low(a_low, a_low + len), mid(a_mid, a_mid + len), up(a_up, a_up + len), r(rhs, rhs + len * w);
+    std::vector<T> nlow((size_t)len), nmid((size_t)len), nup((size_t)len), nr((size_t)len * w);
+    int64_t s = 1;
+    for (int32_t lv = 0; lv < levels; ++lv, s *= 2) {
+        for (int64_t i = 0; i < len; ++i) {
+            const bool hm = i - s >= 0, hp = i + s <= len - 1;
+            const T alpha = hm ? -(low[i] / mid[i - s]) : (T)0, gamma = hp ? -(up[i] / mid[i + s]) : (T)0;
+            nlow[i] = hm ? alpha * low[i - s] : (T)0;
+            nup[i] = hp ? gamma * up[i + s] : (T)0;
+            T m = mid[i];
+            if (hm) m = m + alpha * up[i - s];
+            if (hp) m = m + gamma * low[i + s];
+            nmid[i] = m;
+            for (int64_t c = 0; c < w; ++c) {
+                T v = r[i * w + c];
+                if (hm) v = v + alpha * r[(i - s) * w + c];
+                if (hp) v = v + gamma * r[(i + s) * w + c];
+                nr[i * w + c] = v;
+            }
+        }
+        low.swap(nlow); mid.swap(nmid); up.swap(nup); r.swap(nr);
+    }
+    for (int64_t j = 0; j < s && j < len; ++j) {                  // the interleaved systems
+        const int64_t m = (len - j + s - 1) / s;
+        std::vector<T> sl((size_t)m), sm((size_t)m), su((size_t)m), sr((size_t)m * w), sk((size_t)m * w);
+        for (int64_t t = 0; t < m; ++t) {
+            sl[t] = low[j + t * s]; sm[t] = mid[j + t * s]; su[t] = up[j + t * s];
+            for (int64_t c = 0; c < w; ++c) sr[t * w + c] = r[(j + t * s) * w + c];
+        }
+        thomas(sk.data(), su.data(), sm.data(), sl.data(), sr.data(), m, w);
+        for (int64_t t = 0; t < m; ++t)
+            for (int64_t c = 0; c < w; ++c) k[(j + t * s) * w + c] = sk[t * w + c];
+    }
+}
+// > 0: solve_for_k's full-system solve (:672) uses rowsplit_thomas with that many levels (set by
+// ora_spline_build_rowsplit_* for the duration of one call; periodic systems keep the reference's solve)
+thread_local int32_t g_rowsplit_levels = 0;
+
 template <class T>
 struct SingleBc { int32_t kind; T val; };
 
@@ -355,7 +409,8 @@ int32_t solve_for_k(T* k, const T* x, const T* data, int64_t len, int64_t w, int
     }
     // thomas on the full system (:672); k has row stride ld, so solve into a dense temp
     std::vector<T> kk((size_t)len * w);
-    thomas(kk.data(), a_up.data(), a_mid.data(), a_low.data(), rhs.data(), len, w);
+    if (g_rowsplit_levels > 0) rowsplit_thomas(kk.data(), a_up.data(), a_mid.data(), a_low.data(), rhs.data(), len, w, g_rowsplit_levels);
+    else thomas(kk.data(), a_up.data(), a_mid.data(), a_low.data(), rhs.data(), len, w);
     for (int64_t i = 0; i < len; ++i)
         for (int64_t c = 0; c < w; ++c) K(i, c) = kk[i * w + c];
     return ST_OK;
@@ -521,6 +576,19 @@ int32_t shard_queries(int64_t nq, int32_t nthreads, int64_t* first_bad, F&& fn) 
                                               const T* right_val, T* a, T* b) {                    \
         return spline_build<T>(x, n, data, w, bc_kind, left_kind, left_val, right_kind, right_val, \
                                a, b);                                                              \
+    }                                                                                              \
+    extern "C" int32_t ora_spline_build_rowsplit_##SFX(const T* x, int64_t n, const T* data,      \
+                                                       int64_t w, int32_t bc_kind,                 \
+                                                       const int32_t* left_kind,                   \
+                                                       const T* left_val,                          \
+                                                       const int32_t* right_kind,                  \
+                                                       const T* right_val, int32_t levels, T* a,   \
+                                                       T* b) {                                     \
+        g_rowsplit_levels = levels;                                                                \
+        int32_t st = spline_build<T>(x, n, data, w, bc_kind, left_kind, left_val, right_kind,      \
+                                     right_val, a, b);                                             \
+        g_rowsplit_levels = 0;                                                                     \
+        return st;                                                                                 \
     }                                                                                              \
     extern "C" int32_t ora_interp1d_cubic_##SFX(const T* g, int64_t n, const T* data, const T* a, \
                                                 const T* b, int64_t w, const T* q, int64_t nq,     \

@@ -137,7 +137,9 @@ def bc_arrays(bc, w, dtype):
     return kind, lk, lv, rk, rv
 
 
-def spline_build(x, data, bc):
+def spline_build(x, data, bc, rowsplit_levels=0):
+    """rowsplit_levels > 0: the row-split variant of the solve (NOT the reference's order; the specification a
+    future row-split build kernel is compared with -- ndi_oracle.cpp, rowsplit_thomas)"""
     x = np.ascontiguousarray(x)
     data = np.ascontiguousarray(data, dtype=x.dtype)
     n = len(x)
@@ -145,6 +147,11 @@ def spline_build(x, data, bc):
     kind, lk, lv, rk, rv = bc_arrays(bc, w, x.dtype)
     a = np.zeros((n - 1,) + data.shape[1:], dtype=x.dtype)
     b = np.zeros_like(a)
+    if rowsplit_levels:
+        st = getattr(lib(), f"ora_spline_build_rowsplit_{_sfx(x)}")(
+            _p(x), C.c_int64(n), _p(data), C.c_int64(w), C.c_int32(kind), _p(lk), _p(lv), _p(rk), _p(rv),
+            C.c_int32(rowsplit_levels), _p(a), _p(b))
+        return st, a, b
     st = getattr(lib(), f"ora_spline_build_{_sfx(x)}")(_p(x), C.c_int64(n), _p(data), C.c_int64(w), C.c_int32(kind),
                                                        _p(lk), _p(lv), _p(rk), _p(rv), _p(a), _p(b))
     return st, a, b

@@ -224,7 +224,25 @@ def test_row_split_study_solves_the_same_system_as_the_oracle():
         assert st == O.ST_OK and np.array_equal(a, ra) and np.array_equal(b, rb)
         q = np.sort(rng.uniform(x[0], x[-1], 2000)).astype(dt)
         ref = P.evaluate(x, y, a, b, q)
+        scale = np.maximum(np.abs(ref), np.abs(y).max(axis=0)[None, :])
         for levels in (1, 2, 4):
-            val = P.evaluate(x, y, *P.coefficients(x, y, P.pcr_then_thomas(low, mid, up, rhs, levels)), q)
-            scale = np.maximum(np.abs(ref), np.abs(y).max(axis=0)[None, :])
+            pa, pb = P.coefficients(x, y, P.pcr_then_thomas(low, mid, up, rhs, levels))
+            val = P.evaluate(x, y, pa, pb, q)
             assert float((np.abs(val - ref) / scale).max()) < bar / 10
+            # the oracle's row-split variant (rowsplit_thomas: the operation-by-operation specification a future
+            # row-split build kernel will be compared with) is this very computation
+            st, oa, ob = O.spline_build(x, y, {"kind": "Natural"}, rowsplit_levels=levels)
+            assert st == O.ST_OK and np.array_equal(oa, pa) and np.array_equal(ob, pb)
+        # every boundary kind whose system is tridiagonal: the row-split solve stays inside the bars
+        ind = {"kind": "Individual", "rows": [
+            {"kind": "Mixed", "left": {"kind": "FirstDeriv", "value": 0.5}, "right": {"kind": "Natural"}},
+            {"kind": "NotAKnot"},
+            {"kind": "Mixed", "left": {"kind": "SecondDeriv", "value": -1.0}, "right": {"kind": "Clamped"}}]}
+        for bc in ({"kind": "NotAKnot"}, {"kind": "Clamped"}, ind):
+            st, sa, sb = O.spline_build(x, y, bc)
+            st2, ra2, rb2 = O.spline_build(x, y, bc, rowsplit_levels=3)
+            assert st == O.ST_OK and st2 == O.ST_OK
+            seq = P.evaluate(x, y, sa, sb, q)
+            spl = P.evaluate(x, y, ra2, rb2, q)
+            sc = np.maximum(np.abs(seq), np.abs(y).max(axis=0)[None, :])
+            assert float((np.abs(spl - seq) / sc).max()) < bar / 10
