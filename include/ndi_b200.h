@@ -106,6 +106,7 @@ typedef int32_t ndi_dtype;
 #define NDI_SEARCH_BINARY_SMEM 2   /* grid staged into shared memory by a bulk (TMA) copy */
 #define NDI_SEARCH_UNIFORM_GUESS 3 /* O(1) even-spacing guess (vector_extensions.rs:68-90) + verify, binary fallback */
 #define NDI_SEARCH_BUCKET_LUT 4    /* O(1) expected on any grid: per-handle bucket table + exact finish on the grid */
+#define NDI_SEARCH_MERGE 5         /* sorted batches: a warp searches its smallest and largest query, the rest bisect inside that bracket */
 
 /* value of the device error word when no query failed */
 #define NDI_ERR_WORD_NONE UINT64_MAX
@@ -178,6 +179,20 @@ ndi_status ndi_interp1d_linear_dev(const ndi_interp1d* h, const void* q_dev, int
 ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int32_t* left_kind,
                                      const void* left_val, const int32_t* right_kind, const void* right_val,
                                      int64_t* bad_column);
+/* How ndi_interp1d_spline_build solves the tridiagonal system (cubic_spline.rs:409-721).
+ *   NDI_BUILD_SEQUENTIAL  the reference's elimination order, one serial Thomas sweep per column: coefficients
+ *                         bit-identical to the reference arithmetic; chain-latency-bound on long columns.
+ *   NDI_BUILD_ROWSPLIT    `levels` steps of parallel cyclic reduction, then 2^levels interleaved Thomas solves per
+ *                         column (csrc/ndi_rowsplit.cu); different rounding, inside north_star's 1e-12 (f64) /
+ *                         1e-5 (f32) bars, bit-identical to the oracle's specification of the same scheme.
+ *                         levels == 0 lets the library choose; a request is capped so every system keeps two rows.
+ *   NDI_BUILD_AUTO        row-split for systems of 2048 rows or more, the reference's order below (default).
+ * ndi_interp1d_build_info reports the depth the current coefficients were built with (0: reference order). */
+#define NDI_BUILD_AUTO 0
+#define NDI_BUILD_SEQUENTIAL 1
+#define NDI_BUILD_ROWSPLIT 2
+ndi_status ndi_interp1d_set_build_mode(ndi_interp1d* h, int32_t mode, int32_t levels);
+ndi_status ndi_interp1d_build_info(const ndi_interp1d* h, int32_t* rowsplit_levels);
 /* spline coefficient arrays a, b: (n-1, w) each, copied to host (CubicSplineStrategy, cubic_spline.rs:94-102) */
 ndi_status ndi_interp1d_spline_coeffs(const ndi_interp1d* h, void* a, void* b);
 /* install externally computed coefficients (device or host pointers per NDI_DEVICE_POINTERS) */

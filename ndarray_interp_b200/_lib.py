@@ -17,9 +17,10 @@ OK, OUT_OF_BOUNDS, NAN_QUERY, PERIODIC_MISMATCH, INVALID_ARGUMENT, NOT_MONOTONIC
 CUDA_ERROR = 100
 F32, F64, I32, I64 = 0, 1, 2, 3
 ASSUME_VALID, DEVICE_POINTERS, BORROW = 1, 2, 4
-SEARCH_AUTO, SEARCH_BINARY_GLOBAL, SEARCH_BINARY_SMEM, SEARCH_UNIFORM_GUESS, SEARCH_BUCKET_LUT = 0, 1, 2, 3, 4
+SEARCH_AUTO, SEARCH_BINARY_GLOBAL, SEARCH_BINARY_SMEM, SEARCH_UNIFORM_GUESS, SEARCH_BUCKET_LUT, SEARCH_MERGE = 0, 1, 2, 3, 4, 5
 EXTRAP_NO, EXTRAP_YES, EXTRAP_PERIODIC = 0, 1, 2
 BIN_AUTO, BIN_OFF, BIN_ON = 0, 1, 2
+BUILD_AUTO, BUILD_SEQUENTIAL, BUILD_ROWSPLIT = 0, 1, 2
 ERR_WORD_NONE = 2 ** 64 - 1
 
 DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32,
@@ -49,6 +50,8 @@ SIGNATURES = {
     "ndi_interp1d_linear": (_i32, [_vp, _vp, _i64, _i32, _vp, _pi64]),
     "ndi_interp1d_linear_dev": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "ndi_interp1d_spline_build": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _pi64]),
+    "ndi_interp1d_set_build_mode": (_i32, [_vp, _i32, _i32]),
+    "ndi_interp1d_build_info": (_i32, [_vp, _pi32]),
     "ndi_interp1d_spline_coeffs": (_i32, [_vp, _vp, _vp]),
     "ndi_interp1d_spline_set_coeffs": (_i32, [_vp, _vp, _vp, _u32]),
     "ndi_interp1d_cubic": (_i32, [_vp, _vp, _i64, _i32, _vp, _pi64]),

@@ -85,6 +85,11 @@ struct DeviceGuard {
     ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
 };
 
+static long env_long(const char* name, long dflt) {
+    const char* v = getenv(name);
+    return v && *v ? strtol(v, nullptr, 10) : dflt;
+}
+
 static size_t elem_size(ndi_dtype d) { return (d == NDI_F64 || d == NDI_I64) ? 8 : 4; }
 static bool dtype_ok(ndi_dtype d) { return d == NDI_F32 || d == NDI_F64 || d == NDI_I32 || d == NDI_I64; }
 
@@ -250,10 +255,12 @@ struct GridAids {
 };
 
 static SearchCfg make_search(const GridMeta& gm, int mode, int64_t nq, size_t other_smem) {
-    SearchCfg sc{bisect_top_step(gm.n), 0, 0, 0, 0, nullptr, nullptr, 0, 0.0, 0.0};
+    SearchCfg sc{bisect_top_step(gm.n), 0, 0, 0, 0, nullptr, nullptr, 0, 0.0, 0.0, 0};
     auto use_lut = [&]() { if (gm.lut) { sc.lut = gm.lut; sc.lut_n = gm.lut_n; sc.g0d = gm.g0d; sc.scale = gm.scale; } };
     const size_t bytes = (size_t)gm.n * gm.elem;
-    const size_t room = device_info().smem_optin > other_smem + 1024 ? device_info().smem_optin - other_smem - 1024 : 0;
+    // the kernels' own static shared memory (barriers, per-warp record slabs: up to 16.4 KB) comes off the budget too
+    constexpr size_t kStaticSmem = 17 * 1024;
+    const size_t room = device_info().smem_optin > other_smem + kStaticSmem ? device_info().smem_optin - other_smem - kStaticSmem : 0;
     auto stage = [&](size_t full_limit) {
         if (bytes <= full_limit && bytes <= room) { sc.smem = 1; sc.stage_src = gm.grid; sc.stage_n = (int)gm.n; sc.coarse_shift = 0; }
         else if (gm.coarse && (size_t)gm.coarse_n * gm.elem <= room) {
@@ -265,6 +272,7 @@ static SearchCfg make_search(const GridMeta& gm, int mode, int64_t nq, size_t ot
     case NDI_SEARCH_BINARY_SMEM: stage(gm.coarse ? kFullStageBytes : room); break;
     case NDI_SEARCH_UNIFORM_GUESS: sc.guess = 1; break;
     case NDI_SEARCH_BUCKET_LUT: use_lut(); break;
+    case NDI_SEARCH_MERGE: sc.merge = 1; break;
     default:   // AUTO: O(1) guess on grids where it always hits, else the bucket table;
                // without either (no handle), shared-memory bisection for big batches
         if (gm.uniform_hint) sc.guess = 1;
@@ -338,6 +346,9 @@ struct ndi_interp1d {
     bool owns_tables, owns_coeffs;
     int uniform_hint; int search_mode;
     int fast_tables = 0;             // f32: every data value is 0 or in [2^-56, 2^30] (hoisted-reciprocal division allowed)
+    void* pair = nullptr;            // pair table for thin-row Linear (ndi_eval.cu: rows i, i+1 interleaved), owned
+    int build_mode = NDI_BUILD_AUTO, build_levels = 0;   // spline solve: reference order or row-split (ndi_rowsplit.cu)
+    int built_levels = -1;           // depth of the row-split the current coefficients were built with (0: reference order)
     GridAids aids;
     GridMeta meta() const { return aids.meta(x, n, elem_size(dtype), uniform_hint); }
 };
@@ -450,6 +461,25 @@ static ndi_status pack_view(const void* base, size_t es, int ndim, const int64_t
     CKP(cudaMemcpyAsync(*dense, stage.data(), bytes, cudaMemcpyHostToDevice, st));
     CKP(cudaStreamSynchronize(st));                                // the staging buffer goes away
 #undef CKP
+    return NDI_OK;
+}
+
+// Pair table for Linear on thin rows (ndi_eval.cu: interp1d_linear_pair_kernel): twice the table, so only while
+// it stays comfortably L2-resident -- beyond that the gathers are DRAM sectors either way and nothing is gained.
+// NDI_PAIR_TABLE=0 switches it off (A/B measurement).
+static ndi_status build_pair_table(ndi_interp1d* h, cudaStream_t st) {
+    static const long enabled = env_long("NDI_PAIR_TABLE", 1), max_mb = env_long("NDI_PAIR_MAX_MB", 48);
+    const size_t es = elem_size(h->dtype);
+    const size_t bytes = (size_t)(h->n - 1) * 2 * (size_t)h->w * es;
+    if (!enabled || !pair_table_shape_ok(h->w, es) || bytes > ((size_t)max_mb << 20) || ((uintptr_t)h->data & 15)) return NDI_OK;
+    CK(cudaMalloc(&h->pair, bytes));
+    ndi_status s2 = dispatch(h->dtype, [&](auto tag) -> ndi_status {
+        using T = decltype(tag);
+        CK(launch_pack_pairs<T>((const T*)h->data, h->n, h->w, (T*)h->pair, st));
+        return NDI_OK;
+    });
+    if (s2 != NDI_OK) return s2;
+    CK(cudaStreamSynchronize(st));
     return NDI_OK;
 }
 
@@ -603,6 +633,7 @@ ndi_status ndi_interp1d_create(ndi_dtype dtype, const void* x, int64_t n, const 
         if (st != NDI_OK) { ndi_interp1d_destroy(h); return st; }
     }
     if ((st = scan_fast_tables(dtype, h->data, (size_t)n * (size_t)w, ws, &h->fast_tables)) != NDI_OK) { ndi_interp1d_destroy(h); return st; }
+    if ((st = build_pair_table(h, ws->s[0])) != NDI_OK) { ndi_interp1d_destroy(h); return st; }
     *out = h;
     return NDI_OK;
 }
@@ -637,6 +668,7 @@ ndi_status ndi_interp1d_destroy(ndi_interp1d* h) {
     DeviceGuard g(h->device);
     if (h->owns_tables) { cudaFree(h->x); cudaFree(h->data); }
     if (h->owns_coeffs) { cudaFree(h->a); cudaFree(h->b); }
+    cudaFree(h->pair);
     h->aids.release();
     delete h;
     return NDI_OK;
@@ -652,7 +684,7 @@ ndi_status ndi_interp1d_info(const ndi_interp1d* h, ndi_dtype* dtype, int64_t* n
     return NDI_OK;
 }
 ndi_status ndi_interp1d_set_search_mode(ndi_interp1d* h, int32_t mode) {
-    if (!h || mode < 0 || mode > NDI_SEARCH_BUCKET_LUT) return fail(NDI_INVALID_ARGUMENT, "bad search mode");
+    if (!h || mode < 0 || mode > NDI_SEARCH_MERGE) return fail(NDI_INVALID_ARGUMENT, "bad search mode");
     h->search_mode = mode;
     return NDI_OK;
 }
@@ -672,7 +704,7 @@ ndi_status ndi_interp1d_clone_to_device(const ndi_interp1d* h, int32_t device, n
     const size_t es = elem_size(h->dtype);
     ndi_interp1d* c = new ndi_interp1d(*h);
     c->device = device; c->owns_tables = true; c->owns_coeffs = h->a != nullptr;
-    c->x = c->data = c->a = c->b = nullptr;
+    c->x = c->data = c->a = c->b = c->pair = nullptr;
     auto copy = [&](void** dst, const void* src, size_t bytes) -> ndi_status {
         CK(cudaMalloc(dst, bytes));
         CK(cudaMemcpyPeer(*dst, device, src, h->device, bytes));   // NVLink peer copy
@@ -684,7 +716,8 @@ ndi_status ndi_interp1d_clone_to_device(const ndi_interp1d* h, int32_t device, n
     if (st == NDI_OK && h->b) st = copy(&c->b, h->b, (size_t)(h->n - 1) * h->w * es);
     c->aids = GridAids{};
     if (st == NDI_OK && !h->uniform_hint) st = build_aids(c->dtype, c->x, c->n, nullptr, &c->aids);
-    if (st != NDI_OK) { cudaFree(c->x); cudaFree(c->data); cudaFree(c->a); cudaFree(c->b); c->aids.release(); delete c; return st; }
+    if (st == NDI_OK && h->pair) st = copy(&c->pair, h->pair, (size_t)(h->n - 1) * 2 * h->w * es);
+    if (st != NDI_OK) { cudaFree(c->x); cudaFree(c->data); cudaFree(c->a); cudaFree(c->b); cudaFree(c->pair); c->aids.release(); delete c; return st; }
     *out = c;
     return NDI_OK;
 }
@@ -848,7 +881,7 @@ ndi_status ndi_interp1d_linear_dev(const ndi_interp1d* h, const void* q_dev, int
         using T = decltype(tag);
         SearchCfg sc = make_search(h->meta(), h->search_mode, nq, 0);
         CK(launch_interp1d_linear<T>((const T*)h->x, h->n, sc, (const T*)h->data, h->w, (const T*)q_dev, nq, extrapolate != 0,
-                                     (T*)out_dev, (unsigned long long*)err_word_dev, h->fast_tables, s));
+                                     (T*)out_dev, (unsigned long long*)err_word_dev, h->fast_tables, (const T*)h->pair, s));
         return NDI_OK;
     });
 }
@@ -864,7 +897,7 @@ ndi_status ndi_interp1d_linear(const ndi_interp1d* h, const void* q, int64_t nq,
         SearchCfg sc = make_search(h->meta(), h->search_mode, nq, 0);
         return run_host_eval(he,
             [&](const void* q0, const void*, int64_t cnt, void* o, unsigned long long* err, cudaStream_t s) -> ndi_status {
-                CK(launch_interp1d_linear<T>((const T*)h->x, h->n, sc, (const T*)h->data, h->w, (const T*)q0, cnt, extrapolate != 0, (T*)o, err, h->fast_tables, s));
+                CK(launch_interp1d_linear<T>((const T*)h->x, h->n, sc, (const T*)h->data, h->w, (const T*)q0, cnt, extrapolate != 0, (T*)o, err, h->fast_tables, (const T*)h->pair, s));
                 return NDI_OK;
             },
             [&](const void* q0, const void*, int64_t cnt, unsigned long long* err, cudaStream_t s) -> ndi_status {
@@ -897,6 +930,13 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
     }
     DeviceGuard g(h->device);
     ndi_status st; Workspace* ws = workspace(h->device, &st); if (!ws) return st;
+    // which solve: the reference's elimination order, or the row-split (PCR + Thomas) build
+    static const long env_mode = env_long("NDI_BUILD_MODE", -1), env_levels = env_long("NDI_BUILD_LEVELS", -1);
+    const int mode = env_mode >= 0 ? (int)env_mode : h->build_mode;
+    const int want_levels = env_levels >= 0 ? (int)env_levels : h->build_levels;
+    int levels = 0;
+    if (h->n >= 4 && mode != NDI_BUILD_SEQUENTIAL)
+        levels = rowsplit_levels_for(bc_kind == NDI_BC_PERIODIC ? h->n - 2 : h->n, want_levels, mode == NDI_BUILD_ROWSPLIT);
     return dispatch_float(h->dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
         const size_t coef_bytes = (size_t)(h->n - 1) * h->w * sizeof(T);
@@ -928,7 +968,7 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
         auto body = [&]() -> ndi_status {
             device_info();
             auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-            const size_t scratch_bytes = up(spline_scratch_elems<T>(h->n, h->w, bc_kind) * sizeof(T));
+            const size_t scratch_bytes = up(spline_scratch_elems<T>(h->n, h->w, bc_kind, levels) * sizeof(T));
             const size_t col_i = up((size_t)h->w * sizeof(int32_t)), col_t = up((size_t)h->w * sizeof(T));
             const size_t need = scratch_bytes + (bc_kind == NDI_BC_INDIVIDUAL ? 3 * col_i + 2 * col_t : 0);
             ndi_status gs = grow(&ws->d_build, &ws->d_build_cap, need);
@@ -948,7 +988,7 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
                 CK(cudaMemcpyAsync(pos, pos_host.data(), h->w * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
             }
             CK(cudaMemsetAsync(ws->d_err, 0xff, sizeof(uint64_t), bs));
-            CK(launch_spline_build<T>((const T*)h->x, h->n, (const T*)h->data, h->w, bc_kind, lk, lv, rk, rv, pos, group_count, a, b, scratch, ws->d_err, bs));
+            CK(launch_spline_build<T>((const T*)h->x, h->n, (const T*)h->data, h->w, bc_kind, lk, lv, rk, rv, pos, group_count, levels, a, b, scratch, ws->d_err, bs));
             CK(cudaMemcpyAsync(ws->h_pin, ws->d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, bs));
             CK(cudaStreamSynchronize(bs));
             return NDI_OK;
@@ -964,8 +1004,21 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
         cleanup(true);
         if (h->owns_coeffs) { cudaFreeAsync(h->a, bs); cudaFreeAsync(h->b, bs); }
         h->a = a; h->b = b; h->owns_coeffs = true;
+        h->built_levels = levels;
         return NDI_OK;
     });
+}
+
+ndi_status ndi_interp1d_set_build_mode(ndi_interp1d* h, int32_t mode, int32_t levels) {
+    if (!h || mode < NDI_BUILD_AUTO || mode > NDI_BUILD_ROWSPLIT || levels < 0) return fail(NDI_INVALID_ARGUMENT, "bad build mode");
+    h->build_mode = mode; h->build_levels = levels;
+    return NDI_OK;
+}
+ndi_status ndi_interp1d_build_info(const ndi_interp1d* h, int32_t* rowsplit_levels) {
+    if (!h || !rowsplit_levels) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    if (h->built_levels < 0) return fail(NDI_NO_SPLINE, "no spline coefficients built by this handle");
+    *rowsplit_levels = h->built_levels;
+    return NDI_OK;
 }
 
 ndi_status ndi_interp1d_spline_coeffs(const ndi_interp1d* h, void* a, void* b) {
@@ -990,6 +1043,7 @@ ndi_status ndi_interp1d_spline_set_coeffs(ndi_interp1d* h, const void* a, const 
     if (st != NDI_OK) { if (oa) cudaFree(na); if (ob) cudaFree(nb); return st; }
     if (h->owns_coeffs) { cudaFree(h->a); cudaFree(h->b); }
     h->a = na; h->b = nb; h->owns_coeffs = oa;
+    h->built_levels = -1;
     return NDI_OK;
 }
 
@@ -1127,7 +1181,7 @@ ndi_status ndi_interp2d_info(const ndi_interp2d* h, ndi_dtype* dtype, int64_t* n
     return NDI_OK;
 }
 ndi_status ndi_interp2d_set_search_mode(ndi_interp2d* h, int32_t mode) {
-    if (!h || mode < 0 || mode > NDI_SEARCH_BUCKET_LUT) return fail(NDI_INVALID_ARGUMENT, "bad search mode");
+    if (!h || mode < 0 || mode > NDI_SEARCH_MERGE) return fail(NDI_INVALID_ARGUMENT, "bad search mode");
     h->search_mode = mode;
     return NDI_OK;
 }
@@ -1176,11 +1230,6 @@ ndi_status ndi_interp2d_set_binning(ndi_interp2d* h, int32_t mode, int32_t band_
 }  // extern "C"
 
 namespace {
-
-long env_long(const char* name, long dflt) {
-    const char* v = getenv(name);
-    return v && *v ? strtol(v, nullptr, 10) : dflt;
-}
 
 // Is grouping the queries by table band (ndi_bin.cu) worth its two extra passes?  Measured on B200
 // (profiles/r01/binning.md): yes when the table cannot stay in L2 under random gathers AND an

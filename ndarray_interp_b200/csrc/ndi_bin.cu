@@ -209,7 +209,11 @@ cudaError_t launch_bin_queries(const T* gx, int64_t n, SearchCfg scx, const T* q
                  ((long long)nq + kBinChunk - 1) / kBinChunk, counters, counters + kMaxBands, perm_w, bx, by};
     const size_t smem = stage_bytes(scx, sizeof(T));
     auto blocks = [&](auto kernel) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // the kernels also hold their chunk in STATIC shared memory (up to 47 KB): static + dynamic beyond the
+        // 48 KB default needs the opt-in, not only a large dynamic part
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) { cudaGetLastError(); fa.sharedSizeBytes = 48 * 1024; }
+        if (fa.sharedSizeBytes + smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBinBlock, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         const long long cap = (long long)device_info().sm_count * per_sm;

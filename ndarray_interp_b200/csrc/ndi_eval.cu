@@ -77,6 +77,19 @@ template <class T> __device__ __forceinline__ T shfl_t(T v, int src) { return __
 #endif
 constexpr int kTilesLinear = NDI_TPW_LINEAR, kTilesCubic = NDI_TPW_CUBIC, kTilesBilinear = NDI_TPW_BILINEAR;
 
+// Handing a query's scalars to the lanes that work on its row.  Every warp shuffle is a wavefront on the L1TEX
+// data pipe, the unit that binds the thin-row kernels (profiles/r01/l1_wavefronts.md: a sixth of C3's wavefronts,
+// nine shuffles per round in the bilinear kernel).  With NDI_BCAST_SMEM each lane writes its query's record to a
+// per-warp slab of shared memory once per tile and every round reads the records of its queries with ONE 16-byte
+// (f32) load per 16 bytes of record -- lanes of one query read the same address (broadcast), the queries of a round
+// lie next to each other -- so a round costs 1 (linear) / 3 (bilinear) wavefronts instead of 4 / 9.  Used when a
+// query has at least four lanes (with two or fewer the records of a round span as many wavefronts as the shuffles).
+#ifndef NDI_BCAST_SMEM
+#define NDI_BCAST_SMEM 1
+#endif
+template <class T> struct alignas(16) LinRec { T dq; Slope<T> sl; int is; };                 // f32: 16 bytes
+template <class T> struct alignas(16) BilRec { long long cs; T bx, by; Slope<T> sx, sy; unsigned orow; };   // f32: 48 bytes
+
 // ------------------------------------------------------------------------------------------------
 // K3: Linear::interp_into x batch (linear.rs:73-98)
 // ------------------------------------------------------------------------------------------------
@@ -90,6 +103,8 @@ template <class T, int V, int LPQ>
 __global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THIN_MINBLOCKS : 0) interp1d_linear_kernel(const Eval1<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
+    constexpr bool kBcast = NDI_BCAST_SMEM && LPQ >= 4 && LPQ < 32 && kTilesLinear == 1;
+    __shared__ LinRec<T> recs[kBcast ? kWarpsPerBlock : 1][kBcast ? 32 : 1];
     const GridView<T> g = make_grid_view<T>(p.grid, p.n, p.sc, smem_raw, &bar);
     const T g0 = g.g0, gl = g.gl;
     const int lane = threadIdx.x & 31;
@@ -146,18 +161,28 @@ __global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THI
                     y1 = ld_table<T, V>(row);
                     y2 = ld_table<T, V>(row + p.w);
                 }
+                if constexpr (kBcast) {
+                    recs[threadIdx.x >> 5][lane] = LinRec<T>{dxq[t], slope[t], skip[t] ? -1 : idx[t]};
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int r = 0; r < LPQ; ++r) {
                     const int src = r * QPR + qsel;
+                    int is; bool live_s; T dq; Slope<T> sl;
+                    if constexpr (kBcast) {
+                        const LinRec<T> rc = recs[threadIdx.x >> 5][src];
+                        is = rc.is; live_s = is >= 0; dq = rc.dq; sl = rc.sl;
+                    } else {
 #if NDI_PACK_SHFL >= 1
-                    const int is = __shfl_sync(0xffffffffu, skip[t] ? -1 : idx[t], src);
-                    const bool live_s = is >= 0;
+                        is = __shfl_sync(0xffffffffu, skip[t] ? -1 : idx[t], src);
+                        live_s = is >= 0;
 #else
-                    const int is = __shfl_sync(0xffffffffu, idx[t], src);
-                    const bool live_s = !shfl_b(skip[t], src);
+                        is = __shfl_sync(0xffffffffu, idx[t], src);
+                        live_s = !shfl_b(skip[t], src);
 #endif
-                    const T dq = shfl_t(dxq[t], src);
-                    const Slope<T> sl = slope[t].from_lane(src, dq, p.fast_tables != 0);
+                        dq = shfl_t(dxq[t], src);
+                        sl = slope[t].from_lane(src, dq, p.fast_tables != 0);
+                    }
                     if (live_s && colok) {
                         if (!one_interval) {
                             const T* row = p.data + (long long)is * p.w + col;
@@ -167,6 +192,7 @@ __global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THI
                         st_stream<T, V>(p.out + (qbase + src) * p.w + col, lerp_vec<T, V>(y1, y2, sl, dq));   // linear.rs:94-96
                     }
                 }
+                if constexpr (kBcast) __syncwarp();                    // the slab is rewritten by the next tile
             }
         } else {
             const long long tile = task / p.nslices;
@@ -208,6 +234,121 @@ __global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THI
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3 on a PAIR TABLE (rows of 16 - 64 bytes: an interval's two rows fit one cache line)
+// ------------------------------------------------------------------------------------------------
+// Linear::interp_into gathers rows i and i+1.  For rows of 16 - 64 bytes the two row gathers are two L1TEX
+// wavefronts per query (one per row: the lanes of a load instruction touch one row each), and on C3 those 64
+// wavefronts per 32-query tile are half of what binds the kernel (profiles/r01/l1_wavefronts.md).  A handle
+// with such rows therefore also keeps P, the table with every interval's two rows interleaved in granules of
+// two columns:
+//     P[i] = { y[i][0], y[i][1], y[i+1][0], y[i+1][1],  y[i][2], y[i][3], y[i+1][2], y[i+1][3], ... }   (2 w elements)
+// A query's whole gather is then ONE aligned segment of 2 w elements (at most 128 bytes: one wavefront), and a
+// lane's 32-byte load holds exactly the y1 / y2 values of the columns it produces -- already paired up for the
+// two-column arithmetic of lerp_vec.  Twice the table memory, so only built while P stays L2-resident
+// (ndi_api.cu: want_pair_table).  Same arithmetic, same bits.
+template <class T> struct alignas(32) Pair32 { T v[32 / sizeof(T)]; };
+template <class T>
+__device__ __forceinline__ Pair32<T> ld_pair(const T* p) {          // one 256-bit load (LDG.E.256), read-only path
+    unsigned long long a, b, c, d;
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    unsigned long long t[4] = {a, b, c, d};
+    return *reinterpret_cast<const Pair32<T>*>(t);
+}
+template <class T, int V>
+__device__ __forceinline__ void unpair(const Pair32<T>& pr, Vec<T, V>& y1, Vec<T, V>& y2) {
+#pragma unroll
+    for (int e = 0; e < V; e += 2) {
+        y1.v[e] = pr.v[2 * e]; y1.v[e + 1] = pr.v[2 * e + 1];
+        y2.v[e] = pr.v[2 * e + 2]; y2.v[e + 1] = pr.v[2 * e + 3];
+    }
+}
+
+template <class T, int LPQ>
+__global__ void __launch_bounds__(kBlock) interp1d_linear_pair_kernel(const Eval1<T> p) {
+    constexpr int V = 16 / (int)sizeof(T), QPR = 32 / LPQ;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    constexpr bool kBcast = NDI_BCAST_SMEM && LPQ >= 4;
+    __shared__ LinRec<T> recs[kBcast ? kWarpsPerBlock : 1][kBcast ? 32 : 1];
+    const GridView<T> g = make_grid_view<T>(p.grid, p.n, p.sc, smem_raw, &bar);
+    const T g0 = g.g0, gl = g.gl;
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+    const long long task0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const long long pw = 2 * p.w;                                  // elements per row of P (p.data is P here)
+    T x_ahead = g0;
+    if (task0 < p.ntasks && task0 * 32 + lane < p.nq) x_ahead = ld_query(p.q + task0 * 32 + lane);
+    const int sub = lane % LPQ, qsel = lane / LPQ;
+    const long long col = (long long)sub * V;
+    for (long long task = task0; task < p.ntasks; task += nwarps) {
+        const long long qbase = task * 32, qi = qbase + lane;
+        T x[1] = {x_ahead};
+        const long long qn = (task + nwarps) * 32 + lane;
+        x_ahead = (task + nwarps < p.ntasks && qn < p.nq) ? ld_query(p.q + qn) : g0;
+        int idx[1]; T x1s[1], x2s[1];
+        search_multi<T, 1>(g, x, idx, x1s, x2s);                                       // linear.rs:87, :90-91
+        const bool live = qi < p.nq;
+        const bool bad = live && (p.mode ? Ar<T>::is_nan(x[0]) : !in_range(g0, gl, x[0]));   // linear.rs:80-84
+        const T dxq = Ar<T>::sub(x[0], x1s[0]);
+        const Slope<T> slope = Slope<T>::make(Ar<T>::sub(x2s[0], x1s[0]), dxq, p.fast_tables != 0);
+        report_first_bad(p.err, bad, (unsigned long long)qi);
+        const bool skip = bad || !live;
+        const int idx0 = __shfl_sync(0xffffffffu, idx[0], __ffs(__ballot_sync(0xffffffffu, !skip) | 0x80000000u) - 1);
+        const bool one_interval = __all_sync(0xffffffffu, skip || idx[0] == idx0);
+        Vec<T, V> y1, y2;
+        if (one_interval) unpair<T, V>(ld_pair<T>(p.data + (long long)idx0 * pw + 2 * col), y1, y2);
+        if constexpr (kBcast) {
+            recs[threadIdx.x >> 5][lane] = LinRec<T>{dxq, slope, skip ? -1 : idx[0]};
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < LPQ; ++r) {
+            const int src = r * QPR + qsel;
+            int is; T dq; Slope<T> sl;
+            if constexpr (kBcast) {
+                const LinRec<T> rc = recs[threadIdx.x >> 5][src];
+                is = rc.is; dq = rc.dq; sl = rc.sl;
+            } else if constexpr (LPQ == 1) {                                   // one lane per query: nothing to hand round
+                is = skip ? -1 : idx[0]; dq = dxq; sl = slope;
+            } else {
+                is = __shfl_sync(0xffffffffu, skip ? -1 : idx[0], src);
+                dq = shfl_t(dxq, src);
+                sl = slope.from_lane(src, dq, p.fast_tables != 0);
+            }
+            if (is >= 0) {
+                if (!one_interval) unpair<T, V>(ld_pair<T>(p.data + (long long)is * pw + 2 * col), y1, y2);
+                st_stream<T, V>(p.out + (qbase + src) * p.w + col, lerp_vec<T, V>(y1, y2, sl, dq));   // linear.rs:94-96
+            }
+        }
+        if constexpr (kBcast) __syncwarp();
+    }
+}
+
+// P from the dense table (once per handle)
+template <class T>
+__global__ void __launch_bounds__(256) pack_pairs_kernel(const T* __restrict__ y, long long n, long long w, T* __restrict__ P) {
+    const long long total = (n - 1) * 2 * w, step = (long long)gridDim.x * blockDim.x;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += step) {
+        const long long i = o / (2 * w), e = o - i * 2 * w;
+        const long long granule = e >> 2, within = e & 3;          // {y[i][2g], y[i][2g+1], y[i+1][2g], y[i+1][2g+1]}
+        P[o] = y[(i + (within >> 1)) * w + 2 * granule + (within & 1)];
+    }
+}
+template <class T>
+cudaError_t launch_pack_pairs(const T* y, int64_t n, int64_t w, T* P, cudaStream_t st) {
+    const long long total = (n - 1) * 2 * w;
+    const long long want = (total + 255) / 256, cap = (long long)device_info().sm_count * 16;
+    pack_pairs_kernel<T><<<(unsigned)(want < cap ? (want ? want : 1) : cap), 256, 0, st>>>(y, (long long)n, (long long)w, P);
+    count_launch();
+    return cudaGetLastError();
+}
+bool pair_table_shape_ok(int64_t w, size_t elem) {
+    const int64_t v = 16 / (int64_t)elem;                             // columns per lane
+    const int64_t lanes = w / v;
+    return w % v == 0 && (lanes == 1 || lanes == 2 || lanes == 4);    // rows of 16, 32 or 64 bytes: P rows of 32 - 128 bytes
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5: CubicSplineStrategy::interp_into x batch (cubic_spline.rs:791-830)
 // ------------------------------------------------------------------------------------------------
 template <class T>
@@ -222,6 +363,28 @@ __device__ __forceinline__ T cubic_point(T yl, T yr, T al, T bl, T t, T omt, T t
     const T lin = Ar<T>::add(Ar<T>::mul(omt, yl), Ar<T>::mul(t, yr));
     const T cur = Ar<T>::add(Ar<T>::mul(al, omt), Ar<T>::mul(bl, t));
     return Ar<T>::add(lin, Ar<T>::mul(tt, cur));
+}
+
+// the V columns one lane holds of one query; f32: two columns per instruction (ndi_device.cuh, F2)
+template <class T, int V>
+__device__ __forceinline__ Vec<T, V> cubic_vec(const Vec<T, V>& yl, const Vec<T, V>& yr, const Vec<T, V>& al, const Vec<T, V>& bl,
+                                               T t, T omt, T tt) {
+    Vec<T, V> res;
+    if constexpr (std::is_same<T, float>::value && NDI_F32X2 && V % 2 == 0) {
+        const F2 t2 = F2::both(t), o2 = F2::both(omt), tt2 = F2::both(tt);
+#pragma unroll
+        for (int e = 0; e < V; e += 2) {
+            const F2 l{yl.v[e], yl.v[e + 1]}, r{yr.v[e], yr.v[e + 1]}, a{al.v[e], al.v[e + 1]}, b{bl.v[e], bl.v[e + 1]};
+            const F2 lin = add2(mul2(o2, l), mul2(t2, r));
+            const F2 cur = add2(mul2(a, o2), mul2(b, t2));
+            const F2 o = add2(lin, mul2(tt2, cur));
+            res.v[e] = o.lo; res.v[e + 1] = o.hi;
+        }
+        return res;
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) res.v[e] = cubic_point<T>(yl.v[e], yr.v[e], al.v[e], bl.v[e], t, omt, tt);
+    return res;
 }
 
 // range check, periodic wrap and NaN test of one query (cubic_spline.rs:797-809); returns `bad`
@@ -318,10 +481,7 @@ __global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THI
                             al = ld_table<T, V>(p.a + ro);
                             bl = ld_table<T, V>(p.b + ro);
                         }
-                        Vec<T, V> res;
-#pragma unroll
-                        for (int e = 0; e < V; ++e) res.v[e] = cubic_point<T>(yl.v[e], yr.v[e], al.v[e], bl.v[e], ts, os, tts);
-                        st_stream<T, V>(p.out + (qbase + src) * p.w + col, res);
+                        st_stream<T, V>(p.out + (qbase + src) * p.w + col, cubic_vec<T, V>(yl, yr, al, bl, ts, os, tts));
                     }
                 }
             }
@@ -359,10 +519,7 @@ __global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THI
                     bl = ld_table<T, V>(p.b + ro);
                     cur = is;
                 }
-                Vec<T, V> res;
-#pragma unroll
-                for (int e = 0; e < V; ++e) res.v[e] = cubic_point<T>(yl.v[e], yr.v[e], al.v[e], bl.v[e], ts, os, tts);
-                st_stream<T, V>(p.out + (qbase + s) * p.w + col, res);
+                st_stream<T, V>(p.out + (qbase + s) * p.w + col, cubic_vec<T, V>(yl, yr, al, bl, ts, os, tts));
             }
         }
     }
@@ -379,6 +536,8 @@ template <class T, int V, int LPQ, bool PERM>
 __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (LPQ <= 2 ? 5 : 4) : 3) interp2d_bilinear_kernel(const Eval2<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar[2];
+    constexpr bool kBcast = NDI_BCAST_SMEM && LPQ >= 4 && LPQ < 32 && kTilesBilinear == 1;
+    __shared__ BilRec<T> recs[kBcast ? kWarpsPerBlock : 1][kBcast ? 32 : 1];
     const GridView<T> gx = make_grid_view<T>(p.gx, p.n, p.scx, smem_raw, &bar[0]);
     const GridView<T> gy = make_grid_view<T>(p.gy, p.m, p.scy, smem_raw + stage_bytes(p.scx, sizeof(T)), &bar[1]);
     const T gx0 = gx.g0, gxl = gx.gl, gy0 = gy.g0, gyl = gy.gl;
@@ -443,20 +602,30 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (LPQ <= 2 ? 5 : 4) : 
             for (int t = 0; t < TPW; ++t) {
                 const long long qbase = qbase0 + t * 32;
                 if (qbase >= p.nq) break;
+                if constexpr (kBcast) {
+                    recs[threadIdx.x >> 5][lane] = BilRec<T>{skip[t] ? -1ll : cell[t], bx[t], by[t], slx[t], sly[t], orow[t]};
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int r = 0; r < LPQ; ++r) {
                     const int src = r * QPR + qsel;
+                    long long cs, srow = qbase + src; bool live_s; T sbx, sby; Slope<T> ssx, ssy;
+                    if constexpr (kBcast) {
+                        const BilRec<T> rc = recs[threadIdx.x >> 5][src];
+                        cs = rc.cs; live_s = cs >= 0; sbx = rc.bx; sby = rc.by; ssx = rc.sx; ssy = rc.sy;
+                        if constexpr (PERM) srow = rc.orow;
+                    } else {
 #if NDI_PACK_SHFL >= 1
-                    const long long cs = __shfl_sync(0xffffffffu, skip[t] ? -1ll : cell[t], src);
-                    const bool live_s = cs >= 0;
+                        cs = __shfl_sync(0xffffffffu, skip[t] ? -1ll : cell[t], src);
+                        live_s = cs >= 0;
 #else
-                    const long long cs = __shfl_sync(0xffffffffu, cell[t], src);
-                    const bool live_s = !shfl_b(skip[t], src);
+                        cs = __shfl_sync(0xffffffffu, cell[t], src);
+                        live_s = !shfl_b(skip[t], src);
 #endif
-                    const T sbx = shfl_t(bx[t], src), sby = shfl_t(by[t], src);
-                    const Slope<T> ssx = slx[t].from_lane(src, sbx, p.fast_tables != 0), ssy = sly[t].from_lane(src, sby, p.fast_tables != 0);
-                    long long srow = qbase + src;
-                    if constexpr (PERM) srow = __shfl_sync(0xffffffffu, orow[t], src);
+                        sbx = shfl_t(bx[t], src); sby = shfl_t(by[t], src);
+                        ssx = slx[t].from_lane(src, sbx, p.fast_tables != 0); ssy = sly[t].from_lane(src, sby, p.fast_tables != 0);
+                        if constexpr (PERM) srow = __shfl_sync(0xffffffffu, orow[t], src);
+                    }
                     if (live_s && colok) {
                         const T* c0 = p.data + cs + col;
                         const Vec<T, V> z11 = ld_table<T, V>(c0), z12 = ld_table<T, V>(c0 + p.w);
@@ -464,6 +633,7 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (LPQ <= 2 ? 5 : 4) : 
                         st_stream<T, V>(p.out + srow * p.w + col, bilerp_vec<T, V>(z11, z12, z21, z22, ssx, sbx, ssy, sby));
                     }
                 }
+                if constexpr (kBcast) __syncwarp();                    // the slab is rewritten by the next tile
             }
         } else {
             const long long tile = task / p.nslices;
@@ -625,8 +795,8 @@ static Shape pick_shape(long long w, long long nq, int v, int tiles_per_warp) {
 
 template <class K>
 static cudaError_t prep_smem(K kernel, size_t bytes) {
-    // static shared memory (barriers) counts against the 48 KB default as well
-    if (bytes > 40 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    // static shared memory (barriers, up to 16 KB of per-warp record slabs) counts against the 48 KB default as well
+    if (bytes > 30 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     return cudaSuccess;
 }
 
@@ -675,8 +845,18 @@ template <class T, int V, int LPQ> constexpr auto bilinear_binned = interp2d_bil
 template <class T>
 cudaError_t launch_interp1d_linear(const T* grid, int64_t n, SearchCfg sc, const T* data, int64_t w, const T* q,
                                    int64_t nq, int extrapolate, T* out, unsigned long long* err, int fast_tables,
-                                   cudaStream_t st) {
+                                   const T* pair, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
+    if (pair && pair_table_shape_ok(w, sizeof(T)) && aligned(out, 16)) {
+        const long long tiles = (nq + 31) / 32;
+        Eval1<T> p{grid, (int)n, sc, pair, nullptr, nullptr, (long long)w, q, (long long)nq, extrapolate, out, err, tiles, 1, fast_tables};
+        const size_t smem = stage_bytes(sc, sizeof(T));
+        switch ((int)(w / (16 / (int64_t)sizeof(T)))) {
+        case 1: return launch_eval(interp1d_linear_pair_kernel<T, 1>, p, smem, st);
+        case 2: return launch_eval(interp1d_linear_pair_kernel<T, 2>, p, smem, st);
+        default: return launch_eval(interp1d_linear_pair_kernel<T, 4>, p, smem, st);
+        }
+    }
     Shape sh = pick_shape(w, nq, pick_vec<T>(w, {data, out}), kTilesLinear);
     Eval1<T> p{grid, (int)n, sc, data, nullptr, nullptr, (long long)w, q, (long long)nq, extrapolate, out, err, sh.ntasks, sh.nslices, fast_tables};
     size_t smem = stage_bytes(sc, sizeof(T));
@@ -736,7 +916,8 @@ cudaError_t launch_validate_queries(const T* gx, int64_t n, const T* gy, int64_t
 
 #define NDI_INST_COMMON(T)                                                                                             \
     template cudaError_t launch_interp1d_linear<T>(const T*, int64_t, SearchCfg, const T*, int64_t, const T*, int64_t, \
-                                                   int, T*, unsigned long long*, int, cudaStream_t);                   \
+                                                   int, T*, unsigned long long*, int, const T*, cudaStream_t);         \
+    template cudaError_t launch_pack_pairs<T>(const T*, int64_t, int64_t, T*, cudaStream_t);                           \
     template cudaError_t launch_interp2d_bilinear<T>(const T*, int64_t, SearchCfg, const T*, int64_t, SearchCfg,       \
                                                      const T*, int64_t, const T*, const T*, int64_t, int, T*,          \
                                                      unsigned long long*, const unsigned*, int, cudaStream_t);         \

@@ -270,6 +270,11 @@ __global__ void __launch_bounds__(256) selftest_fdiv_kernel(uint32_t a_mant_begi
         const uint32_t mb = blockIdx.x * 4096u + k * 256u + threadIdx.x;
         const float b = __uint_as_float(b_hi | mb);
         const float r = rcp_refined(b);
+        // zero numerators and both signs through the spline sweeps' entry point (sign of zero included)
+        for (uint32_t v = 0; v < 4; ++v) {
+            const float z = __uint_as_float((v & 1u) << 31), bb = (v & 2u) ? -b : b;
+            bad += __float_as_uint(Hoisted<float>::div(z, bb, Hoisted<float>::rcp(bb))) != __float_as_uint(__fdiv_rn(z, bb));
+        }
         for (uint32_t ma = a_mant_begin; ma < a_mant_begin + a_mant_count; ++ma) {
             const float a = __uint_as_float(a_hi | ma);
             bad += __float_as_uint(div_by(a, b, r)) != __float_as_uint(__fdiv_rn(a, b));

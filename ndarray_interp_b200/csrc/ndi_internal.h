@@ -18,6 +18,7 @@ struct SearchCfg {
     const void* lut;        // non-null: bucket-table search (LutEntry per bucket, see ndi_device.cuh)
     int lut_n;              // number of buckets
     double g0d, scale;      // bucket(x) = (x - g0d) * scale
+    int merge;              // 1: warp-level merge search for sorted batches (bracket from the warp's min / max query)
 };
 
 // largest power of two <= n-2 (0 when n == 2): the first probe distance of the bisection
@@ -49,10 +50,15 @@ cudaError_t launch_validate_queries(const T* g0_gl_x /* grid x */, int64_t n, co
                                     const T* qx, const T* qy, int64_t nq, int check, unsigned long long* err,
                                     cudaStream_t st);
 
+// pair: the handle's pair table (rows i, i+1 interleaved; launch_pack_pairs) or nullptr
 template <class T>
 cudaError_t launch_interp1d_linear(const T* grid, int64_t n, SearchCfg sc, const T* data, int64_t w, const T* q,
                                    int64_t nq, int extrapolate, T* out, unsigned long long* err, int fast_tables,
-                                   cudaStream_t st);
+                                   const T* pair, cudaStream_t st);
+// thin rows (32 - 64 bytes, a whole number of 16-byte lanes): may the linear kernel use a pair table?
+bool pair_table_shape_ok(int64_t w, size_t elem);
+template <class T>
+cudaError_t launch_pack_pairs(const T* y, int64_t n, int64_t w, T* P, cudaStream_t st);
 template <class T>
 cudaError_t launch_interp1d_cubic(const T* grid, int64_t n, SearchCfg sc, const T* data, const T* a, const T* b,
                                   int64_t w, const T* q, int64_t nq, int extrap_mode, T* out,
@@ -107,18 +113,27 @@ struct StridedDesc { int ndim; long long shape[kMaxDims]; long long stride[kMaxD
 cudaError_t launch_pack_strided(const void* src_dev, long long origin, const StridedDesc& d, size_t elem,
                                 long long count, void* dst_dev, cudaStream_t st);
 
-// ---- spline construction (ndi_spline.cu) -----------------------------------------------------
+// ---- spline construction (ndi_spline.cu, ndi_rowsplit.cu) ----------------------------------------
 // Builds a, b ((n-1) x w each) on the device.  For bc_kind == INDIVIDUAL the four boundary arrays are
 // device arrays of w entries; pos (device, w entries) gives every column its position when the
 // columns are grouped by (left kind, right kind) after specialisation, group_count (host, 9
 // entries, group = 3 * variant(left) + variant(right), variant: NotAKnot 0, FirstDeriv 1,
 // SecondDeriv 2) the size of each group.  scratch: spline_scratch_elems() elements.
-// err: device word, set to the first column with a periodic mismatch.
+// levels == 0: the reference's elimination order (bit-identical coefficients); levels > 0: the row-split
+// build, `levels` steps of parallel cyclic reduction followed by 2^levels interleaved Thomas solves per
+// column (see rowsplit_levels_for).  err: device word, set to the first column with a periodic mismatch.
 template <class T>
 cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w, int bc_kind, const int32_t* lk,
                                 const T* lv, const int32_t* rk, const T* rv, const int32_t* pos, const int64_t* group_count,
-                                T* a, T* b, T* scratch, unsigned long long* err, cudaStream_t st);
+                                int levels, T* a, T* b, T* scratch, unsigned long long* err, cudaStream_t st);
 template <class T>
-size_t spline_scratch_elems(int64_t n, int64_t w, int bc_kind);
+size_t spline_scratch_elems(int64_t n, int64_t w, int bc_kind, int levels);
+// row-split depth for a system of `rows` rows: `requested` > 0 is honoured up to the deepest split that keeps
+// two rows per system and fits the reduce kernel's shared-memory tile; requested == 0 picks the depth that
+// leaves chains of about 256 rows -- unless the system is shorter than kRowsplitAutoRows and `force` is
+// not set, where the reference's order is kept (0); 0 also when the system is too short to split at all
+constexpr int kMaxRowsplitLevels = 6;
+constexpr int64_t kRowsplitAutoRows = 2048;
+int rowsplit_levels_for(int64_t rows, int requested, bool force);
 
 }  // namespace ndi

@@ -36,131 +36,17 @@
 // Reference quirk kept on purpose: the last diagonal entry of the NotAKnot system is
 // x[n-1]-x[n-2] (:635) where the textbook system has x[n-2]-x[n-3]; see
 // tests/test_oracle_golden.py::test_not_a_knot_right_boundary_quirk.
-#include "ndi_device.cuh"
-#include "ndi_internal.h"
+#include "ndi_spline.cuh"
 
 namespace ndi {
 
-enum { SB_NAK = 0, SB_NATURAL = 1, SB_CLAMPED = 2, SB_FIRST = 3, SB_SECOND = 4 };
-enum { BC_NAK = 0, BC_NATURAL = 1, BC_CLAMPED = 2, BC_PERIODIC = 3, BC_INDIVIDUAL = 4 };
-
-template <class T>
-struct Side { int kind; T val; };
-
-// SingleBoundary::specialize (:287-296)
-template <class T>
-__host__ __device__ inline Side<T> specialize(Side<T> s) {
-    if (s.kind == SB_NATURAL) return {SB_SECOND, (T)0};
-    if (s.kind == SB_CLAMPED) return {SB_FIRST, (T)0};
-    return s;
-}
-
-template <class T> struct A : Ar<T> {};
-#define ADD A<T>::add
-#define SUB A<T>::sub
-#define MUL A<T>::mul
-#define DIV A<T>::div
-
-// matrix row i of the full (non-periodic) system: (:440-451) interior, (:584-590) the 3-point
-// NotAKnot parabola system, (:599-669) boundary rows.
-template <class T>
-__device__ __forceinline__ void matrix_row(const T* __restrict__ x, int n, int i, int lk, int rk, bool nak3, T& up,
-                                           T& mid, T& low) {
-    const T two = (T)2, one = (T)1, zero = (T)0;
-    if (i > 0 && i < n - 1) {
-        const T dxn = SUB(x[i + 1], x[i]), dxn_1 = SUB(x[i], x[i - 1]);
-        up = dxn_1; mid = MUL(two, ADD(dxn, dxn_1)); low = dxn;
-    } else if (i == 0) {
-        low = zero;
-        const T dx0 = SUB(x[1], x[0]);
-        if (nak3) { mid = one; up = one; }
-        else if (lk == SB_NAK) { mid = SUB(x[2], x[1]); up = SUB(x[2], x[0]); }
-        else if (lk == SB_FIRST) { mid = one; up = zero; }
-        else { up = dx0; mid = MUL(two, dx0); }
-    } else {
-        up = zero;
-        const T dx_1 = SUB(x[n - 1], x[n - 2]);
-        if (nak3) { low = one; mid = one; }
-        else if (rk == SB_NAK) { mid = dx_1; low = SUB(x[n - 1], x[n - 3]); }
-        else if (rk == SB_FIRST) { mid = one; low = zero; }
-        else { mid = MUL(two, dx_1); low = dx_1; }
-    }
-}
-// row i of the condensed periodic system (:512-518), i in [0, n-3]
-template <class T>
-__device__ __forceinline__ void matrix_row_periodic(const T* __restrict__ x, int n, int i, T& up, T& mid, T& low) {
-    const T two = (T)2;
-    if (i == 0) {
-        const T dx0 = SUB(x[1], x[0]), dx_1 = SUB(x[n - 1], x[n - 2]);
-        mid = MUL(two, ADD(dx_1, dx0)); up = dx_1; low = (T)0;
-    } else {
-        const T dxn = SUB(x[i + 1], x[i]), dxn_1 = SUB(x[i], x[i - 1]);
-        up = dxn_1; mid = MUL(two, ADD(dxn, dxn_1)); low = dxn;
-    }
-}
-
-// right-hand sides ---------------------------------------------------------------------------
-template <class T>
-__device__ __forceinline__ T rhs_interior(T yl, T ym, T yr, T dxn, T dxn_1) {       // :468
-    const T three = (T)3;
-    return MUL(three, ADD(DIV(MUL(dxn, SUB(ym, yl)), dxn_1), DIV(MUL(dxn_1, SUB(yr, ym)), dxn)));
-}
-template <class T>
-__device__ __forceinline__ T rhs_left(const T* __restrict__ x, Side<T> l, T y0, T y1, T y2) {
-    const T two = (T)2, three = (T)3;
-    const T dx0 = SUB(x[1], x[0]), dx1 = SUB(x[2], x[1]);
-    if (l.kind == SB_NAK) {                                                           // :600-610
-        const T d = SUB(x[2], x[0]);
-        const T tmp1 = MUL(ADD(dx0, MUL(two, d)), dx1);
-        return DIV(ADD(DIV(MUL(tmp1, SUB(y1, y0)), dx0), DIV(MUL(MUL(dx0, dx0), SUB(y2, y1)), dx1)), d);
-    }
-    if (l.kind == SB_FIRST) return l.val;                                             // :614-618
-    return SUB(MUL(three, SUB(y1, y0)), DIV(MUL(l.val, MUL(dx0, dx0)), two));         // :629
-}
-template <class T>
-__device__ __forceinline__ T rhs_right(const T* __restrict__ x, int n, Side<T> r, T y_1, T y_2, T y_3) {
-    const T two = (T)2, three = (T)3;
-    const T dx_1 = SUB(x[n - 1], x[n - 2]), dx_2 = SUB(x[n - 2], x[n - 3]);
-    if (r.kind == SB_NAK) {                                                           // :635-647
-        const T d = SUB(x[n - 1], x[n - 3]);
-        const T tmp1 = MUL(ADD(MUL(two, d), dx_1), dx_2);
-        return DIV(ADD(DIV(MUL(MUL(dx_1, dx_1), SUB(y_2, y_3)), dx_2), DIV(MUL(tmp1, SUB(y_1, y_2)), dx_1)), d);
-    }
-    if (r.kind == SB_FIRST) return r.val;                                             // :651-655
-    return ADD(MUL(three, SUB(y_1, y_2)), DIV(MUL(r.val, MUL(dx_1, dx_1)), two));     // :666
-}
-
-// ---- shared-matrix factorisation -------------------------------------------------------------------
-// The elimination w[i] = low[i] / mid'[i-1]; mid'[i] = mid[i] - w[i] * up[i-1] (thomas :690-692) is a
-// serial chain by definition (division -> multiply -> subtract, in the reference's order).  One
-// block: all threads form the matrix rows of a tile in shared memory, thread 0 runs the chain over
-// the tile out of shared memory (so its only latency is the arithmetic), all threads write the
-// tile back.  fac layout: up[n] | mid[n] (eliminated) | wl[n] | k2[n]
-constexpr int kFacTile = 1024, kFacBlock = 256;
-template <class T> struct alignas(4 * sizeof(T)) FacRow { T up, mid, wl, rmid; };
-template <class T>
-__device__ __forceinline__ FacRow<T> ld_fac(const FacRow<T>* p) {
-    FacRow<T> f;
-    if constexpr (sizeof(T) == 4) { const int4 v = __ldg(reinterpret_cast<const int4*>(p)); f = *reinterpret_cast<const FacRow<T>*>(&v); }
-    else {
-        const int4 v0 = __ldg(reinterpret_cast<const int4*>(p)), v1 = __ldg(reinterpret_cast<const int4*>(p) + 1);
-        int4 t[2] = {v0, v1};
-        f = *reinterpret_cast<const FacRow<T>*>(t);
-    }
-    return f;
-}
-// Individual boundaries: the matrix differs between columns only through the KIND of the two boundary
-// rows (three kinds each after specialize()), so there are at most nine matrices.  Block g = 3*l + r
-// factorises the one with left kind kIndKinds[l] and right kind kIndKinds[r] into fac + g * fac_stride.
-__constant__ int kIndKinds[3] = {SB_NAK, SB_FIRST, SB_SECOND};
-__host__ __device__ inline int ind_variant(int specialized_kind) { return specialized_kind == SB_NAK ? 0 : (specialized_kind == SB_FIRST ? 1 : 2); }
 
 template <class T>
 __global__ void __launch_bounds__(kFacBlock) spline_factor_kernel(const T* __restrict__ x, int n, int periodic, int lk, int rk,
                                                                   T* __restrict__ fac, size_t fac_stride) {
     __shared__ T su[kFacTile], sm[kFacTile], sl[kFacTile];
     __shared__ T carry[2];
-    if (gridDim.x > 1) { lk = kIndKinds[blockIdx.x / 3]; rk = kIndKinds[blockIdx.x % 3]; fac += blockIdx.x * fac_stride; }
+    if (gridDim.x > 1) { lk = ind_kind(blockIdx.x / 3); rk = ind_kind(blockIdx.x % 3); fac += blockIdx.x * fac_stride; }
     FacRow<T>* rows = reinterpret_cast<FacRow<T>*>(fac);
     T* k2 = fac + 4 * (size_t)n;
     const bool nak3 = !periodic && n == 3 && lk == SB_NAK && rk == SB_NAK;
@@ -332,7 +218,6 @@ __global__ void __launch_bounds__(128) spline_columns_kernel(const T* __restrict
 
 // ---- the three-launch build ---------------------------------------------------------------------------
 constexpr int kRows = 8, kRing = 4;       // sweep: kRing batches of kRows rows in flight per thread
-constexpr int kRowGroup = 4;              // rhs / ab: rows per thread, sharing their loads
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -432,18 +317,9 @@ __device__ __forceinline__ void cp_async_fac(unsigned smem_addr, const FacRow<T>
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr + 16), "l"(reinterpret_cast<const char*>(src) + 16) : "memory");
 }
 
-// Individual boundaries sweep all (up to nine) groups of columns in ONE launch: the groups are
-// independent and each is bound by its chain latency, not by throughput.
-struct SweepGroups {
-    int ngroups;                 // 0: one group = all ncols columns, factorisation at fac
-    int first_block[10];         // blocks [first_block[g], first_block[g+1]) sweep group g
-    long long col_off[9], count[9];
-    unsigned long long fac_stride;
-};
-
 template <class T, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) spline_sweep_kernel(int len, long long w, long long ncols, const T* __restrict__ fac,
-                                                             T* __restrict__ R, const SweepGroups groups) {
+__global__ void __launch_bounds__(BLOCK) spline_sweep_kernel(int total_len, int nsys, long long w, long long ncols,
+                                                             const T* __restrict__ fac, T* __restrict__ R, const SweepGroups groups) {
     extern __shared__ __align__(32) unsigned char ring_raw[];
     constexpr int kSuper = kRing * kRows;                     // rows per outer iteration
     static_assert(kSuper == 32, "one matrix row per lane and outer iteration");
@@ -456,39 +332,47 @@ __global__ void __launch_bounds__(BLOCK) spline_sweep_kernel(int len, long long 
         block -= groups.first_block[g];
         ncols = groups.count[g]; R += groups.col_off[g]; fac += g * groups.fac_stride;
     }
+    // interleaved systems (row-split build): the blocks of a group are laid out system by system; system j is
+    // rows j, j + nsys, ... of R, so a chain advances by nsys rows per step and reads every nsys-th matrix row
+    const int bps = (int)((ncols + BLOCK - 1) / BLOCK);       // blocks per system
+    const int sys = block / bps;
+    block -= sys * bps;
+    const int len = (total_len - sys + nsys - 1) / nsys;      // rows of this system
+    const long long rs = (long long)nsys * w;                 // elements between consecutive rows of a chain
+    R += (long long)sys * w;
     const long long c0 = (long long)block * BLOCK + threadIdx.x;
     const bool live = c0 < ncols;                             // dead lanes shadow the last column (they stage matrix rows too)
-    const long long c = live ? c0 : ncols - 1;                // w: row stride of R, ncols: columns this launch sweeps
+    const long long c = live ? c0 : ncols - 1;                // w: row stride of R, ncols: columns of this group
     const int lane = threadIdx.x & 31;
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(ring_raw);
     const unsigned ring = smem0 + threadIdx.x * (unsigned)sizeof(T);
     const unsigned facbuf = smem0 + kSuper * kSlot + (threadIdx.x >> 5) * (2 * kSuper * kFacBytes);   // this warp's [2][32] rows
-    const FacRow<T>* rows = reinterpret_cast<const FacRow<T>*>(fac);
+    const FacRow<T>* rows = reinterpret_cast<const FacRow<T>*>(fac) + sys;   // row t of this system: rows[t * nsys]
     T* col = R + c;
 
     T k;                                                      // k[len-1] after the forward sweep, then the running k[i+1]
     // ---- forward: r[i] = rhs[i] - wl[i] * r[i-1], i = 1 .. len-1
     {
-        const T* pf = col + w;                                // next row to prefetch
+        const T* pf = col + rs;                                // next row to prefetch
         int pf_left = len - 1;
         auto prefetch = [&](int slot0) {
 #pragma unroll
             for (int j = 0; j < kRows; ++j) {
                 if (j < pf_left) cp_async_elem<T>(ring + (slot0 + j) * kSlot, pf);
-                pf += w;
+                pf += rs;
             }
             pf_left -= kRows;
         };
         int fac_row = 1 + lane;                               // the matrix row this lane stages next
         auto stage_fac = [&](int buf) {
-            if (fac_row < len) cp_async_fac<T>(facbuf + (buf * kSuper + lane) * kFacBytes, rows + fac_row);
+            if (fac_row < len) cp_async_fac<T>(facbuf + (buf * kSuper + lane) * kFacBytes, rows + (long long)fac_row * nsys);
             fac_row += kSuper;
         };
         stage_fac(0);
 #pragma unroll
         for (int b = 0; b < kRing - 1; ++b) { prefetch(b * kRows); cp_async_commit(); }
         T prev = col[0];
-        T* wp = col + w;
+        T* wp = col + rs;
         int buf = 0;
         for (int left = len - 1; left > 0; buf ^= 1) {
 #pragma unroll
@@ -511,15 +395,15 @@ __global__ void __launch_bounds__(BLOCK) spline_sweep_kernel(int len, long long 
                         prev = SUB(rv[j], MUL(wv[j], prev));                          // :698
                         if (live) *wp = prev;
                     }
-                    wp += w;
+                    wp += rs;
                 }
                 left -= kRows;
             }
             __syncwarp();                                     // everyone is done with buf before it is staged again
         }
-        const FacRow<T> flast = ld_fac<T>(rows + len - 1);
+        const FacRow<T> flast = ld_fac<T>(rows + (long long)(len - 1) * nsys);
         k = Hoisted<T>::div(prev, flast.mid, flast.rmid);                             // :704-708
-        if (live) col[(long long)(len - 1) * w] = k;
+        if (live) col[(long long)(len - 1) * rs] = k;
     }
     cp_async_wait<0>();
     __threadfence();                                          // the swept values are read back below
@@ -527,25 +411,25 @@ __global__ void __launch_bounds__(BLOCK) spline_sweep_kernel(int len, long long 
 
     // ---- backward: k[i] = (r[i] - up[i] * k[i+1]) / mid[i], i = len-2 .. 0
     {
-        const T* pf = col + (long long)(len - 2) * w;
+        const T* pf = col + (long long)(len - 2) * rs;
         int pf_left = len - 1;
         auto prefetch = [&](int slot0) {
 #pragma unroll
             for (int j = 0; j < kRows; ++j) {
                 if (j < pf_left) cp_async_elem<T>(ring + (slot0 + j) * kSlot, pf);
-                pf -= w;
+                pf -= rs;
             }
             pf_left -= kRows;
         };
         int fac_row = len - 2 - lane;
         auto stage_fac = [&](int buf) {
-            if (fac_row >= 0) cp_async_fac<T>(facbuf + (buf * kSuper + lane) * kFacBytes, rows + fac_row);
+            if (fac_row >= 0) cp_async_fac<T>(facbuf + (buf * kSuper + lane) * kFacBytes, rows + (long long)fac_row * nsys);
             fac_row -= kSuper;
         };
         stage_fac(0);
 #pragma unroll
         for (int b = 0; b < kRing - 1; ++b) { prefetch(b * kRows); cp_async_commit(); }
-        T* wp = col + (long long)(len - 2) * w;
+        T* wp = col + (long long)(len - 2) * rs;
         int buf = 0;
         for (int left = len - 1; left > 0; buf ^= 1) {
 #pragma unroll
@@ -568,7 +452,7 @@ __global__ void __launch_bounds__(BLOCK) spline_sweep_kernel(int len, long long 
                         k = Hoisted<T>::div(SUB(rv[j], MUL(uv[j], k)), mv[j], iv[j]);  // :716
                         if (live) *wp = k;
                     }
-                    wp -= w;
+                    wp -= rs;
                 }
                 left -= kRows;
             }
@@ -693,50 +577,78 @@ __global__ void __launch_bounds__(128) spline_columns_individual_kernel(
     }
 }
 
+static size_t seq_fac_elems(int64_t n) { return (5 * (size_t)n + 3) & ~(size_t)3; }
+
 template <class T>
-size_t spline_scratch_elems(int64_t n, int64_t w, int bc_kind) {
-    // factorisation(s) (FacRow[n] + k2[n], padded) + the matrix R; Individual: nine factorisations (n < 4: a diagonal per column)
-    const size_t fac = (5 * (size_t)n + 3) & ~(size_t)3;
+size_t spline_scratch_elems(int64_t n, int64_t w, int bc_kind, int levels) {
+    // factorisation(s) (FacRow[n] + k2[n] (+ the row-split coefficients), padded) + the matrix R;
+    // Individual: nine factorisations (n < 4: a diagonal per column)
+    const size_t fac = levels > 0 ? rowsplit_fac_elems(n, levels) : seq_fac_elems(n);
     if (bc_kind == BC_INDIVIDUAL) return n < 4 ? (size_t)n * (size_t)w : 9 * fac + (size_t)n * (size_t)w;
     return fac + (size_t)n * (size_t)w;
 }
 
 template <class T>
+cudaError_t launch_spline_sweep(int len, int nsys, long long w, const T* fac, size_t fac_stride, T* R, const int64_t* counts,
+                                cudaStream_t st) {
+    // few chains: small blocks so that more SMs take part; many: 128-thread blocks
+    const int blk = ((long long)nsys * w <= 32ll * 2 * device_info().sm_count) ? 32 : 128;
+    SweepGroups sg = {};
+    long long nblocks = (long long)nsys * ((w + blk - 1) / blk);
+    if (counts) {
+        sg.ngroups = 9; sg.fac_stride = fac_stride;
+        long long off = 0, first = 0;
+        for (int g = 0; g < 9; ++g) {
+            sg.first_block[g] = (int)first; sg.col_off[g] = off; sg.count[g] = counts[g];
+            first += (long long)nsys * ((counts[g] + blk - 1) / blk); off += counts[g];
+        }
+        sg.first_block[9] = (int)first;
+        nblocks = first;
+    }
+    if (nblocks <= 0) return cudaSuccess;
+    const size_t smem = (size_t)kRing * kRows * blk * sizeof(T) + (size_t)(blk / 32) * 2 * kRing * kRows * sizeof(FacRow<T>);
+    if (blk == 32) spline_sweep_kernel<T, 32><<<(unsigned)nblocks, 32, smem, st>>>(len, nsys, w, w, fac, R, sg);
+    else spline_sweep_kernel<T, 128><<<(unsigned)nblocks, 128, smem, st>>>(len, nsys, w, w, fac, R, sg);
+    count_launch();
+    return cudaGetLastError();
+}
+
+static int row_group_grid(long long w, long long nrows) {
+    const long long chunks = (w + 255) / 256;
+    const long long cap = (long long)device_info().sm_count * 8;
+    const long long tasks = chunks * ((nrows + kRowGroup - 1) / kRowGroup);
+    return (int)(tasks < cap ? tasks : cap);
+}
+
+template <class T>
+cudaError_t launch_spline_ab(const T* x, int n, const T* y, long long w, int periodic, const T* fac, const T* R, T* a, T* b,
+                             const int32_t* pos, cudaStream_t st) {
+    spline_ab_kernel<T><<<row_group_grid(w, n - 1), 256, 0, st>>>(x, n, y, w, periodic, fac, R, a, b, pos);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <class T>
+cudaError_t launch_spline_periodic_close(const T* x, int n, long long w, const T* fac, T* R, cudaStream_t st) {
+    spline_periodic_close_kernel<T><<<(int)((w + 255) / 256), 256, 0, st>>>(x, n, w, fac, R);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// levels == 0: the reference's elimination order (coefficients bit-identical to the reference arithmetic);
+// levels > 0: row-split build -- `levels` steps of parallel cyclic reduction, then 2^levels interleaved systems
+// per column (ndi_rowsplit.cu); the caller has checked that the systems keep at least two rows.
+template <class T>
 cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w, int bc_kind, const int32_t* lk,
                                 const T* lv, const int32_t* rk, const T* rv, const int32_t* pos, const int64_t* group_count,
-                                T* a, T* b, T* scratch, unsigned long long* err, cudaStream_t st) {
+                                int levels, T* a, T* b, T* scratch, unsigned long long* err, cudaStream_t st) {
     if (w <= 0) return cudaSuccess;
     // few columns: small blocks so that more SMs take part; many columns: 128-thread blocks
     const int block = (w <= 32ll * 2 * device_info().sm_count) ? 32 : 128;
     const int grid = (int)((w + block - 1) / block);
-    const size_t fac_elems = (5 * (size_t)n + 3) & ~(size_t)3;
-    const long long chunks = (w + 255) / 256;
-    const long long cap = (long long)device_info().sm_count * 8;
-    auto grid_for = [&](long long nrows) {
-        const long long tasks = chunks * ((nrows + kRowGroup - 1) / kRowGroup);
-        return (int)(tasks < cap ? tasks : cap);
-    };
-    auto sweep = [&](int len, const T* fac, T* Rm, const int64_t* counts) -> cudaError_t {
-        // few columns: small blocks so that more SMs take part; many columns: 128-thread blocks
-        const int blk = (w <= 32ll * 2 * device_info().sm_count) ? 32 : 128;
-        SweepGroups sg = {};
-        int nblocks = (int)((w + blk - 1) / blk);
-        if (counts) {
-            sg.ngroups = 9; sg.fac_stride = fac_elems;
-            long long off = 0; int first = 0;
-            for (int g = 0; g < 9; ++g) {
-                sg.first_block[g] = first; sg.col_off[g] = off; sg.count[g] = counts[g];
-                first += (int)((counts[g] + blk - 1) / blk); off += counts[g];
-            }
-            sg.first_block[9] = first;
-            nblocks = first;
-        }
-        const size_t smem = (size_t)kRing * kRows * blk * sizeof(T) + (size_t)(blk / 32) * 2 * kRing * kRows * sizeof(FacRow<T>);
-        if (blk == 32) spline_sweep_kernel<T, 32><<<nblocks, 32, smem, st>>>(len, (long long)w, (long long)w, fac, Rm, sg);
-        else spline_sweep_kernel<T, 128><<<nblocks, 128, smem, st>>>(len, (long long)w, (long long)w, fac, Rm, sg);
-        count_launch();
-        return cudaGetLastError();
-    };
+    const size_t fac_elems = levels > 0 ? rowsplit_fac_elems(n, levels) : seq_fac_elems(n);
+    const int nsys = 1 << levels;
+    cudaError_t e;
     if (bc_kind == BC_INDIVIDUAL) {
         if (n < 4 || !pos || !group_count) {                 // the 3-point special cases: one factorisation per column
             spline_columns_individual_kernel<T><<<grid, block, 0, st>>>(x, (int)n, data, (long long)w, lk, lv, rk, rv, a, b, scratch);
@@ -745,56 +657,60 @@ cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w,
         }
         // columns grouped by (left kind, right kind): nine shared-matrix builds in the same three launches
         T* R = scratch + 9 * fac_elems;
-        spline_factor_kernel<T><<<9, kFacBlock, 0, st>>>(x, (int)n, 0, 0, 0, scratch, fac_elems);
-        count_launch();
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        spline_rhs_kernel<T><<<grid_for(n), 256, 0, st>>>(x, (int)n, data, (long long)w, 0, Side<T>{SB_NAK, (T)0}, Side<T>{SB_NAK, (T)0}, R, err,
-                                                          lk, lv, rk, rv, pos);
-        count_launch();
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if ((e = sweep((int)n, scratch, R, group_count)) != cudaSuccess) return e;
-        spline_ab_kernel<T><<<grid_for(n - 1), 256, 0, st>>>(x, (int)n, data, (long long)w, 0, scratch, R, a, b, pos);
-        count_launch();
-        return cudaGetLastError();
+        if (levels > 0) {
+            if ((e = launch_rowsplit_front<T>(x, n, data, w, bc_kind, levels, lk, lv, rk, rv, pos, scratch, fac_elems, R, err, st)) != cudaSuccess) return e;
+        } else {
+            spline_factor_kernel<T><<<9, kFacBlock, 0, st>>>(x, (int)n, 0, 0, 0, scratch, fac_elems);
+            count_launch();
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            spline_rhs_kernel<T><<<row_group_grid(w, n), 256, 0, st>>>(x, (int)n, data, (long long)w, 0, Side<T>{SB_NAK, (T)0}, Side<T>{SB_NAK, (T)0}, R, err,
+                                                                       lk, lv, rk, rv, pos);
+            count_launch();
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+        if ((e = launch_spline_sweep<T>((int)n, nsys, (long long)w, scratch, fac_elems, R, group_count, st)) != cudaSuccess) return e;
+        return launch_spline_ab<T>(x, (int)n, data, (long long)w, 0, scratch, R, a, b, pos, st);
     }
     Side<T> l{SB_NAK, (T)0}, r{SB_NAK, (T)0};
     if (bc_kind == BC_NATURAL) l = r = Side<T>{SB_NATURAL, (T)0};
     if (bc_kind == BC_CLAMPED) l = r = Side<T>{SB_CLAMPED, (T)0};
     const int periodic = bc_kind == BC_PERIODIC;
     const Side<T> ls = specialize(l), rs = specialize(r);
-    spline_factor_kernel<T><<<1, kFacBlock, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, scratch, 0);
-    count_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
     if (n >= 4) {
         T* R = scratch + fac_elems;
-        const int rows = periodic ? (int)n - 1 : (int)n;
-        spline_rhs_kernel<T><<<grid_for(rows), 256, 0, st>>>(x, (int)n, data, (long long)w, periodic, l, r, R, err);
-        count_launch();
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if ((e = sweep(periodic ? (int)n - 2 : (int)n, scratch, R, nullptr)) != cudaSuccess) return e;
-        if (periodic) {
-            spline_periodic_close_kernel<T><<<(int)chunks, 256, 0, st>>>(x, (int)n, (long long)w, scratch, R);
+        if (levels > 0) {
+            if ((e = launch_rowsplit_front<T>(x, n, data, w, bc_kind, levels, nullptr, nullptr, nullptr, nullptr, nullptr, scratch, 0, R, err, st)) != cudaSuccess) return e;
+        } else {
+            spline_factor_kernel<T><<<1, kFacBlock, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, scratch, 0);
+            count_launch();
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            const int rows = periodic ? (int)n - 1 : (int)n;
+            spline_rhs_kernel<T><<<row_group_grid(w, rows), 256, 0, st>>>(x, (int)n, data, (long long)w, periodic, l, r, R, err);
             count_launch();
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
         }
-        spline_ab_kernel<T><<<grid_for(n - 1), 256, 0, st>>>(x, (int)n, data, (long long)w, periodic, scratch, R, a, b);
-        count_launch();
-        return cudaGetLastError();
+        if ((e = launch_spline_sweep<T>(periodic ? (int)n - 2 : (int)n, nsys, (long long)w, scratch, 0, R, nullptr, st)) != cudaSuccess) return e;
+        if (periodic && (e = launch_spline_periodic_close<T>(x, (int)n, (long long)w, scratch, R, st)) != cudaSuccess) return e;
+        return launch_spline_ab<T>(x, (int)n, data, (long long)w, periodic, scratch, R, a, b, nullptr, st);
     }
+    spline_factor_kernel<T><<<1, kFacBlock, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, scratch, 0);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     spline_columns_kernel<T><<<grid, block, 0, st>>>(x, (int)n, data, (long long)w, periodic, l, r, scratch, a, b, err);
     count_launch();
     return cudaGetLastError();
 }
 
-template cudaError_t launch_spline_build<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*,
-                                                const float*, const int32_t*, const float*, const int32_t*, const int64_t*,
-                                                float*, float*, float*, unsigned long long*, cudaStream_t);
-template cudaError_t launch_spline_build<double>(const double*, int64_t, const double*, int64_t, int, const int32_t*,
-                                                 const double*, const int32_t*, const double*, const int32_t*, const int64_t*,
-                                                 double*, double*, double*, unsigned long long*, cudaStream_t);
-template size_t spline_scratch_elems<float>(int64_t, int64_t, int);
-template size_t spline_scratch_elems<double>(int64_t, int64_t, int);
+#define NDI_INST_SPLINE(T)                                                                                                   \
+    template cudaError_t launch_spline_build<T>(const T*, int64_t, const T*, int64_t, int, const int32_t*, const T*,         \
+                                                const int32_t*, const T*, const int32_t*, const int64_t*, int, T*, T*, T*,   \
+                                                unsigned long long*, cudaStream_t);                                          \
+    template cudaError_t launch_spline_sweep<T>(int, int, long long, const T*, size_t, T*, const int64_t*, cudaStream_t);    \
+    template cudaError_t launch_spline_ab<T>(const T*, int, const T*, long long, int, const T*, const T*, T*, T*,            \
+                                             const int32_t*, cudaStream_t);                                                  \
+    template cudaError_t launch_spline_periodic_close<T>(const T*, int, long long, const T*, T*, cudaStream_t);              \
+    template size_t spline_scratch_elems<T>(int64_t, int64_t, int, int);
+NDI_INST_SPLINE(float)
+NDI_INST_SPLINE(double)
 
 }  // namespace ndi

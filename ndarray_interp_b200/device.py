@@ -78,6 +78,17 @@ class DeviceInterp1D:
     def set_search_mode(self, mode):
         L.check(self.lib.ndi_interp1d_set_search_mode(self.h, int(mode)))
 
+    def set_build_mode(self, mode, levels=0):
+        """how spline_build solves the tridiagonal system: L.BUILD_AUTO / BUILD_SEQUENTIAL (the reference's order,
+        bit-identical coefficients) / BUILD_ROWSPLIT (`levels` steps of cyclic reduction, 0: library's choice)"""
+        L.check(self.lib.ndi_interp1d_set_build_mode(self.h, int(mode), int(levels)))
+
+    def build_levels(self):
+        """row-split depth the current coefficients were built with (0: the reference's order)"""
+        lv = C.c_int32(-1)
+        L.check(self.lib.ndi_interp1d_build_info(self.h, C.byref(lv)))
+        return lv.value
+
     def spline_build(self, bc_kind=0, left_kind=None, left_val=None, right_kind=None, right_val=None):
         """CubicSpline::calc_coefficients on the device; returns the status (0 or PERIODIC_MISMATCH)"""
         torch.cuda.current_stream().synchronize()

@@ -183,10 +183,19 @@ class CubicSpline(Interp1DStrategyBuilder):
     def __init__(self):
         self._extrapolate = False
         self._boundary = BoundaryCondition.NotAKnot
+        self._solver = (L.BUILD_AUTO, 0)
 
     @classmethod
     def new(cls):
         return cls()
+
+    def solver(self, mode, levels=0):
+        """NOT in the reference (device-side knob, include/ndi_b200.h: ndi_interp1d_set_build_mode): "auto",
+        "sequential" -- the reference's elimination order, coefficients bit-identical to its arithmetic -- or
+        "rowsplit" -- parallel cyclic reduction + Thomas, `levels` reduction steps (0: the library's choice)."""
+        self._solver = ({"auto": L.BUILD_AUTO, "sequential": L.BUILD_SEQUENTIAL, "rowsplit": L.BUILD_ROWSPLIT}[mode],
+                        int(levels))
+        return self
 
     def extrapolate(self, extrapolate):
         self._extrapolate = bool(extrapolate)
@@ -222,21 +231,22 @@ class CubicSpline(Interp1DStrategyBuilder):
             mode = L.EXTRAP_PERIODIC
         else:
             mode = L.EXTRAP_YES
-        return CubicSplineStrategy(_BC[bc.kind], (lk, lv, rk, rv), mode)
+        return CubicSplineStrategy(_BC[bc.kind], (lk, lv, rk, rv), mode, self._solver)
 
 
 class CubicSplineStrategy(Interp1DStrategy):
     """The CubicSpline 1d interpolation Strategy (Implementation) (cubic_spline.rs:94-102).
     The coefficient arrays a, b live on the device inside the interpolator's handle."""
 
-    def __init__(self, bc_kind, individual, mode):
-        self._bc_kind, self._individual, self._mode = bc_kind, individual, mode
+    def __init__(self, bc_kind, individual, mode, solver=(0, 0)):
+        self._bc_kind, self._individual, self._mode, self._solver = bc_kind, individual, mode, solver
 
     def _bind(self, interpolator):
         # CubicSpline::calc_coefficients (cubic_spline.rs:310-368) on the device
         h = interpolator._handle()
         lk, lv, rk, rv = self._individual
         bad = C.c_int64(-1)
+        L.check(L.load().ndi_interp1d_set_build_mode(h, *self._solver))
         st = L.check(L.load().ndi_interp1d_spline_build(h, self._bc_kind, L.ptr(lk), L.ptr(lv), L.ptr(rk), L.ptr(rv),
                                                         C.byref(bad)))
         if st == L.PERIODIC_MISMATCH:                      # cubic_spline.rs:483-507
@@ -248,6 +258,12 @@ class CubicSplineStrategy(Interp1DStrategy):
                 msg = f"First: {_ndarray_debug(first)}, last: {_ndarray_debug(last)}"
             raise BuilderError.ValueError(
                 "for periodic boundary condition the first and last value must be equal. " + msg)
+
+    def rowsplit_levels(self, interpolator):
+        """depth of the row-split the coefficients were built with (0: the reference's elimination order)"""
+        lv = C.c_int32(-1)
+        L.check(L.load().ndi_interp1d_build_info(interpolator._handle(), C.byref(lv)))
+        return lv.value
 
     def coefficients(self, interpolator):
         """(a, b) copied back from the device: shape (n-1, ...data.shape[1:])"""

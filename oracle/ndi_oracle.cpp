@@ -221,10 +221,11 @@ void thomas(T* k, const T* a_up, T* a_mid, const T* a_low, T* rhs, int64_t len, 
     }
 }
 
-// Row-split variant of the solve (NOT the reference's order; DESIGN.md section 7 item 3): `levels` steps of
+// Row-split variant of the solve (NOT the reference's order; DESIGN.md section 4, K6): `levels` steps of
 // parallel cyclic reduction, then thomas() on each of the 2^levels interleaved systems (rows j, j+S, j+2S, ...).
-// It exists so that a future row-split build kernel has an operation-by-operation specification to be compared
-// with, the way every shipped kernel is compared with the functions above.  One reduction step with stride s:
+// It is the operation-by-operation specification the row-split build kernels (csrc/ndi_rowsplit.cu,
+// NDI_BUILD_ROWSPLIT) are compared with bit for bit, the way every other kernel is compared with the functions
+// above; the functions above remain the statement of the reference's own arithmetic.  One reduction step with stride s:
 //     alpha = -(low[i] / mid[i-s])   (0 when i-s < 0)        gamma = -(up[i] / mid[i+s])   (0 when i+s > len-1)
 //     low'[i] = alpha * low[i-s]     up'[i] = gamma * up[i+s]
 //     mid'[i] = (mid[i] + alpha * up[i-s]) + gamma * low[i+s]
@@ -268,7 +269,7 @@ void rowsplit_thomas(T* k, const T* a_up, const T* a_mid, const T* a_low, const 
     }
 }
 // > 0: solve_for_k's full-system solve (:672) uses rowsplit_thomas with that many levels (set by
-// ora_spline_build_rowsplit_* for the duration of one call; periodic systems keep the reference's solve)
+// ora_spline_build_rowsplit_* for the duration of one call; periodic: both solves of the condensed system)
 thread_local int32_t g_rowsplit_levels = 0;
 
 template <class T>
@@ -347,8 +348,13 @@ int32_t solve_for_k(T* k, const T* x, const T* data, int64_t len, int64_t w, int
         std::vector<T> k1((size_t)m * w, zero), k2((size_t)m * w, zero);
         {
             std::vector<T> mid1(a_mid.begin(), a_mid.begin() + m), mid2(mid1);
-            thomas(k1.data(), a_up.data(), mid1.data(), a_low.data(), rhs1.data(), m, w); // :543-549
-            thomas(k2.data(), a_up.data(), mid2.data(), a_low.data(), rhs2.data(), m, w); // :550
+            if (g_rowsplit_levels > 0) {                          // row-split specification: both solves of the condensed system
+                rowsplit_thomas(k1.data(), a_up.data(), mid1.data(), a_low.data(), rhs1.data(), m, w, g_rowsplit_levels);
+                rowsplit_thomas(k2.data(), a_up.data(), mid2.data(), a_low.data(), rhs2.data(), m, w, g_rowsplit_levels);
+            } else {
+                thomas(k1.data(), a_up.data(), mid1.data(), a_low.data(), rhs1.data(), m, w); // :543-549
+                thomas(k2.data(), a_up.data(), mid2.data(), a_low.data(), rhs2.data(), m, w); // :550
+            }
         }
         for (int64_t c = 0; c < w; ++c) {
             T k_m1 = (rhs[(len - 2) * w + c] - k1[0 * w + c] * dx_2 - k1[(len - 3) * w + c] * dx_1)

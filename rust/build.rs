@@ -2,7 +2,7 @@
 //! No Triton, no multi-backend dispatch, no CPU fallback: without nvcc the build fails.
 use std::{env, path::PathBuf, process::Command};
 
-const SOURCES: [&str; 5] = ["ndi_api.cu", "ndi_eval.cu", "ndi_bin.cu", "ndi_grid.cu", "ndi_spline.cu"];
+const SOURCES: [&str; 6] = ["ndi_api.cu", "ndi_eval.cu", "ndi_bin.cu", "ndi_grid.cu", "ndi_spline.cu", "ndi_rowsplit.cu"];
 
 fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
@@ -34,7 +34,7 @@ fn main() {
     println!("cargo:rustc-link-search=native={cuda}/lib64");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
-    for h in ["ndi_device.cuh", "ndi_internal.h"] {
+    for h in ["ndi_device.cuh", "ndi_spline.cuh", "ndi_internal.h"] {
         println!("cargo:rerun-if-changed={}", csrc.join(h).display());
     }
 }

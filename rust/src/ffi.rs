@@ -35,6 +35,9 @@ extern "C" {
     pub fn ndi_interp1d_destroy(h: *mut ndi_interp1d) -> ndi_status;
     pub fn ndi_interp1d_linear(h: *const ndi_interp1d, q: *const c_void, nq: i64, extrapolate: i32, out: *mut c_void, first_bad: *mut i64) -> ndi_status;
     pub fn ndi_interp1d_spline_build(h: *mut ndi_interp1d, bc_kind: i32, left_kind: *const i32, left_val: *const c_void, right_kind: *const i32, right_val: *const c_void, bad_column: *mut i64) -> ndi_status;
+    /// spline solve: 0 auto, 1 the reference's elimination order, 2 row-split (PCR + Thomas) with `levels` reduction steps
+    pub fn ndi_interp1d_set_build_mode(h: *mut ndi_interp1d, mode: i32, levels: i32) -> ndi_status;
+    pub fn ndi_interp1d_build_info(h: *const ndi_interp1d, rowsplit_levels: *mut i32) -> ndi_status;
     pub fn ndi_interp1d_spline_coeffs(h: *const ndi_interp1d, a: *mut c_void, b: *mut c_void) -> ndi_status;
     pub fn ndi_interp1d_cubic(h: *const ndi_interp1d, q: *const c_void, nq: i64, extrap_mode: i32, out: *mut c_void, first_bad: *mut i64) -> ndi_status;
 

@@ -84,10 +84,28 @@ enum Extrapolate {
 }
 
 /// The CubicSpline 1d interpolation Strategy (Implementation).
-/// The coefficient arrays `a`, `b` live in the interpolator's device table.
+/// The coefficient arrays `a`, `b` live in the interpolator's device table; `spec` is the boundary
+/// condition as the C ABI takes it, consumed by [`Interp1DStrategy::bind`] when the coefficients are built.
+/// Same type parameters as the reference's `CubicSplineStrategy<Sd, D>`.
 #[derive(Debug)]
-pub struct CubicSplineStrategy {
+pub struct CubicSplineStrategy<Sd, D>
+where
+    Sd: Data,
+    D: Dimension + RemoveAxis,
+{
     extrapolate: Extrapolate,
+    spec: Option<BoundarySpec<Sd::Elem>>,
+    _dim: std::marker::PhantomData<D>,
+}
+
+/// `bc_kind` plus, for `Individual`, one (kind, value) pair per column and side
+#[derive(Debug)]
+struct BoundarySpec<T> {
+    kind: i32,
+    lk: Vec<i32>,
+    lv: Vec<T>,
+    rk: Vec<i32>,
+    rv: Vec<T>,
 }
 
 impl<T: SplineNum, D: Dimension + RemoveAxis> CubicSpline<T, D> {
@@ -123,9 +141,9 @@ where
     D: Dimension + RemoveAxis,
 {
     const MINIMUM_DATA_LENGHT: usize = 3;
-    type FinishedStrat = CubicSplineStrategy;
+    type FinishedStrat = CubicSplineStrategy<Sd, D>;
 
-    fn build<Sx2>(self, _x: &ArrayBase<Sx2, Ix1>, data: &ArrayBase<Sd, D>, table: &mut DeviceTable1D) -> Result<CubicSplineStrategy, BuilderError>
+    fn build<Sx2>(self, _x: &ArrayBase<Sx2, Ix1>, data: &ArrayBase<Sd, D>) -> Result<CubicSplineStrategy<Sd, D>, BuilderError>
     where
         Sx2: Data<Elem = Sd::Elem>,
     {
@@ -160,33 +178,6 @@ where
                 4
             }
         };
-        let mut bad_column = -1i64;
-        let st = unsafe {
-            ffi::ndi_interp1d_spline_build(
-                table.0,
-                kind,
-                if lk.is_empty() { std::ptr::null() } else { lk.as_ptr() },
-                if lv.is_empty() { std::ptr::null() } else { lv.as_ptr() as *const c_void },
-                if rk.is_empty() { std::ptr::null() } else { rk.as_ptr() },
-                if rv.is_empty() { std::ptr::null() } else { rv.as_ptr() as *const c_void },
-                &mut bad_column,
-            )
-        };
-        match st {
-            ffi::NDI_OK => {}
-            ffi::NDI_PERIODIC_MISMATCH => {
-                let (first, last) = (data.index_axis(Axis(0), 0), data.index_axis(Axis(0), data.shape()[0] - 1));
-                let msg = if data.ndim() == 1 {
-                    format!("First: {:?}, last: {:?}", data.first().unwrap_or_else(|| unreachable!()), data.last().unwrap_or_else(|| unreachable!()))
-                } else {
-                    format!("First: {first:?}, last: {last:?}")
-                };
-                return Err(BuilderError::ValueError(format!(
-                    "for periodic boundary condition the first and last value must be equal. {msg}"
-                )));
-            }
-            _ => panic!("ndi_interp1d_spline_build failed ({st}): {}", ffi::last_error()),
-        }
         let extrapolate = if !self.extrapolate {
             Extrapolate::No
         } else if matches!(self.boundary, BoundaryCondition::Periodic) {
@@ -194,17 +185,43 @@ where
         } else {
             Extrapolate::Yes
         };
-        Ok(CubicSplineStrategy { extrapolate })
+        Ok(CubicSplineStrategy { extrapolate, spec: Some(BoundarySpec { kind, lk, lv, rk, rv }), _dim: std::marker::PhantomData })
     }
 }
 
-impl<Sd, Sx, D> Interp1DStrategy<Sd, Sx, D> for CubicSplineStrategy
+impl<Sd, Sx, D> Interp1DStrategy<Sd, Sx, D> for CubicSplineStrategy<Sd, D>
 where
     Sd: Data,
     Sd::Elem: SplineNum,
     Sx: Data<Elem = Sd::Elem>,
     D: Dimension + RemoveAxis,
 {
+    /// CubicSpline::calc_coefficients on the device (K6), once, with the uploaded tables
+    fn bind(&mut self, data: &ArrayBase<Sd, D>, table: &mut DeviceTable1D) -> Result<(), BuilderError> {
+        let Some(spec) = self.spec.take() else { return Ok(()) };
+        let ptr_i = |v: &Vec<i32>| if v.is_empty() { std::ptr::null() } else { v.as_ptr() };
+        let ptr_t = |v: &Vec<Sd::Elem>| if v.is_empty() { std::ptr::null() } else { v.as_ptr() as *const c_void };
+        let mut bad_column = -1i64;
+        let st = unsafe {
+            ffi::ndi_interp1d_spline_build(table.0, spec.kind, ptr_i(&spec.lk), ptr_t(&spec.lv), ptr_i(&spec.rk), ptr_t(&spec.rv), &mut bad_column)
+        };
+        match st {
+            ffi::NDI_OK => Ok(()),
+            ffi::NDI_PERIODIC_MISMATCH => {
+                let (first, last) = (data.index_axis(Axis(0), 0), data.index_axis(Axis(0), data.shape()[0] - 1));
+                let msg = if data.ndim() == 1 {
+                    format!("First: {:?}, last: {:?}", data.first().unwrap_or_else(|| unreachable!()), data.last().unwrap_or_else(|| unreachable!()))
+                } else {
+                    format!("First: {first:?}, last: {last:?}")
+                };
+                Err(BuilderError::ValueError(format!(
+                    "for periodic boundary condition the first and last value must be equal. {msg}"
+                )))
+            }
+            _ => panic!("ndi_interp1d_spline_build failed ({st}): {}", ffi::last_error()),
+        }
+    }
+
     fn interp_into(
         &self,
         interp: &Interp1D<Sd, Sx, D, Self>,

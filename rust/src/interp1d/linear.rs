@@ -3,7 +3,7 @@ use std::ffi::c_void;
 
 use ndarray::{ArrayBase, ArrayViewMut, Data, Dimension, Ix1, RemoveAxis};
 
-use super::{eval_result, DeviceTable1D, Interp1D, Interp1DStrategy, Interp1DStrategyBuilder};
+use super::{eval_result, Interp1D, Interp1DStrategy, Interp1DStrategyBuilder};
 use crate::{ffi, BuilderError, InterpolateError, NdiElem};
 
 /// Linear Interpolation Strategy
@@ -41,7 +41,7 @@ where
     const MINIMUM_DATA_LENGHT: usize = 2;
     type FinishedStrat = Linear;
 
-    fn build<Sx2>(self, _x: &ArrayBase<Sx2, Ix1>, _data: &ArrayBase<Sd, D>, _table: &mut DeviceTable1D) -> Result<Linear, BuilderError>
+    fn build<Sx2>(self, _x: &ArrayBase<Sx2, Ix1>, _data: &ArrayBase<Sd, D>) -> Result<Linear, BuilderError>
     where
         Sx2: Data<Elem = Sd::Elem>,
     {

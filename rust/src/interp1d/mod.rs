@@ -42,14 +42,14 @@ where
     const MINIMUM_DATA_LENGHT: usize;
     type FinishedStrat: Interp1DStrategy<Sd, Sx, D>;
 
-    /// validate data / prepare the strategy.  Guarantees as in the reference: x strictly rising,
-    /// `x.len() == data.shape()[0] >= MINIMUM_DATA_LENGHT`.  `table` is the uploaded copy of
-    /// `(x, data)`; strategies that need device-side preparation (spline coefficients) do it here.
+    /// initialize the strategy by validating data (signature of the reference trait, unchanged).
+    /// Guarantees as in the reference: x strictly rising, `x.len() == data.shape()[0] >= MINIMUM_DATA_LENGHT`.
+    /// Device-side preparation (spline coefficients) happens afterwards, in
+    /// [`Interp1DStrategy::bind`], once the tables have been uploaded.
     fn build<Sx2>(
         self,
         x: &ArrayBase<Sx2, Ix1>,
         data: &ArrayBase<Sd, D>,
-        table: &mut DeviceTable1D,
     ) -> Result<Self::FinishedStrat, BuilderError>
     where
         Sx2: Data<Elem = Sd::Elem>;
@@ -70,6 +70,15 @@ where
         target: ArrayViewMut<'_, Sd::Elem, D::Smaller>,
         x: Sx::Elem,
     ) -> Result<(), InterpolateError>;
+
+    /// NOT in the reference trait.  Called once by [`Interp1DBuilder::build`] after
+    /// [`Interp1DStrategyBuilder::build`], with the uploaded device copy of `(x, data)`; strategies that keep
+    /// device-side state (the spline coefficients) create it here.  Provided: the default does nothing, so a
+    /// strategy written against the reference's two trait methods compiles and runs unchanged
+    /// (`examples/custom_strategy.rs`).
+    fn bind(&mut self, _data: &ArrayBase<Sd, D>, _table: &mut DeviceTable1D) -> Result<(), BuilderError> {
+        Ok(())
+    }
 
     /// The batch loop.  `xs` and `out` are contiguous, `out` holds `xs.len()` rows.  The default
     /// is the reference's loop over `interp_into` (host code, for user strategies); the built-in
@@ -349,8 +358,9 @@ where
                 data.shape()[0],
             )));
         }
+        let mut strategy = strategy.build(&x, &data)?;
         let mut table = upload(&x, &data, ffi::NDI_ASSUME_VALID)?;
-        let strategy = strategy.build(&x, &data, &mut table)?;
+        strategy.bind(&data, &mut table)?;
         Ok(Interp1D { x, data, strategy, table })
     }
 }

@@ -48,7 +48,7 @@ where
     Self: Sized,
 {
     /// Interpolate at position `(x, y)` into `target` (shape = data shape without axes 0 and 1).
-    fn interp_into(&self, interpolator: &Interp2D<Sd, Sx, Sy, D, Self>, target: ArrayViewMut<'_, Sd::Elem, Smaller2<D>>, x: Sx::Elem, y: Sy::Elem) -> Result<(), InterpolateError>;
+    fn interp_into(&self, interpolator: &Interp2D<Sd, Sx, Sy, D, Self>, target: ArrayViewMut<'_, Sd::Elem, <D::Smaller as Dimension>::Smaller>, x: Sx::Elem, y: Sy::Elem) -> Result<(), InterpolateError>;
 
     /// the batch loop; default = the reference's loop over `interp_into`, `Bilinear` = one launch
     fn interp_batch_into(&self, interpolator: &Interp2D<Sd, Sx, Sy, D, Self>, xs: &[Sd::Elem], ys: &[Sd::Elem], out: &mut [Sd::Elem]) -> Result<(), InterpolateError> {
@@ -109,7 +109,7 @@ where
     D: Dimension + RemoveAxis,
     D::Smaller: RemoveAxis,
 {
-    fn interp_into(&self, interpolator: &Interp2D<Sd, Sx, Sy, D, Self>, mut target: ArrayViewMut<'_, Sd::Elem, Smaller2<D>>, x: Sx::Elem, y: Sy::Elem) -> Result<(), InterpolateError> {
+    fn interp_into(&self, interpolator: &Interp2D<Sd, Sx, Sy, D, Self>, mut target: ArrayViewMut<'_, Sd::Elem, <D::Smaller as Dimension>::Smaller>, x: Sx::Elem, y: Sy::Elem) -> Result<(), InterpolateError> {
         match target.as_slice_mut() {
             Some(out) => self.interp_batch_into(interpolator, &[x], &[y], out),
             None => {

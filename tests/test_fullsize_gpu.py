@@ -36,11 +36,20 @@ def test_c2_cubic_natural_f64_full_size(D):
     y = rng.standard_normal((n, w))
     q = np.sort(rng.uniform(g[0], g[-1], nq))
     ip = D.DeviceInterp1D(dev(g), dev(y))
+    ip.set_build_mode(L.BUILD_SEQUENTIAL)                               # the reference's elimination order
     st, _ = ip.spline_build(1)
-    assert st == 0
+    assert st == 0 and ip.build_levels() == 0
     a, b = ip.coeffs_to_host()
-    st, a_ref, b_ref = O.spline_build(g, y, {"kind": "Natural"})
-    assert np.array_equal(a, a_ref) and np.array_equal(b, b_ref)        # K6 at the full C2 shape
+    st, a_seq, b_seq = O.spline_build(g, y, {"kind": "Natural"})
+    assert np.array_equal(a, a_seq) and np.array_equal(b, b_seq)        # K6 at the full C2 shape, reference order
+    ip.set_build_mode(L.BUILD_AUTO)                                     # 4096 rows: AUTO takes the row-split build
+    st, _ = ip.spline_build(1)
+    assert st == 0 and ip.build_levels() == 4
+    a, b = ip.coeffs_to_host()
+    st, a_ref, b_ref = O.spline_build(g, y, {"kind": "Natural"}, rowsplit_levels=4)
+    assert np.array_equal(a, a_ref) and np.array_equal(b, b_ref)        # bit for bit against its specification
+    for got, ref in ((a, a_seq), (b, b_seq)):                           # and inside 1e-12 of the reference order
+        assert float((np.abs(got - ref) / np.maximum(np.abs(ref), np.abs(y).max(axis=0)[None, :])).max()) <= 1e-12
     err = D.new_err_word()
     out = ip.cubic(dev(q), 0, err=err)
     assert D.err_word_value(err) == D.ERR_NONE
@@ -66,7 +75,7 @@ def test_c3_linear_extrapolate_f32_full_size(D):
     q = (float(g[0]) + span * rng.uniform(-0.026, 1.026, (4096, 4096))).astype(np.float32)
     ip = D.DeviceInterp1D(dev(g), dev(y))
     outs = []
-    for mode in (L.SEARCH_AUTO, L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS, L.SEARCH_BUCKET_LUT):
+    for mode in (L.SEARCH_AUTO, L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS, L.SEARCH_BUCKET_LUT, L.SEARCH_MERGE):
         ip.set_search_mode(mode)
         err = D.new_err_word()
         out = ip.linear(dev(q), True, err=err)
@@ -176,8 +185,8 @@ def test_c5b_cubic_f32_at_scale_sorted(D):
     st, _ = ip.spline_build(1)
     assert st == 0
     a, b = ip.coeffs_to_host()
-    st, a_ref, b_ref = O.spline_build(g, y, {"kind": "Natural"})
-    assert np.array_equal(a, a_ref) and np.array_equal(b, b_ref)
+    st, a_ref, b_ref = O.spline_build(g, y, {"kind": "Natural"}, rowsplit_levels=ip.build_levels())
+    assert ip.build_levels() == 4 and np.array_equal(a, a_ref) and np.array_equal(b, b_ref)
     q = torch.sort(torch.rand(nq, dtype=torch.float32, device="cuda") * float(g[-1] - g[0]) + float(g[0]))[0].clamp(float(g[0]), float(g[-1]))
     err = D.new_err_word()
     out = ip.cubic(q, 0, err=err)

@@ -229,8 +229,8 @@ def test_row_split_study_solves_the_same_system_as_the_oracle():
             pa, pb = P.coefficients(x, y, P.pcr_then_thomas(low, mid, up, rhs, levels))
             val = P.evaluate(x, y, pa, pb, q)
             assert float((np.abs(val - ref) / scale).max()) < bar / 10
-            # the oracle's row-split variant (rowsplit_thomas: the operation-by-operation specification a future
-            # row-split build kernel will be compared with) is this very computation
+            # the oracle's row-split variant (rowsplit_thomas: the operation-by-operation specification the
+            # row-split build kernels are compared with) is this very computation
             st, oa, ob = O.spline_build(x, y, {"kind": "Natural"}, rowsplit_levels=levels)
             assert st == O.ST_OK and np.array_equal(oa, pa) and np.array_equal(ob, pb)
         # every boundary kind whose system is tridiagonal: the row-split solve stays inside the bars
@@ -238,7 +238,10 @@ def test_row_split_study_solves_the_same_system_as_the_oracle():
             {"kind": "Mixed", "left": {"kind": "FirstDeriv", "value": 0.5}, "right": {"kind": "Natural"}},
             {"kind": "NotAKnot"},
             {"kind": "Mixed", "left": {"kind": "SecondDeriv", "value": -1.0}, "right": {"kind": "Clamped"}}]}
-        for bc in ({"kind": "NotAKnot"}, {"kind": "Clamped"}, ind):
+        yp = y.copy(); yp[-1] = yp[0]
+        for bc in ({"kind": "NotAKnot"}, {"kind": "Clamped"}, ind, {"kind": "Periodic"}):
+            if bc["kind"] == "Periodic":
+                y = yp
             st, sa, sb = O.spline_build(x, y, bc)
             st2, ra2, rb2 = O.spline_build(x, y, bc, rowsplit_levels=3)
             assert st == O.ST_OK and st2 == O.ST_OK

@@ -171,7 +171,7 @@ def test_linear_matches_oracle(dt, trailing):
         assert same(strict.interp_array(qi), ref)
 
 
-@pytest.mark.parametrize("mode", [L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS, L.SEARCH_BUCKET_LUT])
+@pytest.mark.parametrize("mode", [L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS, L.SEARCH_BUCKET_LUT, L.SEARCH_MERGE])
 @pytest.mark.parametrize("kind", ["uniform", "random", "exp"])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_linear_every_search_mode_gives_the_same_bits(mode, kind, dt):
@@ -286,7 +286,7 @@ def test_bilinear_error_axis_precedence():
         assert same(buf, ref)
 
 
-@pytest.mark.parametrize("mode", [L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS, L.SEARCH_BUCKET_LUT])
+@pytest.mark.parametrize("mode", [L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS, L.SEARCH_BUCKET_LUT, L.SEARCH_MERGE])
 def test_bilinear_every_search_mode(mode):
     rng = np.random.default_rng(9)
     gx, gy = np.linspace(0, 1, 2048).astype(np.float32), np.cumsum(rng.uniform(0.5, 1.5, 777)).astype(np.float32)
@@ -324,6 +324,25 @@ def test_bilinear_binned_matches_oracle(dt, trailing, band_rows):
         qx, qy = make_queries(rng, gx, nq, dt, False), make_queries(rng, gy, nq, dt, False)
         st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, False)
         assert same(strict.interp_array(qx, qy), ref)
+
+
+@pytest.mark.parametrize("dt,n", [(np.float32, 8000), (np.float64, 1000), (np.int64, 3000), (np.float32, 20000)],
+                         ids=["f32-n8000", "f64-n1000", "i64-n3000", "f32-n20000-coarse"])
+@pytest.mark.parametrize("mode", [L.SEARCH_BINARY_SMEM, L.SEARCH_BINARY_GLOBAL, L.SEARCH_MERGE])
+def test_bilinear_binned_with_every_staged_search(dt, n, mode):
+    """binning passes x every search strategy: the scatter kernel holds 30 - 47 KB of static shared memory, so an
+    x-grid staged next to it needs the shared-memory opt-in although the dynamic part alone is below 48 KB"""
+    rng = np.random.default_rng(n + mode)
+    m, w, nq = 9, 4, 50_000
+    gx, gy = make_grid(rng, n, dt, "random"), make_grid(rng, m, dt, "random")
+    data = make_data(rng, (n, m, w), dt)
+    ip = Interp2D.new_unchecked(gx, gy, data, Bilinear.new().extrapolate(True))
+    L.check(L.load().ndi_interp2d_set_search_mode(ip._handle(), mode))
+    _force_binning(ip, 64)
+    qx, qy = make_queries(rng, gx, nq, dt, True), make_queries(rng, gy, nq, dt, True)
+    st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, True)
+    assert st == O.ST_OK
+    assert same(ip.interp_array(qx, qy), ref)
 
 
 def test_bilinear_binned_errors_like_the_reference():
@@ -451,7 +470,7 @@ def test_ddiv_selftest_sample():
 
 # ---- i64 (Linear / Bilinear are generic over Num) -----------------------
 @pytest.mark.parametrize("mode", [L.SEARCH_AUTO, L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS,
-                                  L.SEARCH_BUCKET_LUT])
+                                  L.SEARCH_BUCKET_LUT, L.SEARCH_MERGE])
 def test_i64_values_beyond_2_pow_53_and_wrapping(mode):
     """grid / data values that no double represents exactly (the bucket function rounds them, the search must
     not) and products that wrap like a Rust release build"""

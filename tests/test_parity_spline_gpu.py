@@ -167,8 +167,26 @@ def test_spline_build_large_column_count_and_long_columns():
         g = grid(rng, n, dt)
         y = rng.normal(size=(n, w)).astype(dt)
         st, a_ref, b_ref = O.spline_build(g, y, {"kind": "Natural"})
-        interp = build(g, y, "Natural")
+        strat = CubicSpline.new().boundary(BoundaryCondition.Natural).solver("sequential")
+        interp = Interp1DBuilder.new(y).x(g).strategy(strat).build()
         a, b = interp.strategy.coefficients(interp)
         assert same(a, a_ref) and same(b, b_ref)
         # an interpolant reproduces its knots: t = 0 gives exactly y[i]
         assert same(interp.interp_array(g[:-1]), y[:-1])
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64], ids=["f32", "f64"])
+def test_spline_sign_of_zero_follows_the_oracle(dt):
+    """a flat column with FirstDeriv(-0.0) on both sides: k, a and b are zeros whose SIGN the sweeps' hoisted
+    division must keep (IEEE: -0 / b = -0 for b > 0); compared bytewise, not by value"""
+    n, w = 50, 6
+    g = np.arange(n, dtype=dt) * dt(0.5)
+    y = np.zeros((n, w), dt); y[:, 3] = dt(2.5)
+    rows = [RowBoundary.Mixed(SingleBoundary.FirstDeriv(-0.0), SingleBoundary.FirstDeriv(-0.0)) for _ in range(w)]
+    spec = [{"kind": "Mixed", "left": {"kind": "FirstDeriv", "value": -0.0}, "right": {"kind": "FirstDeriv", "value": -0.0}}
+            for _ in range(w)]
+    st, a_ref, b_ref = O.spline_build(g, y, {"kind": "Individual", "rows": spec})
+    assert st == O.ST_OK
+    interp = Interp1DBuilder.new(y).x(g).strategy(CubicSpline.new().boundary(BoundaryCondition.Individual([rows]))).build()
+    a, b = interp.strategy.coefficients(interp)
+    assert a.tobytes() == a_ref.tobytes() and b.tobytes() == b_ref.tobytes()
