@@ -12,7 +12,8 @@ def _header():
     text = open(os.path.join(ROOT, "include", "ndi_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
     protos = {}
-    for ret, name, args in re.findall(r"([\w\s\*]+?)\b(ndi_\w+)\s*\(([^;{}]*?)\)\s*;", text):
+    code = re.sub(r"^\s*#[^\n]*$", " ", text, flags=re.M)          # prototypes only: no preprocessor lines
+    for ret, name, args in re.findall(r"([\w\s\*]+?)\b(ndi_\w+)\s*\(([^;{}]*?)\)\s*;", code):
         args = [a.strip() for a in args.split(",")] if args.strip() not in ("", "void") else []
         protos[name] = (ret.strip(), args)
     consts = {k: v for k, v in re.findall(r"#define\s+(NDI_\w+)\s+(\d+)u?\b", text)}
