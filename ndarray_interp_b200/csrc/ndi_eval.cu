@@ -375,9 +375,9 @@ __device__ __forceinline__ Vec<T, V> cubic_vec(const Vec<T, V>& yl, const Vec<T,
 #pragma unroll
         for (int e = 0; e < V; e += 2) {
             const F2 l{yl.v[e], yl.v[e + 1]}, r{yr.v[e], yr.v[e + 1]}, a{al.v[e], al.v[e + 1]}, b{bl.v[e], bl.v[e + 1]};
-            const F2 lin = add2(mul2(o2, l), mul2(t2, r));
-            const F2 cur = add2(mul2(a, o2), mul2(b, t2));
-            const F2 o = add2(lin, mul2(tt2, cur));
+            const F2 lin = add_halves(mul2(o2, l), mul2(t2, r));       // sums of products: per half (ndi_device.cuh)
+            const F2 cur = add_halves(mul2(a, o2), mul2(b, t2));
+            const F2 o = add_halves(lin, mul2(tt2, cur));
             res.v[e] = o.lo; res.v[e + 1] = o.hi;
         }
         return res;

@@ -10,13 +10,13 @@
 //          row[i] + alpha[i] row[i-s] + gamma[i] row[i+s],   alpha = -(low[i] / mid[i-s]),  gamma = -(up[i] / mid[i+s])
 //      which couples row i to rows i +- 2s only.  After L steps the system has fallen apart into S = 2^L
 //      independent tridiagonal systems (rows j, j+S, j+2S, ... for j < S).  The matrix depends only on x, so
-//      alpha / gamma and the reduced matrix are formed ONCE (rowsplit_factor_kernel); per column only
+//      alpha / gamma and the reduced matrix are formed ONCE (rowsplit_level_kernel, one launch per step); per column only
 //          rhs'[i] = (rhs[i] + alpha[i] rhs[i-s]) + gamma[i] rhs[i+s]
 //      remains, an elementwise pass.  All L passes run on a tile held in shared memory
 //      (rowsplit_reduce_kernel: rows of the tile plus a halo of 2^L - 1 rows on either side, right-hand sides
 //      formed in the same kernel from y), so the matrix R is written once.
-//   2. Thomas on the S interleaved systems: S short division chains for the matrix (one thread each, in the
-//      factor kernel) and S * w chains of n / S rows for the columns (spline_sweep_kernel of ndi_spline.cu
+//   2. Thomas on the S interleaved systems: S short division chains for the matrix (one thread each,
+//      rowsplit_chain_kernel) and S * w chains of n / S rows for the columns (spline_sweep_kernel of ndi_spline.cu
 //      with nsys = S).
 //   3. a, b from k: the same kernel as the reference-order build.
 //
@@ -46,60 +46,78 @@ int rowsplit_levels_for(int64_t rows, int requested, bool force) {
     return lv;
 }
 
-constexpr int kRsFacBlock = 512;
+constexpr int kRsBlock = 256;
 constexpr int kRsChain = 8;              // rows a chain thread loads ahead of its dependent steps
 
+// The matrix side of the reduction runs level by level; a level is elementwise over the rows (row i reads rows
+// i - s, i, i + s of the previous level), so each level is one launch over all rows -- with a single block looping
+// over the levels a 65536-row system spent 0.4 ms here.  blockIdx.y selects the matrix (Individual: nine).
 template <class T>
-__global__ void __launch_bounds__(kRsFacBlock) rowsplit_factor_kernel(const T* __restrict__ x, int n, int periodic, int lk, int rk,
-                                                                     int levels, T* __restrict__ fac, size_t fac_stride) {
-    if (gridDim.x > 1) { lk = ind_kind(blockIdx.x / 3); rk = ind_kind(blockIdx.x % 3); fac += blockIdx.x * fac_stride; }
-    const int len = periodic ? n - 2 : n;
-    const size_t N = (size_t)n;
-    FacRow<T>* rows = reinterpret_cast<FacRow<T>*>(fac);
-    T* k2 = fac + 4 * N;
-    T* coef = fac + 5 * N;
-    T* cur = coef + 2 * (size_t)levels * N;
-    T* nxt = cur + 4 * N;
-    // level 0: the matrix of solve_for_k (:440-451, boundary rows :599-669; periodic: the condensed system :512-518)
-    {
-        T dx0 = (T)0, dx_3 = (T)0;
-        if (periodic) { dx0 = SUB(x[1], x[0]); dx_3 = SUB(x[n - 3], x[n - 4]); }
-        for (int i = threadIdx.x; i < len; i += kRsFacBlock) {
-            T u, m, l;
-            if (periodic) matrix_row_periodic<T>(x, n, i, u, m, l); else matrix_row<T>(x, n, i, lk, rk, false, u, m, l);
-            cur[i] = l; cur[N + i] = m; cur[2 * N + i] = u;
-            if (periodic) cur[3 * N + i] = i == 0 ? -dx0 : (i == len - 1 ? -dx_3 : (T)0);      // rhs2 (:535-538)
-        }
+struct RsFac {
+    T* fac; size_t fac_stride; int n, len, levels, periodic, lk, rk;
+    __device__ __forceinline__ T* base() const { return fac + blockIdx.y * fac_stride; }
+    __device__ __forceinline__ T* set(int which) const { return base() + (5 + 2 * (size_t)levels) * (size_t)n + (size_t)which * 4 * (size_t)n; }
+};
+
+// level 0: the matrix of solve_for_k (:440-451, boundary rows :599-669; periodic: the condensed system :512-518)
+template <class T>
+__global__ void __launch_bounds__(kRsBlock) rowsplit_matrix_kernel(const T* __restrict__ x, const RsFac<T> f) {
+    const int i = blockIdx.x * kRsBlock + threadIdx.x;
+    if (i >= f.len) return;
+    const size_t N = (size_t)f.n;
+    const int n = f.n;
+    int lk = f.lk, rk = f.rk;
+    if (gridDim.y > 1) { lk = ind_kind(blockIdx.y / 3); rk = ind_kind(blockIdx.y % 3); }
+    T* cur = f.set(0);
+    T u, m, l;
+    if (f.periodic) matrix_row_periodic<T>(x, n, i, u, m, l); else matrix_row<T>(x, n, i, lk, rk, false, u, m, l);
+    cur[i] = l; cur[N + i] = m; cur[2 * N + i] = u;
+    if (f.periodic) {                                                 // rhs2 (:535-538)
+        const T dx0 = SUB(x[1], x[0]), dx_3 = SUB(x[n - 3], x[n - 4]);
+        cur[3 * N + i] = i == 0 ? -dx0 : (i == f.len - 1 ? -dx_3 : (T)0);
     }
-    for (int lv = 0, s = 1; lv < levels; ++lv, s <<= 1) {
-        __syncthreads();
-        const T *low = cur, *mid = cur + N, *up = cur + 2 * N, *r2 = cur + 3 * N;
-        T* cf = coef + 2 * (size_t)lv * N;
-        for (int i = threadIdx.x; i < len; i += kRsFacBlock) {
-            const bool hm = i - s >= 0, hp = i + s <= len - 1;
-            const T alpha = hm ? -DIV(low[i], mid[i - s]) : (T)0;
-            const T gamma = hp ? -DIV(up[i], mid[i + s]) : (T)0;
-            cf[2 * (size_t)i] = alpha; cf[2 * (size_t)i + 1] = gamma;
-            nxt[i] = hm ? MUL(alpha, low[i - s]) : (T)0;
-            nxt[2 * N + i] = hp ? MUL(gamma, up[i + s]) : (T)0;
-            T m = mid[i];
-            if (hm) m = ADD(m, MUL(alpha, up[i - s]));
-            if (hp) m = ADD(m, MUL(gamma, low[i + s]));
-            nxt[N + i] = m;
-            if (periodic) {
-                T v = r2[i];
-                if (hm) v = ADD(v, MUL(alpha, r2[i - s]));
-                if (hp) v = ADD(v, MUL(gamma, r2[i + s]));
-                nxt[3 * N + i] = v;
-            }
-        }
-        T* t = cur; cur = nxt; nxt = t;
+}
+
+// one reduction level with stride s = 2^lv: set (lv & 1) -> set ((lv + 1) & 1), and {alpha, gamma} of the level
+template <class T>
+__global__ void __launch_bounds__(kRsBlock) rowsplit_level_kernel(const RsFac<T> f, int lv) {
+    const int i = blockIdx.x * kRsBlock + threadIdx.x;
+    if (i >= f.len) return;
+    const size_t N = (size_t)f.n;
+    const int s = 1 << lv, len = f.len;
+    const T* cur = f.set(lv & 1);
+    T* nxt = f.set((lv + 1) & 1);
+    const T *low = cur, *mid = cur + N, *up = cur + 2 * N, *r2 = cur + 3 * N;
+    T* cf = f.base() + 5 * N + 2 * (size_t)lv * N;
+    const bool hm = i - s >= 0, hp = i + s <= len - 1;
+    const T alpha = hm ? -DIV(low[i], mid[i - s]) : (T)0;
+    const T gamma = hp ? -DIV(up[i], mid[i + s]) : (T)0;
+    cf[2 * (size_t)i] = alpha; cf[2 * (size_t)i + 1] = gamma;
+    nxt[i] = hm ? MUL(alpha, low[i - s]) : (T)0;
+    nxt[2 * N + i] = hp ? MUL(gamma, up[i + s]) : (T)0;
+    T m = mid[i];
+    if (hm) m = ADD(m, MUL(alpha, up[i - s]));
+    if (hp) m = ADD(m, MUL(gamma, low[i + s]));
+    nxt[N + i] = m;
+    if (f.periodic) {
+        T v = r2[i];
+        if (hm) v = ADD(v, MUL(alpha, r2[i - s]));
+        if (hp) v = ADD(v, MUL(gamma, r2[i + s]));
+        nxt[3 * N + i] = v;
     }
-    __syncthreads();
-    // Thomas elimination (:690-692) of the S interleaved systems, one thread each; rows of a system are S apart
-    const int S = 1 << levels;
-    const int j = threadIdx.x;
+}
+
+// Thomas elimination (:690-692) of the S = 2^levels interleaved systems, one thread each; rows of a system are S
+// apart.  Periodic: the shared second solution k2 as well (forward :698, back substitution :704-720).
+template <class T>
+__global__ void __launch_bounds__(64) rowsplit_chain_kernel(const RsFac<T> f) {
+    const int S = 1 << f.levels, len = f.len, periodic = f.periodic;
+    const int j = blockIdx.x * 64 + threadIdx.x;
     if (j >= S || j >= len) return;
+    const size_t N = (size_t)f.n;
+    FacRow<T>* rows = reinterpret_cast<FacRow<T>*>(f.base());
+    T* k2 = f.base() + 4 * N;
+    const T* cur = f.set(f.levels & 1);
     const T *low = cur, *mid = cur + N, *up = cur + 2 * N, *r2 = cur + 3 * N;
     const int m_rows = (len - j + S - 1) / S;
     T m_prev = mid[j], u_prev = up[j], r_prev = periodic ? r2[j] : (T)0;
@@ -119,12 +137,12 @@ __global__ void __launch_bounds__(kRsFacBlock) rowsplit_factor_kernel(const T* _
                 const T wgt = DIV(lo[q], m_prev);
                 const T mm = SUB(mi[q], MUL(wgt, u_prev));
                 rows[i] = FacRow<T>{uu[q], mm, wgt, Hoisted<T>::rcp(mm)};
-                if (periodic) { r_prev = SUB(rr[q], MUL(wgt, r_prev)); k2[i] = r_prev; }   // forward sweep of rhs2 (:698)
+                if (periodic) { r_prev = SUB(rr[q], MUL(wgt, r_prev)); k2[i] = r_prev; }
                 m_prev = mm; u_prev = uu[q];
             }
         }
     }
-    if (periodic) {                                                   // back substitution of rhs2 (:704-720)
+    if (periodic) {
         T kr = DIV(r_prev, m_prev);
         k2[j + (m_rows - 1) * S] = kr;
         for (int t = m_rows - 2; t >= 0; --t) {
@@ -249,7 +267,16 @@ cudaError_t launch_rowsplit_front(const T* x, int64_t n, const T* data, int64_t 
     if (bc_kind == BC_NATURAL) l = r = Side<T>{SB_NATURAL, (T)0};
     if (bc_kind == BC_CLAMPED) l = r = Side<T>{SB_CLAMPED, (T)0};
     const Side<T> ls = specialize(l), rs = specialize(r);
-    rowsplit_factor_kernel<T><<<individual ? 9 : 1, kRsFacBlock, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, levels, fac, fac_stride);
+    const int len = periodic ? (int)n - 2 : (int)n;
+    const RsFac<T> f{fac, fac_stride, (int)n, len, levels, periodic, ls.kind, rs.kind};
+    const dim3 rows_grid((unsigned)((len + kRsBlock - 1) / kRsBlock), individual ? 9 : 1);
+    rowsplit_matrix_kernel<T><<<rows_grid, kRsBlock, 0, st>>>(x, f);
+    count_launch();
+    for (int lv = 0; lv < levels; ++lv) {
+        rowsplit_level_kernel<T><<<rows_grid, kRsBlock, 0, st>>>(f, lv);
+        count_launch();
+    }
+    rowsplit_chain_kernel<T><<<dim3((unsigned)(((1 << levels) + 63) / 64), individual ? 9 : 1), 64, 0, st>>>(f);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

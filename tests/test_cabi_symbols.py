@@ -60,3 +60,27 @@ def test_fails_loudly_without_a_gpu():
     from ndarray_interp_b200.interp1d import Interp1D
     with pytest.raises(_lib.NdiLibraryError, match="no CPU fallback"):
         Interp1D.builder(np.array([1.0, 2.0, 3.0])).build()
+
+
+def test_packed_f32x2_products_are_not_contracted_into_fma():
+    """ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (one rounding where the reference rounds twice; found
+    by the GPU parity tests).  The kernels therefore add products per half with scalar adds (csrc/ndi_device.cuh).
+    Here, without a GPU: in the built library every packed FMA of the thin-row kernels is one of the two explicit
+    fmas of the exact division (as many FFMA2 as FMUL2 in lerp / bilerp, none at all in the cubic form)."""
+    import shutil
+    so = os.path.join(ROOT, "ndarray_interp_b200", "libndi_b200.so")
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+
+    def counts(kernel):
+        sass = subprocess.check_output([tool, "-sass", "-fun", kernel, so], text=True, stderr=subprocess.DEVNULL)
+        return {op: len(re.findall(r"\b" + op + r"\b", sass)) for op in ("FFMA2", "FMUL2", "FADD2")}
+    lin = counts("_ZN3ndi22interp1d_linear_kernelIfLi4ELi4EEEvNS_5Eval1IT_EE")
+    pair = counts("_ZN3ndi27interp1d_linear_pair_kernelIfLi4EEEvNS_5Eval1IT_EE")
+    bil = counts("_ZN3ndi24interp2d_bilinear_kernelIfLi4ELi8ELb1EEEvNS_5Eval2IT_EE")
+    cub = counts("_ZN3ndi21interp1d_cubic_kernelIfLi4ELi8EEEvNS_5Eval1IT_EE")
+    for c in (lin, pair, bil):
+        assert c["FMUL2"] > 0 and c["FFMA2"] == c["FMUL2"], c      # per pair of columns: q0 = a r, m dq | two fmas of div_by
+        assert c["FADD2"] * 2 <= c["FMUL2"], c                      # only the subtractions are packed adds
+    assert cub["FMUL2"] > 0 and cub["FFMA2"] == 0 and cub["FADD2"] == 0, cub
