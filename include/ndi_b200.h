@@ -235,6 +235,30 @@ ndi_status ndi_interp2d_bilinear(const ndi_interp2d* h, const void* qx, const vo
 ndi_status ndi_interp2d_bilinear_dev(const ndi_interp2d* h, const void* qx_dev, const void* qy_dev, int64_t nq,
                                      int32_t extrapolate, void* out_dev, uint64_t* err_word_dev, void* stream);
 
+/* ---- one interpolator on several devices of one process ------------------------------------------- */
+/* SURVEY.md section 8(b) `ndi_replicate`: the handle's tables (grid, data, spline coefficients, search aids) are
+ * peer-copied to every listed device of this process (the handle's own device may be in the list and is then used
+ * as it is).  A group call takes HOST pointers like the single-device entry point it replaces -- the batch loops of
+ * interp1d/mod.rs:272-343 and interp2d/mod.rs:215-307 -- cuts the batch into contiguous blocks of queries, one per
+ * device, and evaluates the blocks concurrently (one worker thread, two streams and one set of pinned staging
+ * buffers per device; no collective).  Error semantics are those of the single-device call for the WHOLE batch:
+ * *first_bad is the first failing query in row-major order whichever block holds it, and rows at and after it stay
+ * untouched in every block (a query-only pre-pass runs on all blocks before any row is written).  Batches below
+ * 32768 queries stay on the first device.  Build the spline BEFORE replicating.  The handle must outlive the group. */
+typedef struct ndi_interp1d_group ndi_interp1d_group;
+typedef struct ndi_interp2d_group ndi_interp2d_group;
+ndi_status ndi_interp1d_replicate(const ndi_interp1d* h, const int32_t* devices, int32_t ndev, ndi_interp1d_group** out);
+ndi_status ndi_interp1d_group_destroy(ndi_interp1d_group* g);
+ndi_status ndi_interp1d_group_size(const ndi_interp1d_group* g, int32_t* ndev);
+ndi_status ndi_interp1d_group_linear(ndi_interp1d_group* g, const void* q, int64_t nq, int32_t extrapolate, void* out,
+                                     int64_t* first_bad);
+ndi_status ndi_interp1d_group_cubic(ndi_interp1d_group* g, const void* q, int64_t nq, int32_t extrap_mode, void* out,
+                                    int64_t* first_bad);
+ndi_status ndi_interp2d_replicate(const ndi_interp2d* h, const int32_t* devices, int32_t ndev, ndi_interp2d_group** out);
+ndi_status ndi_interp2d_group_destroy(ndi_interp2d_group* g);
+ndi_status ndi_interp2d_group_bilinear(ndi_interp2d_group* g, const void* qx, const void* qy, int64_t nq,
+                                       int32_t extrapolate, void* out, int64_t* first_bad, int32_t* bad_axis);
+
 /* ---- self-test ------------------------------------------------------------------------------ */
 /* The Linear / Bilinear kernels form the reciprocal of a query's divisor once and finish every
  * quotient with two fused multiply-adds (csrc/ndi_device.cuh: rcp_refined, div_by) instead of a full

@@ -69,6 +69,14 @@ SIGNATURES = {
     "ndi_interp2d_set_binning": (_i32, [_vp, _i32, _i32]),
     "ndi_interp2d_bilinear": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _pi64, _pi32]),
     "ndi_interp2d_bilinear_dev": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "ndi_interp1d_replicate": (_i32, [_vp, _pi32, _i32, C.POINTER(_vp)]),
+    "ndi_interp1d_group_destroy": (_i32, [_vp]),
+    "ndi_interp1d_group_size": (_i32, [_vp, _pi32]),
+    "ndi_interp1d_group_linear": (_i32, [_vp, _vp, _i64, _i32, _vp, _pi64]),
+    "ndi_interp1d_group_cubic": (_i32, [_vp, _vp, _i64, _i32, _vp, _pi64]),
+    "ndi_interp2d_replicate": (_i32, [_vp, _pi32, _i32, C.POINTER(_vp)]),
+    "ndi_interp2d_group_destroy": (_i32, [_vp]),
+    "ndi_interp2d_group_bilinear": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _pi64, _pi32]),
 }
 
 _lib = None

@@ -16,6 +16,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <thread>
 #include <unordered_map>
 #include <cstdarg>
@@ -732,6 +733,12 @@ struct HostEval {
     const void* q[2]; int64_t nq; void* out;
     // launch(q0_dev, q1_dev, nq, out_dev, err_dev, stream) evaluates a contiguous range of queries
     // validate(q0_dev, q1_dev, nq, err_dev, stream) is the K7 pre-pass over all queries
+    // A batch fanned out over several devices (ndi_*_group_*) runs the pipeline in two phases per shard, on the
+    // shard's worker thread, because the reference stops at the first failing query of the WHOLE batch:
+    //   phase 1  queries up, pre-pass: *err_word = first failing query of this shard
+    //   phase 2  evaluate the first `nvalid` rows only (the caller knows the batch-wide first failure by now)
+    int phase = 0;            // 0: everything in one call
+    int64_t nvalid = 0;       // phase 2
 };
 
 template <class Launch, class Validate>
@@ -742,7 +749,7 @@ ndi_status run_host_eval(const HostEval& he, Launch&& launch, Validate&& validat
     ndi_status st; Workspace* ws = workspace(he.device, &st); if (!ws) return st;
     const size_t qbytes = (size_t)he.nq * he.es;
     const size_t row = (size_t)he.w * he.es;
-    if ((size_t)he.nq * row <= kTinyBytes && qbytes <= kTinyQueryBytes) {
+    if (he.phase == 0 && (size_t)he.nq * row <= kTinyBytes && qbytes <= kTinyQueryBytes) {
         // scalar / tiny-batch latency path (interp_scalar, interp, interp_into: interp1d/mod.rs:108-175): the
         // pinned workspace is mapped into the device's address space, so the kernel reads the queries from
         // it and writes the rows into it over PCIe; publish_kernel hands over the error word and raises the
@@ -773,7 +780,7 @@ ndi_status run_host_eval(const HostEval& he, Launch&& launch, Validate&& validat
         memcpy(he.out, ws->h_pin + 64, (size_t)nvalid * row);
         return NDI_OK;
     }
-    for (int c = 0; c < he.ncoord; ++c) {
+    for (int c = 0; c < he.ncoord && he.phase != 2; ++c) {    // phase 2: this thread uploaded them in phase 1
         if ((st = grow(&ws->d_q[c], &ws->d_q_cap[c], qbytes)) != NDI_OK) return st;
         CK(cudaMemcpyAsync(ws->d_q[c], he.q[c], qbytes, cudaMemcpyHostToDevice, ws->s[0]));
     }
@@ -782,7 +789,7 @@ ndi_status run_host_eval(const HostEval& he, Launch&& launch, Validate&& validat
     unsigned long long* d_err = ws->d_err;
     const size_t total = (size_t)he.nq * row;
 
-    if (total <= kSmallBytes) {
+    if (he.phase == 0 && total <= kSmallBytes) {
         // latency path: fused launch, one synchronisation
         if ((st = grow(&ws->d_out[0], &ws->d_out_cap[0], total)) != NDI_OK) return st;
         CK(cudaMemsetAsync(d_err, 0xff, sizeof(uint64_t), ws->s[0]));
@@ -798,13 +805,19 @@ ndi_status run_host_eval(const HostEval& he, Launch&& launch, Validate&& validat
     }
 
     // K7 pre-pass: where would the reference stop?
-    CK(cudaMemsetAsync(d_err, 0xff, sizeof(uint64_t), ws->s[0]));
-    if ((st = validate(dq0, dq1, he.nq, d_err, ws->s[0])) != NDI_OK) return st;
-    CK(cudaMemcpyAsync(ws->h_pin, d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws->s[0]));
-    CK(cudaStreamSynchronize(ws->s[0]));
-    memcpy(err_word, ws->h_pin, sizeof(uint64_t));
     int64_t nvalid = he.nq;
-    if (*err_word != NDI_ERR_WORD_NONE) nvalid = (int64_t)(he.ncoord > 1 ? *err_word >> 1 : *err_word);
+    if (he.phase != 2) {
+        CK(cudaMemsetAsync(d_err, 0xff, sizeof(uint64_t), ws->s[0]));
+        if ((st = validate(dq0, dq1, he.nq, d_err, ws->s[0])) != NDI_OK) return st;
+        CK(cudaMemcpyAsync(ws->h_pin, d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws->s[0]));
+        CK(cudaStreamSynchronize(ws->s[0]));
+        memcpy(err_word, ws->h_pin, sizeof(uint64_t));
+        if (*err_word != NDI_ERR_WORD_NONE) nvalid = (int64_t)(he.ncoord > 1 ? *err_word >> 1 : *err_word);
+        if (he.phase == 1) return NDI_OK;
+    } else {
+        nvalid = he.nvalid < he.nq ? he.nvalid : he.nq;
+        if (nvalid <= 0) return NDI_OK;
+    }
 
     static const bool stage_pageable = [] { const char* e = getenv("NDI_STAGE_PAGEABLE"); return !(e && *e == '0'); }();
     if (stage_pageable && row <= kStageBytes / 32 && is_pageable_host(he.out)) {
@@ -886,13 +899,11 @@ ndi_status ndi_interp1d_linear_dev(const ndi_interp1d* h, const void* q_dev, int
     });
 }
 
-ndi_status ndi_interp1d_linear(const ndi_interp1d* h, const void* q, int64_t nq, int32_t extrapolate, void* out,
-                               int64_t* first_bad) {
-    if (first_bad) *first_bad = -1;
-    ndi_status st = check_eval_args(h, q, nq, out); if (st != NDI_OK) return st;
-    HostEval he{h->device, elem_size(h->dtype), 1, h->w, {q, nullptr}, nq, out};
-    uint64_t word;
-    st = dispatch(h->dtype, [&](auto tag) -> ndi_status {
+// one shard of a host batch (phase 0: the whole call; 1 / 2: see HostEval)
+static ndi_status linear_host(const ndi_interp1d* h, const void* q, int64_t nq, int32_t extrapolate, void* out,
+                              uint64_t* word, int phase, int64_t nvalid) {
+    HostEval he{h->device, elem_size(h->dtype), 1, h->w, {q, nullptr}, nq, out, phase, nvalid};
+    return dispatch(h->dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
         SearchCfg sc = make_search(h->meta(), h->search_mode, nq, 0);
         return run_host_eval(he,
@@ -904,15 +915,23 @@ ndi_status ndi_interp1d_linear(const ndi_interp1d* h, const void* q, int64_t nq,
                 CK(launch_validate_queries<T>((const T*)h->x, h->n, nullptr, 0, (const T*)q0, nullptr, cnt,
                                               extrapolate ? CHECK_NOT_NAN : CHECK_IN_RANGE, err, s));
                 return NDI_OK;
-            }, &word);
+            }, word);
     });
-    if (st != NDI_OK) return st;
-    if (word != NDI_ERR_WORD_NONE) {
-        if (first_bad) *first_bad = (int64_t)word;
-        return extrapolate ? fail(NDI_NAN_QUERY, "not implemented: failed to convert NaN to usize (query %lld)", (long long)word)
-                           : fail(NDI_OUT_OF_BOUNDS, "query %lld is not in range", (long long)word);
-    }
-    return NDI_OK;
+}
+static ndi_status eval1d_status(uint64_t word, int nan_only, int64_t* first_bad) {
+    if (word == NDI_ERR_WORD_NONE) return NDI_OK;
+    if (first_bad) *first_bad = (int64_t)word;
+    return nan_only ? fail(NDI_NAN_QUERY, "not implemented: failed to convert NaN to usize (query %lld)", (long long)word)
+                    : fail(NDI_OUT_OF_BOUNDS, "query %lld is not in range", (long long)word);
+}
+
+ndi_status ndi_interp1d_linear(const ndi_interp1d* h, const void* q, int64_t nq, int32_t extrapolate, void* out,
+                               int64_t* first_bad) {
+    if (first_bad) *first_bad = -1;
+    ndi_status st = check_eval_args(h, q, nq, out); if (st != NDI_OK) return st;
+    uint64_t word;
+    if ((st = linear_host(h, q, nq, extrapolate, out, &word, 0, 0)) != NDI_OK) return st;
+    return eval1d_status(word, extrapolate, first_bad);
 }
 
 // ---- cubic spline ---------------------------------------------------------------------------------------------
@@ -1063,15 +1082,10 @@ ndi_status ndi_interp1d_cubic_dev(const ndi_interp1d* h, const void* q_dev, int6
     });
 }
 
-ndi_status ndi_interp1d_cubic(const ndi_interp1d* h, const void* q, int64_t nq, int32_t extrap_mode, void* out,
-                              int64_t* first_bad) {
-    if (first_bad) *first_bad = -1;
-    ndi_status st = check_eval_args(h, q, nq, out); if (st != NDI_OK) return st;
-    if (!h->a) return fail(NDI_NO_SPLINE, "no spline coefficients: call ndi_interp1d_spline_build first");
-    if (extrap_mode < 0 || extrap_mode > 2) return fail(NDI_INVALID_ARGUMENT, "bad extrapolation mode %d", extrap_mode);
-    HostEval he{h->device, elem_size(h->dtype), 1, h->w, {q, nullptr}, nq, out};
-    uint64_t word;
-    st = dispatch_float(h->dtype, [&](auto tag) -> ndi_status {
+static ndi_status cubic_host(const ndi_interp1d* h, const void* q, int64_t nq, int32_t extrap_mode, void* out,
+                             uint64_t* word, int phase, int64_t nvalid) {
+    HostEval he{h->device, elem_size(h->dtype), 1, h->w, {q, nullptr}, nq, out, phase, nvalid};
+    return dispatch_float(h->dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
         SearchCfg sc = make_search(h->meta(), h->search_mode, nq, 0);
         const int check = extrap_mode == NDI_EXTRAP_NO ? CHECK_IN_RANGE : (extrap_mode == NDI_EXTRAP_YES ? CHECK_NOT_NAN : CHECK_FINITE_IF_OUTSIDE);
@@ -1084,15 +1098,19 @@ ndi_status ndi_interp1d_cubic(const ndi_interp1d* h, const void* q, int64_t nq, 
             [&](const void* q0, const void*, int64_t cnt, unsigned long long* err, cudaStream_t s) -> ndi_status {
                 CK(launch_validate_queries<T>((const T*)h->x, h->n, nullptr, 0, (const T*)q0, nullptr, cnt, check, err, s));
                 return NDI_OK;
-            }, &word);
+            }, word);
     });
-    if (st != NDI_OK) return st;
-    if (word != NDI_ERR_WORD_NONE) {
-        if (first_bad) *first_bad = (int64_t)word;
-        return extrap_mode ? fail(NDI_NAN_QUERY, "not implemented: failed to convert NaN to usize (query %lld)", (long long)word)
-                           : fail(NDI_OUT_OF_BOUNDS, "query %lld is not in range", (long long)word);
-    }
-    return NDI_OK;
+}
+
+ndi_status ndi_interp1d_cubic(const ndi_interp1d* h, const void* q, int64_t nq, int32_t extrap_mode, void* out,
+                              int64_t* first_bad) {
+    if (first_bad) *first_bad = -1;
+    ndi_status st = check_eval_args(h, q, nq, out); if (st != NDI_OK) return st;
+    if (!h->a) return fail(NDI_NO_SPLINE, "no spline coefficients: call ndi_interp1d_spline_build first");
+    if (extrap_mode < 0 || extrap_mode > 2) return fail(NDI_INVALID_ARGUMENT, "bad extrapolation mode %d", extrap_mode);
+    uint64_t word;
+    if ((st = cubic_host(h, q, nq, extrap_mode, out, &word, 0, 0)) != NDI_OK) return st;
+    return eval1d_status(word, extrap_mode, first_bad);
 }
 
 // ---- Interp2D ---------------------------------------------------------------------------------------------------
@@ -1294,15 +1312,10 @@ ndi_status ndi_interp2d_bilinear_dev(const ndi_interp2d* h, const void* qx_dev, 
     });
 }
 
-ndi_status ndi_interp2d_bilinear(const ndi_interp2d* h, const void* qx, const void* qy, int64_t nq, int32_t extrapolate,
-                                 void* out, int64_t* first_bad, int32_t* bad_axis) {
-    if (first_bad) *first_bad = -1;
-    if (bad_axis) *bad_axis = -1;
-    ndi_status st = check_eval_args(h, qx, nq, out); if (st != NDI_OK) return st;
-    if (nq > 0 && !qy) return fail(NDI_INVALID_ARGUMENT, "null pointer");
-    HostEval he{h->device, elem_size(h->dtype), 2, h->w, {qx, qy}, nq, out};
-    uint64_t word;
-    st = dispatch(h->dtype, [&](auto tag) -> ndi_status {
+static ndi_status bilinear_host(const ndi_interp2d* h, const void* qx, const void* qy, int64_t nq, int32_t extrapolate,
+                                void* out, uint64_t* word, int phase, int64_t nvalid) {
+    HostEval he{h->device, elem_size(h->dtype), 2, h->w, {qx, qy}, nq, out, phase, nvalid};
+    return dispatch(h->dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
         SearchCfg sx, sy; search2(h, sizeof(T), nq, &sx, &sy);
         return run_host_eval(he,
@@ -1313,18 +1326,244 @@ ndi_status ndi_interp2d_bilinear(const ndi_interp2d* h, const void* qx, const vo
                 CK(launch_validate_queries<T>((const T*)h->x, h->n, (const T*)h->y, h->m, (const T*)q0, (const T*)q1, cnt,
                                               extrapolate ? CHECK_NOT_NAN : CHECK_IN_RANGE, err, s));
                 return NDI_OK;
-            }, &word);
+            }, word);
+    });
+}
+static ndi_status eval2d_status(uint64_t word, int nan_only, int64_t* first_bad, int32_t* bad_axis) {
+    if (word == NDI_ERR_WORD_NONE) return NDI_OK;
+    const int64_t idx = (int64_t)(word >> 1);
+    const int axis = (int)(word & 1);
+    if (first_bad) *first_bad = idx;
+    if (bad_axis) *bad_axis = axis;
+    return nan_only ? fail(NDI_NAN_QUERY, "not implemented: failed to convert NaN to usize (query %lld)", (long long)idx)
+                    : fail(NDI_OUT_OF_BOUNDS, "%s of query %lld is not in range", axis ? "y" : "x", (long long)idx);
+}
+
+ndi_status ndi_interp2d_bilinear(const ndi_interp2d* h, const void* qx, const void* qy, int64_t nq, int32_t extrapolate,
+                                 void* out, int64_t* first_bad, int32_t* bad_axis) {
+    if (first_bad) *first_bad = -1;
+    if (bad_axis) *bad_axis = -1;
+    ndi_status st = check_eval_args(h, qx, nq, out); if (st != NDI_OK) return st;
+    if (nq > 0 && !qy) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    uint64_t word;
+    if ((st = bilinear_host(h, qx, qy, nq, extrapolate, out, &word, 0, 0)) != NDI_OK) return st;
+    return eval2d_status(word, extrapolate, first_bad, bad_axis);
+}
+
+}  // extern "C"
+
+// ---- one interpolator on several devices of this process (ndi_replicate) ------------------
+// The tables are peer-copied to every device (ndi_interp*_clone_to_device); a host call cuts the batch into
+// contiguous blocks of queries, one per device (keeps sorted batches sorted and makes the
+// first failing query a minimum over the blocks), and runs the blocks concurrently, each on its own worker thread
+// with its own per-thread workspace (streams, pinned staging).  No collective, no data shared between the blocks.
+namespace {
+
+class Workers {                                   // one persistent thread per device of a group
+public:
+    explicit Workers(int n) : slots_(n) {
+        for (int i = 0; i < n; ++i) threads_.emplace_back([this, i] { run(i); });
+    }
+    ~Workers() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    // fn(member) on every worker; returns the first non-OK status (and its message, into this thread's slot)
+    ndi_status all(const std::function<ndi_status(int)>& fn) {
+        std::unique_lock<std::mutex> lk(mu_);
+        fn_ = &fn; pending_ = (int)slots_.size(); ++epoch_;
+        for (auto& s : slots_) { s.todo = true; s.st = NDI_OK; }
+        cv_.notify_all();
+        done_.wait(lk, [&] { return pending_ == 0; });
+        for (auto& s : slots_)
+            if (s.st != NDI_OK) { snprintf(g_err, sizeof(g_err), "%s", s.msg); return s.st; }
+        return NDI_OK;
+    }
+private:
+    struct Slot { bool todo = false; ndi_status st = NDI_OK; char msg[512] = ""; };
+    void run(int i) {
+        for (;;) {
+            const std::function<ndi_status(int)>* fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || slots_[i].todo; });
+                if (stop_) return;
+                slots_[i].todo = false;
+                fn = fn_;
+            }
+            const ndi_status st = (*fn)(i);
+            std::lock_guard<std::mutex> lk(mu_);
+            slots_[i].st = st;
+            if (st != NDI_OK) snprintf(slots_[i].msg, sizeof(slots_[i].msg), "%s", g_err);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::mutex mu_; std::condition_variable cv_, done_;
+    std::vector<Slot> slots_; std::vector<std::thread> threads_;
+    const std::function<ndi_status(int)>* fn_ = nullptr; int pending_ = 0; unsigned long long epoch_ = 0; bool stop_ = false;
+};
+
+// block k of nq queries cut into nd contiguous blocks whose starts are multiples of 32
+inline int64_t block_start(int64_t nq, int nd, int k) { return k >= nd ? nq : ((nq * k / nd) & ~31ll); }
+
+// the two-phase fan-out shared by the three strategies.  word_of(k, lo, cnt, phase, nvalid, &word) runs one block.
+// Returns the batch-wide error word (1-D: query index; 2-D: 2 * index + axis) through *word.
+template <class Block>
+ndi_status fan_out(Workers& pool, int nd, int64_t nq, int ncoord, Block&& block, uint64_t* word) {
+    std::vector<uint64_t> words((size_t)nd, NDI_ERR_WORD_NONE);
+    ndi_status st = pool.all([&](int k) -> ndi_status {
+        const int64_t lo = block_start(nq, nd, k), cnt = block_start(nq, nd, k + 1) - lo;
+        return cnt > 0 ? block(k, lo, cnt, 1, 0, &words[(size_t)k]) : NDI_OK;
     });
     if (st != NDI_OK) return st;
-    if (word != NDI_ERR_WORD_NONE) {
-        const int64_t idx = (int64_t)(word >> 1);
-        const int axis = (int)(word & 1);
-        if (first_bad) *first_bad = idx;
-        if (bad_axis) *bad_axis = axis;
-        return extrapolate ? fail(NDI_NAN_QUERY, "not implemented: failed to convert NaN to usize (query %lld)", (long long)idx)
-                           : fail(NDI_OUT_OF_BOUNDS, "%s of query %lld is not in range", axis ? "y" : "x", (long long)idx);
+    *word = NDI_ERR_WORD_NONE;
+    int64_t first = nq;                                          // rows before `first` are evaluated
+    for (int k = 0; k < nd; ++k) {
+        if (words[(size_t)k] == NDI_ERR_WORD_NONE) continue;
+        const int64_t lo = block_start(nq, nd, k);
+        const uint64_t w = ncoord > 1 ? words[(size_t)k] + 2 * (uint64_t)lo : words[(size_t)k] + (uint64_t)lo;
+        if (w < *word) *word = w;
     }
+    if (*word != NDI_ERR_WORD_NONE) first = (int64_t)(ncoord > 1 ? *word >> 1 : *word);
+    return pool.all([&](int k) -> ndi_status {
+        const int64_t lo = block_start(nq, nd, k), cnt = block_start(nq, nd, k + 1) - lo;
+        const int64_t nvalid = first - lo < cnt ? first - lo : cnt;
+        uint64_t unused;
+        return (cnt > 0 && nvalid > 0) ? block(k, lo, cnt, 2, nvalid, &unused) : NDI_OK;
+    });
+}
+
+constexpr int64_t kGroupMinQueries = 1 << 15;       // below this a batch stays on the first device (latency path)
+
+}  // namespace
+
+struct ndi_interp1d_group {
+    std::vector<ndi_interp1d*> members; std::vector<char> owned;
+    Workers pool;
+    explicit ndi_interp1d_group(int n) : pool(n) {}
+};
+struct ndi_interp2d_group {
+    std::vector<ndi_interp2d*> members; std::vector<char> owned;
+    Workers pool;
+    explicit ndi_interp2d_group(int n) : pool(n) {}
+};
+
+extern "C" {
+
+ndi_status ndi_interp1d_replicate(const ndi_interp1d* h, const int32_t* devices, int32_t ndev, ndi_interp1d_group** out) {
+    if (!h || !devices || !out || ndev < 1 || ndev > 64) return fail(NDI_INVALID_ARGUMENT, "need a handle and 1..64 devices");
+    *out = nullptr;
+    int count = 0; CK(cudaGetDeviceCount(&count));
+    for (int k = 0; k < ndev; ++k) {
+        if (devices[k] < 0 || devices[k] >= count) return fail(NDI_INVALID_ARGUMENT, "device %d does not exist (%d visible)", devices[k], count);
+        for (int j = 0; j < k; ++j) if (devices[j] == devices[k]) return fail(NDI_INVALID_ARGUMENT, "device %d listed twice", devices[k]);
+    }
+    ndi_interp1d_group* g = new ndi_interp1d_group(ndev);
+    for (int k = 0; k < ndev; ++k) {
+        if (devices[k] == h->device) { g->members.push_back(const_cast<ndi_interp1d*>(h)); g->owned.push_back(0); continue; }
+        ndi_interp1d* c = nullptr;
+        const ndi_status st = ndi_interp1d_clone_to_device(h, devices[k], &c);
+        if (st != NDI_OK) { ndi_interp1d_group_destroy(g); return st; }
+        g->members.push_back(c); g->owned.push_back(1);
+    }
+    *out = g;
     return NDI_OK;
+}
+ndi_status ndi_interp1d_group_destroy(ndi_interp1d_group* g) {
+    if (!g) return NDI_OK;
+    for (size_t k = 0; k < g->members.size(); ++k) if (g->owned[k]) ndi_interp1d_destroy(g->members[k]);
+    delete g;
+    return NDI_OK;
+}
+ndi_status ndi_interp1d_group_size(const ndi_interp1d_group* g, int32_t* ndev) {
+    if (!g || !ndev) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    *ndev = (int32_t)g->members.size();
+    return NDI_OK;
+}
+
+ndi_status ndi_interp1d_group_linear(ndi_interp1d_group* g, const void* q, int64_t nq, int32_t extrapolate, void* out,
+                                     int64_t* first_bad) {
+    if (first_bad) *first_bad = -1;
+    if (!g || g->members.empty()) return fail(NDI_INVALID_ARGUMENT, "null group");
+    const ndi_interp1d* h0 = g->members[0];
+    const int nd = (int)g->members.size();
+    if (nd == 1 || nq < kGroupMinQueries) return ndi_interp1d_linear(h0, q, nq, extrapolate, out, first_bad);
+    ndi_status st = check_eval_args(h0, q, nq, out); if (st != NDI_OK) return st;
+    const size_t es = elem_size(h0->dtype), row = (size_t)h0->w * es;
+    uint64_t word;
+    st = fan_out(g->pool, nd, nq, 1, [&](int k, int64_t lo, int64_t cnt, int phase, int64_t nvalid, uint64_t* w) {
+        return linear_host(g->members[(size_t)k], (const unsigned char*)q + (size_t)lo * es, cnt, extrapolate,
+                           (unsigned char*)out + (size_t)lo * row, w, phase, nvalid);
+    }, &word);
+    if (st != NDI_OK) return st;
+    return eval1d_status(word, extrapolate, first_bad);
+}
+
+ndi_status ndi_interp1d_group_cubic(ndi_interp1d_group* g, const void* q, int64_t nq, int32_t extrap_mode, void* out,
+                                    int64_t* first_bad) {
+    if (first_bad) *first_bad = -1;
+    if (!g || g->members.empty()) return fail(NDI_INVALID_ARGUMENT, "null group");
+    const ndi_interp1d* h0 = g->members[0];
+    const int nd = (int)g->members.size();
+    if (nd == 1 || nq < kGroupMinQueries) return ndi_interp1d_cubic(h0, q, nq, extrap_mode, out, first_bad);
+    ndi_status st = check_eval_args(h0, q, nq, out); if (st != NDI_OK) return st;
+    if (!h0->a) return fail(NDI_NO_SPLINE, "no spline coefficients: build the spline before ndi_interp1d_replicate");
+    if (extrap_mode < 0 || extrap_mode > 2) return fail(NDI_INVALID_ARGUMENT, "bad extrapolation mode %d", extrap_mode);
+    const size_t es = elem_size(h0->dtype), row = (size_t)h0->w * es;
+    uint64_t word;
+    st = fan_out(g->pool, nd, nq, 1, [&](int k, int64_t lo, int64_t cnt, int phase, int64_t nvalid, uint64_t* w) {
+        return cubic_host(g->members[(size_t)k], (const unsigned char*)q + (size_t)lo * es, cnt, extrap_mode,
+                          (unsigned char*)out + (size_t)lo * row, w, phase, nvalid);
+    }, &word);
+    if (st != NDI_OK) return st;
+    return eval1d_status(word, extrap_mode, first_bad);
+}
+
+ndi_status ndi_interp2d_replicate(const ndi_interp2d* h, const int32_t* devices, int32_t ndev, ndi_interp2d_group** out) {
+    if (!h || !devices || !out || ndev < 1 || ndev > 64) return fail(NDI_INVALID_ARGUMENT, "need a handle and 1..64 devices");
+    *out = nullptr;
+    int count = 0; CK(cudaGetDeviceCount(&count));
+    for (int k = 0; k < ndev; ++k) {
+        if (devices[k] < 0 || devices[k] >= count) return fail(NDI_INVALID_ARGUMENT, "device %d does not exist (%d visible)", devices[k], count);
+        for (int j = 0; j < k; ++j) if (devices[j] == devices[k]) return fail(NDI_INVALID_ARGUMENT, "device %d listed twice", devices[k]);
+    }
+    ndi_interp2d_group* g = new ndi_interp2d_group(ndev);
+    for (int k = 0; k < ndev; ++k) {
+        if (devices[k] == h->device) { g->members.push_back(const_cast<ndi_interp2d*>(h)); g->owned.push_back(0); continue; }
+        ndi_interp2d* c = nullptr;
+        const ndi_status st = ndi_interp2d_clone_to_device(h, devices[k], &c);
+        if (st != NDI_OK) { ndi_interp2d_group_destroy(g); return st; }
+        g->members.push_back(c); g->owned.push_back(1);
+    }
+    *out = g;
+    return NDI_OK;
+}
+ndi_status ndi_interp2d_group_destroy(ndi_interp2d_group* g) {
+    if (!g) return NDI_OK;
+    for (size_t k = 0; k < g->members.size(); ++k) if (g->owned[k]) ndi_interp2d_destroy(g->members[k]);
+    delete g;
+    return NDI_OK;
+}
+
+ndi_status ndi_interp2d_group_bilinear(ndi_interp2d_group* g, const void* qx, const void* qy, int64_t nq, int32_t extrapolate,
+                                       void* out, int64_t* first_bad, int32_t* bad_axis) {
+    if (first_bad) *first_bad = -1;
+    if (bad_axis) *bad_axis = -1;
+    if (!g || g->members.empty()) return fail(NDI_INVALID_ARGUMENT, "null group");
+    const ndi_interp2d* h0 = g->members[0];
+    const int nd = (int)g->members.size();
+    if (nd == 1 || nq < kGroupMinQueries) return ndi_interp2d_bilinear(h0, qx, qy, nq, extrapolate, out, first_bad, bad_axis);
+    ndi_status st = check_eval_args(h0, qx, nq, out); if (st != NDI_OK) return st;
+    if (!qy) return fail(NDI_INVALID_ARGUMENT, "null pointer");
+    const size_t es = elem_size(h0->dtype), row = (size_t)h0->w * es;
+    uint64_t word;
+    st = fan_out(g->pool, nd, nq, 2, [&](int k, int64_t lo, int64_t cnt, int phase, int64_t nvalid, uint64_t* w) {
+        return bilinear_host(g->members[(size_t)k], (const unsigned char*)qx + (size_t)lo * es, (const unsigned char*)qy + (size_t)lo * es,
+                             cnt, extrapolate, (unsigned char*)out + (size_t)lo * row, w, phase, nvalid);
+    }, &word);
+    if (st != NDI_OK) return st;
+    return eval2d_status(word, extrapolate, first_bad, bad_axis);
 }
 
 }  // extern "C"

@@ -68,10 +68,10 @@ class Linear(Interp1DStrategyBuilder, Interp1DStrategy):
         return self
 
     def interp_batch_into(self, interpolator, xs_flat, out_rows):
-        h = interpolator._handle()
         bad = C.c_int64(-1)
-        st = L.check(L.load().ndi_interp1d_linear(h, L.ptr(xs_flat), xs_flat.size, int(self._extrapolate),
-                                                  L.ptr(out_rows), C.byref(bad)))
+        fn, h = ((L.load().ndi_interp1d_group_linear, interpolator._group.ptr) if getattr(interpolator, "_group", None)
+                 else (L.load().ndi_interp1d_linear, interpolator._handle()))
+        st = L.check(fn(h, L.ptr(xs_flat), xs_flat.size, int(self._extrapolate), L.ptr(out_rows), C.byref(bad)))
         _raise_eval(st, xs_flat, bad.value, "x")
 
     def interp_into(self, interpolator, target, x):        # linear.rs:73-98
@@ -274,10 +274,10 @@ class CubicSplineStrategy(Interp1DStrategy):
         return a, b
 
     def interp_batch_into(self, interpolator, xs_flat, out_rows):
-        h = interpolator._handle()
         bad = C.c_int64(-1)
-        st = L.check(L.load().ndi_interp1d_cubic(h, L.ptr(xs_flat), xs_flat.size, self._mode, L.ptr(out_rows),
-                                                 C.byref(bad)))
+        fn, h = ((L.load().ndi_interp1d_group_cubic, interpolator._group.ptr) if getattr(interpolator, "_group", None)
+                 else (L.load().ndi_interp1d_cubic, interpolator._handle()))
+        st = L.check(fn(h, L.ptr(xs_flat), xs_flat.size, self._mode, L.ptr(out_rows), C.byref(bad)))
         _raise_eval(st, xs_flat, bad.value, "x")
 
     def interp_into(self, interpolator, target, x):        # cubic_spline.rs:791-830
@@ -340,6 +340,23 @@ class _Handle1D:
             pass
 
 
+class _Group:
+    """owner of a ndi_interp{1,2}d_group (the handle it was made from is kept alive)"""
+
+    def __init__(self, create, destroy, handle, devices, keep):
+        dev = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        self.ptr, self._destroy, self._keep = C.c_void_p(), destroy, keep
+        L.check(create(handle, dev, len(devices), C.byref(self.ptr)))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._destroy(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
 class Interp1D:
     """One dimensional interpolator (interp1d/mod.rs:38-51)"""
 
@@ -361,6 +378,17 @@ class Interp1D:
         x, data = _prepare(x, data)
         h = _Handle1D(x, data, L.ASSUME_VALID) if _is_builtin(strategy) else None
         return cls(x, data, strategy, h)
+
+    def replicate(self, devices):
+        """NOT in the reference: fan this interpolator out over several GPUs of this process (include/ndi_b200.h:
+        ndi_interp1d_replicate).  Returns an interpolator with the same methods whose batch calls cut the queries into
+        contiguous blocks, one per device, evaluated concurrently; errors and untouched rows as on one device."""
+        if not _is_builtin(self.strategy):
+            raise TypeError("only the built-in strategies run on the device")
+        other = Interp1D.__new__(Interp1D)
+        other.x, other.data, other.strategy, other._h = self.x, self.data, self.strategy, self._h
+        other._group = _Group(L.load().ndi_interp1d_replicate, L.load().ndi_interp1d_group_destroy, self._handle(), devices, self)
+        return other
 
     def _handle(self):
         if self._h is None:              # user strategy calling back into the accessors
@@ -407,7 +435,9 @@ class Interp1D:
         q = np.ascontiguousarray(xs, dtype=self.data.dtype).reshape(-1)
         rows_shape = (q.size,) + self.data.shape[1:]
         direct = isinstance(buffer, np.ndarray) and buffer.flags.c_contiguous and buffer.dtype == self.data.dtype
-        rows = buffer.reshape(rows_shape) if direct else np.zeros(rows_shape, dtype=self.data.dtype)
+        # a strided / foreign-dtype buffer is evaluated through a dense copy that STARTS from the caller's values:
+        # rows at and after a failing query must come back untouched (interp1d/mod.rs:321, :336-340)
+        rows = buffer.reshape(rows_shape) if direct else np.array(buffer, dtype=self.data.dtype).reshape(rows_shape)
         try:
             self.strategy.interp_batch_into(self, q, rows)
         finally:

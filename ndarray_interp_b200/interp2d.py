@@ -55,9 +55,10 @@ class Bilinear(Interp2DStrategyBuilder, Interp2DStrategy):
 
     def interp_batch_into(self, interpolator, xs_flat, ys_flat, out_rows):
         bad, axis = C.c_int64(-1), C.c_int32(-1)
-        st = L.check(L.load().ndi_interp2d_bilinear(interpolator._handle(), L.ptr(xs_flat), L.ptr(ys_flat), xs_flat.size,
-                                                    int(self._extrapolate), L.ptr(out_rows), C.byref(bad),
-                                                    C.byref(axis)))
+        fn, h = ((L.load().ndi_interp2d_group_bilinear, interpolator._group.ptr) if getattr(interpolator, "_group", None)
+                 else (L.load().ndi_interp2d_bilinear, interpolator._handle()))
+        st = L.check(fn(h, L.ptr(xs_flat), L.ptr(ys_flat), xs_flat.size, int(self._extrapolate), L.ptr(out_rows),
+                        C.byref(bad), C.byref(axis)))
         if st == L.OUT_OF_BOUNDS:                          # bilinear.rs:71-80: x is checked first
             name, v = ("x", xs_flat[bad.value]) if axis.value == 0 else ("y", ys_flat[bad.value])
             raise InterpolateError.OutOfBounds(f"{name} = {rust_debug(v)} is not in range")
@@ -119,6 +120,17 @@ class Interp2D:
         h = _Handle2D(x, y, data, L.ASSUME_VALID) if isinstance(strategy, Bilinear) else None
         return cls(x, y, data, strategy, h)
 
+    def replicate(self, devices):
+        """NOT in the reference: fan this interpolator out over several GPUs of this process (include/ndi_b200.h:
+        ndi_interp2d_replicate); batch calls cut the queries into contiguous blocks, one per device."""
+        from .interp1d import _Group
+        if not isinstance(self.strategy, Bilinear):
+            raise TypeError("only the built-in strategies run on the device")
+        other = Interp2D.__new__(Interp2D)
+        other.x, other.y, other.data, other.strategy, other._h = self.x, self.y, self.data, self.strategy, self._h
+        other._group = _Group(L.load().ndi_interp2d_replicate, L.load().ndi_interp2d_group_destroy, self._handle(), devices, self)
+        return other
+
     def _handle(self):
         if self._h is None:
             self._h = _Handle2D(self.x, self.y, self.data, L.ASSUME_VALID)
@@ -167,7 +179,9 @@ class Interp2D:
         qy = np.ascontiguousarray(ys, dtype=dt).reshape(-1)
         rows_shape = (qx.size,) + self.data.shape[2:]
         direct = isinstance(buffer, np.ndarray) and buffer.flags.c_contiguous and buffer.dtype == dt
-        rows = buffer.reshape(rows_shape) if direct else np.zeros(rows_shape, dtype=dt)
+        # dense stand-in for a strided buffer starts from the caller's values: rows at and after a failing query
+        # come back untouched (interp2d/mod.rs:255-307)
+        rows = buffer.reshape(rows_shape) if direct else np.array(buffer, dtype=dt).reshape(rows_shape)
         try:
             self.strategy.interp_batch_into(self, qx, qy, rows)
         finally:
