@@ -83,3 +83,71 @@ def test_first_error_across_two_ranks(bad_positions):
         assert got == want                      # the reference's answer: first failing query overall
         assert bcast == list(map(float, range(8)))
         assert gathered == list(map(float, range(6)))
+
+
+def _data_worker(rank, world, port, results):
+    """the multi-GPU data flow of bench.py on CPU, the oracle standing in for the kernels: spline built on a column
+    shard, coefficients all-gathered, queries evaluated per contiguous block, blocks gathered"""
+    from oracle import oracle_py as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)                       # same tables on every rank ("replicated")
+        n, w, nq = 200, 8, 1001
+        x = np.cumsum(rng.uniform(0.5, 1.5, n))
+        y = rng.normal(size=(n, w))
+        q = np.sort(rng.uniform(x[0], x[-1], nq))
+        q[700] = x[-1] + 1.0                                    # a failing query in the second block
+        c_lo, c_hi = P.column_shards(w, world)[rank]
+        st, a_sh, b_sh = O.spline_build(x, np.ascontiguousarray(y[:, c_lo:c_hi]), {"kind": "Natural"})
+        assert st == 0
+        ga = [torch.empty((n - 1, c_hi - c_lo), dtype=torch.float64) for _ in range(world)]
+        gb = [torch.empty((n - 1, c_hi - c_lo), dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(ga, torch.from_numpy(a_sh))
+        dist.all_gather(gb, torch.from_numpy(b_sh))
+        a_full, b_full = torch.cat(ga, dim=1).contiguous().numpy(), torch.cat(gb, dim=1).contiguous().numpy()
+        lo, hi = P.shard_bounds(nq, world, rank)
+        st, out, bad = O.interp1d_cubic(x, y, a_full, b_full, q[lo:hi], 0, out=np.full((hi - lo, w), -1.0))
+        local = bad if st != 0 else P.ERR_NONE
+        first = P.first_error(local, lo)
+        outs = [torch.empty((P.shard_bounds(nq, world, r)[1] - P.shard_bounds(nq, world, r)[0], w), dtype=torch.float64)
+                for r in range(world)]
+        dist.all_gather(outs, torch.from_numpy(out)) if len({o.shape for o in outs}) == 1 else None
+        results[rank] = (a_full, b_full, first, out, (lo, hi))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_build_allgather_and_sharded_evaluation_equal_the_single_process_result():
+    from oracle import oracle_py as O
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_data_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    rng = np.random.default_rng(11)
+    n, w, nq = 200, 8, 1001
+    x = np.cumsum(rng.uniform(0.5, 1.5, n))
+    y = rng.normal(size=(n, w))
+    q = np.sort(rng.uniform(x[0], x[-1], nq))
+    q[700] = x[-1] + 1.0
+    st, a, b = O.spline_build(x, y, {"kind": "Natural"})
+    st, ref, bad = O.interp1d_cubic(x, y, a, b, q, 0, out=np.full((nq, w), -1.0))
+    assert bad == 700
+    for r in range(world):
+        a_full, b_full, first, out, (lo, hi) = results[r]
+        assert np.array_equal(a_full, a) and np.array_equal(b_full, b)      # columns are independent: shards == full build
+        assert first == (700, 0)                                            # the batch-wide first failure on every rank
+        upto = min(hi, 700) - lo                                            # rows before it equal the single-process rows
+        assert np.array_equal(out[:max(upto, 0)], ref[lo:lo + max(upto, 0)])
+
+
+def test_bench_workload_sharding_strong_and_weak():
+    import bench
+    assert bench.queries_per_gpu(bench.WORKLOADS["c5a"], 8) == 1 << 25 and bench.queries_per_gpu(bench.WORKLOADS["c5a"], 1) == 1 << 28
+    assert bench.queries_per_gpu(bench.WORKLOADS["c2"], 8) == 1 << 20
+    c2 = bench.WORKLOADS["c2"]
+    assert bench.algorithmic_bytes(c2, 1 << 20) == 8 * (1 << 20) + 8 * 1024 * (1 << 20) + 8 * (4096 + 4096 * 1024 + 2 * 4095 * 1024)
+    assert abs(bench.algorithmic_bytes(c2, 1 << 20) / 1e9 - 8.699) < 0.001       # SURVEY.md section 8(d)
+    assert abs(bench.algorithmic_bytes(bench.WORKLOADS["c3"], 1 << 24) / 1e9 - 1.145) < 0.001
+    assert abs(bench.algorithmic_bytes(bench.WORKLOADS["c4"], 1 << 24) / 1e9 - 0.805) < 0.001
