@@ -186,7 +186,8 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
  *                         column (csrc/ndi_rowsplit.cu); different rounding, inside north_star's 1e-12 (f64) /
  *                         1e-5 (f32) bars, bit-identical to the oracle's specification of the same scheme.
  *                         levels == 0 lets the library choose; a request is capped so every system keeps two rows.
- *   NDI_BUILD_AUTO        row-split for systems of 2048 rows or more, the reference's order below (default).
+ *   NDI_BUILD_AUTO        row-split for systems of 2048 rows or more with fewer than 8192 columns (where the serial
+ *                         chains bind), the reference's order otherwise (default).
  * ndi_interp1d_build_info reports the depth the current coefficients were built with (0: reference order). */
 #define NDI_BUILD_AUTO 0
 #define NDI_BUILD_SEQUENTIAL 1

@@ -954,7 +954,10 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
     const int mode = env_mode >= 0 ? (int)env_mode : h->build_mode;
     const int want_levels = env_levels >= 0 ? (int)env_levels : h->build_levels;
     int levels = 0;
-    if (h->n >= 4 && mode != NDI_BUILD_SEQUENTIAL)
+    // AUTO: the row-split build where the serial chains bind -- long systems of few columns.  With many columns the
+    // reference-order sweeps already fill the machine and the extra passes of the reduction cost more than the
+    // shorter chains save (4096 x 16384 f32: 1.21 ms against 1.34 ms; profiles/r02/spline_build.jsonl).
+    if (h->n >= 4 && mode != NDI_BUILD_SEQUENTIAL && (mode == NDI_BUILD_ROWSPLIT || h->w < kRowsplitAutoMaxColumns))
         levels = rowsplit_levels_for(bc_kind == NDI_BC_PERIODIC ? h->n - 2 : h->n, want_levels, mode == NDI_BUILD_ROWSPLIT);
     return dispatch_float(h->dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
@@ -979,8 +982,9 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
         // the call, and the previous pair must stay valid until this build has succeeded.
         cudaStream_t bs = ws->s[0];
         constexpr size_t kBuildKeepBytes = (size_t)1 << 30;
+        void* big_scratch = nullptr;
         auto cleanup = [&](bool keep) {
-            if (ws->d_build_cap > kBuildKeepBytes) { cudaFree(ws->d_build); ws->d_build = nullptr; ws->d_build_cap = 0; }
+            if (big_scratch) { cudaFreeAsync(big_scratch, bs); big_scratch = nullptr; }
             if (!keep) { cudaFreeAsync(a, bs); cudaFreeAsync(b, bs); }
             cudaGetLastError();
         };
@@ -990,9 +994,17 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
             const size_t scratch_bytes = up(spline_scratch_elems<T>(h->n, h->w, bc_kind, levels) * sizeof(T));
             const size_t col_i = up((size_t)h->w * sizeof(int32_t)), col_t = up((size_t)h->w * sizeof(T));
             const size_t need = scratch_bytes + (bc_kind == NDI_BC_INDIVIDUAL ? 3 * col_i + 2 * col_t : 0);
-            ndi_status gs = grow(&ws->d_build, &ws->d_build_cap, need);
-            if (gs != NDI_OK) return gs;
-            unsigned char* base = static_cast<unsigned char*>(ws->d_build);
+            unsigned char* base;
+            if (need > kBuildKeepBytes) {
+                // beyond what a thread keeps for itself: from the stream-ordered pool, which caches the block between
+                // builds (cudaMalloc + cudaFree of 2 GB per call cost 20 ms of a 33 ms build, profiles/r02)
+                CK(cudaMallocAsync(&big_scratch, need, bs));
+                base = static_cast<unsigned char*>(big_scratch);
+            } else {
+                ndi_status gs = grow(&ws->d_build, &ws->d_build_cap, need);
+                if (gs != NDI_OK) return gs;
+                base = static_cast<unsigned char*>(ws->d_build);
+            }
             scratch = reinterpret_cast<T*>(base);
             CK(cudaMallocAsync((void**)&a, coef_bytes, bs));
             CK(cudaMallocAsync((void**)&b, coef_bytes, bs));
@@ -1277,7 +1289,7 @@ ndi_status bilinear_on_device(const ndi_interp2d* h, const SearchCfg& sx, const 
     BandPlan bp;
     if (!want_binning(h, nq, sizeof(T), &bp)) {
         CK(launch_interp2d_bilinear<T>((const T*)h->x, h->n, sx, (const T*)h->y, h->m, sy, (const T*)h->data, h->w, qx, qy, nq,
-                                       extrapolate, out, err, nullptr, h->fast_tables, s));
+                                       extrapolate, out, err, nullptr, h->fast_tables, nullptr, s));
         return NDI_OK;
     }
     void* scratch = nullptr;
@@ -1285,10 +1297,11 @@ ndi_status bilinear_on_device(const ndi_interp2d* h, const SearchCfg& sx, const 
     // the scatter kernel keeps its chunk in static shared memory: leave room when staging the grid
     const SearchCfg sbin = make_search(h->meta_x(), h->search_mode, nq, 48 * 1024);
     const unsigned* perm = nullptr; const T *bx = nullptr, *by = nullptr;
-    cudaError_t e = launch_bin_queries<T>((const T*)h->x, h->n, sbin, qx, qy, nq, bp, scratch, &perm, &bx, &by, s);
+    unsigned long long* next_task = nullptr;
+    cudaError_t e = launch_bin_queries<T>((const T*)h->x, h->n, sbin, qx, qy, nq, bp, scratch, &perm, &bx, &by, &next_task, s);
     if (e == cudaSuccess)
         e = launch_interp2d_bilinear<T>((const T*)h->x, h->n, sx, (const T*)h->y, h->m, sy, (const T*)h->data, h->w, bx, by, nq,
-                                        extrapolate, out, err, perm, h->fast_tables, s);
+                                        extrapolate, out, err, perm, h->fast_tables, next_task, s);
     cudaFreeAsync(scratch, s);
     if (e != cudaSuccess) return cuda_fail(e, "binned bilinear launch");
     return NDI_OK;

@@ -191,19 +191,20 @@ BandPlan plan_bands(int64_t n, int64_t m, int64_t w, size_t elem, size_t band_by
 
 size_t bin_scratch_bytes(int64_t nq, size_t elem) {
     const size_t q = ((size_t)nq + 63) & ~(size_t)63;
-    return 2 * kMaxBands * sizeof(unsigned) + q * (sizeof(unsigned) + 2 * elem);
+    return (2 * kMaxBands + 4) * sizeof(unsigned) + q * (sizeof(unsigned) + 2 * elem);     // counters, task counter, perm, qx, qy
 }
 
 template <class T>
 cudaError_t launch_bin_queries(const T* gx, int64_t n, SearchCfg scx, const T* qx, const T* qy, int64_t nq,
                                BandPlan bp, void* scratch, const unsigned** perm, const T** bqx, const T** bqy,
-                               cudaStream_t st) {
+                               unsigned long long** next_task, cudaStream_t st) {
     const size_t q = ((size_t)nq + 63) & ~(size_t)63;
     unsigned* counters = static_cast<unsigned*>(scratch);
-    unsigned* perm_w = counters + 2 * kMaxBands;
+    unsigned* perm_w = counters + 2 * kMaxBands + 4;             // 16 bytes in between: the evaluation's tile counter
     T* bx = reinterpret_cast<T*>(perm_w + q);
     T* by = bx + q;
-    cudaError_t e = cudaMemsetAsync(counters, 0, 2 * kMaxBands * sizeof(unsigned), st);
+    *next_task = reinterpret_cast<unsigned long long*>(counters + 2 * kMaxBands);
+    cudaError_t e = cudaMemsetAsync(counters, 0, (2 * kMaxBands + 4) * sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
     BinArgs<T> p{gx, (int)n, scx, qx, qy, (long long)nq, bp.band_shift, bp.nbands,
                  ((long long)nq + kBinChunk - 1) / kBinChunk, counters, counters + kMaxBands, perm_w, bx, by};
@@ -230,7 +231,8 @@ cudaError_t launch_bin_queries(const T* gx, int64_t n, SearchCfg scx, const T* q
 
 #define NDI_INST_BIN(T)                                                                                              \
     template cudaError_t launch_bin_queries<T>(const T*, int64_t, SearchCfg, const T*, const T*, int64_t, BandPlan, \
-                                               void*, const unsigned**, const T**, const T**, cudaStream_t);
+                                               void*, const unsigned**, const T**, const T**, unsigned long long**, \
+                                               cudaStream_t);
 NDI_INST_BIN(float)
 NDI_INST_BIN(double)
 NDI_INST_BIN(int32_t)

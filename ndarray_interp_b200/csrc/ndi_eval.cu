@@ -52,6 +52,7 @@ struct Eval2 {                       // bilinear
     long long ntasks; int nslices;
     const unsigned* perm;            // binned batch (ndi_bin.cu): output row of query i is perm[i]
     int fast_tables;
+    unsigned long long* next_task;   // binned batch: tiles are handed out in order through this counter (zeroed by the binning pass)
 };
 
 // first-error report for a binned batch: lanes are not in query order, every failing lane reports
@@ -545,12 +546,26 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (LPQ <= 2 ? 5 : 4) : 
     const long long rowx = (long long)p.m * p.w;      // elements between x-rows
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     const long long task0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    // A binned batch is only as good as the L2 residency of the band it walks through.  With tiles assigned by a
+    // fixed stride the warps of a long launch drift apart (a 2^28-query batch runs for 20 ms; SMs a few per cent
+    // slower end up many bands behind, the set of bands in flight outgrows L2 and every gather goes to DRAM:
+    // 74 GB read for a 2.1 GB table, profiles/r02).  So the tiles of a binned batch are handed out IN ORDER through
+    // an atomic counter: whatever the speed of an SM, all warps work within a few thousand tiles of each other.
+    const bool dyn = PERM && LPQ < 32 && kTilesBilinear == 1 && p.next_task != nullptr;
+    auto fetch_task = [&]() -> long long {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(p.next_task, 1ull);
+        return (long long)__shfl_sync(0xffffffffu, t, 0);
+    };
+    const long long first = dyn ? fetch_task() : task0;
     T x_ahead = gx0, y_ahead = gy0; unsigned row_ahead = 0;   // thin rows: the next tile's query, loaded one tile ahead
-    if (LPQ < 32 && kTilesBilinear == 1 && task0 < p.ntasks && task0 * 32 + lane < p.nq) {
-        x_ahead = ld_query(p.qx + task0 * 32 + lane); y_ahead = ld_query(p.qy + task0 * 32 + lane);
-        if constexpr (PERM) row_ahead = __ldcs(p.perm + task0 * 32 + lane);
+    if (LPQ < 32 && kTilesBilinear == 1 && first < p.ntasks && first * 32 + lane < p.nq) {
+        x_ahead = ld_query(p.qx + first * 32 + lane); y_ahead = ld_query(p.qy + first * 32 + lane);
+        if constexpr (PERM) row_ahead = __ldcs(p.perm + first * 32 + lane);
     }
-    for (long long task = task0; task < p.ntasks; task += nwarps) {
+    long long next = 0;
+    for (long long task = first; task < p.ntasks; task = next) {
+        next = dyn ? fetch_task() : task + nwarps;
         if constexpr (LPQ < 32) {
             constexpr int TPW = kTilesBilinear, QPR = 32 / LPQ;
             const long long qbase0 = task * (32 * TPW);
@@ -560,8 +575,8 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (LPQ <= 2 ? 5 : 4) : 
             unsigned orow[TPW];                                                        // output row (PERM only)
             if constexpr (TPW == 1) {
                 x[0] = x_ahead; y[0] = y_ahead; orow[0] = row_ahead;
-                const long long qn = (task + nwarps) * 32 + lane;
-                const bool more = task + nwarps < p.ntasks && qn < p.nq;
+                const long long qn = next * 32 + lane;
+                const bool more = next < p.ntasks && qn < p.nq;
                 x_ahead = more ? ld_query(p.qx + qn) : gx0;
                 y_ahead = more ? ld_query(p.qy + qn) : gy0;
                 if constexpr (PERM) row_ahead = more ? __ldcs(p.perm + qn) : 0u;
@@ -630,7 +645,7 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (LPQ <= 2 ? 5 : 4) : 
                         const T* c0 = p.data + cs + col;
                         const Vec<T, V> z11 = ld_table<T, V>(c0), z12 = ld_table<T, V>(c0 + p.w);
                         const Vec<T, V> z21 = ld_table<T, V>(c0 + rowx), z22 = ld_table<T, V>(c0 + rowx + p.w);
-                        st_stream<T, V>(p.out + srow * p.w + col, bilerp_vec<T, V>(z11, z12, z21, z22, ssx, sbx, ssy, sby));
+                        st_stream<T, V>(p.out + srow * p.w + col, bilerp_vec<T, V, (LPQ > 2)>(z11, z12, z21, z22, ssx, sbx, ssy, sby));
                     }
                 }
                 if constexpr (kBcast) __syncwarp();                    // the slab is rewritten by the next tile
@@ -878,10 +893,10 @@ template <class T>
 cudaError_t launch_interp2d_bilinear(const T* gx, int64_t n, SearchCfg scx, const T* gy, int64_t m, SearchCfg scy,
                                      const T* data, int64_t w, const T* qx, const T* qy, int64_t nq, int extrapolate,
                                      T* out, unsigned long long* err, const unsigned* perm, int fast_tables,
-                                     cudaStream_t st) {
+                                     unsigned long long* next_task, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
     Shape sh = pick_shape(w, nq, pick_vec<T>(w, {data, out}), kTilesBilinear);
-    Eval2<T> p{gx, (int)n, scx, gy, (int)m, scy, data, (long long)w, qx, qy, (long long)nq, extrapolate, out, err, sh.ntasks, sh.nslices, perm, fast_tables};
+    Eval2<T> p{gx, (int)n, scx, gy, (int)m, scy, data, (long long)w, qx, qy, (long long)nq, extrapolate, out, err, sh.ntasks, sh.nslices, perm, fast_tables, perm ? next_task : nullptr};
     size_t smem = stage_bytes(scx, sizeof(T)) + stage_bytes(scy, sizeof(T));
     if (perm) { NDI_VEC_SWITCH(bilinear_binned, T, sh, p, smem, st) }
     NDI_VEC_SWITCH(bilinear_direct, T, sh, p, smem, st)
@@ -920,7 +935,8 @@ cudaError_t launch_validate_queries(const T* gx, int64_t n, const T* gy, int64_t
     template cudaError_t launch_pack_pairs<T>(const T*, int64_t, int64_t, T*, cudaStream_t);                           \
     template cudaError_t launch_interp2d_bilinear<T>(const T*, int64_t, SearchCfg, const T*, int64_t, SearchCfg,       \
                                                      const T*, int64_t, const T*, const T*, int64_t, int, T*,          \
-                                                     unsigned long long*, const unsigned*, int, cudaStream_t);         \
+                                                     unsigned long long*, const unsigned*, int, unsigned long long*,   \
+                                                     cudaStream_t);                                                    \
     template cudaError_t launch_lower_index<T>(const T*, int64_t, SearchCfg, const T*, int64_t, int64_t*,              \
                                                unsigned long long*, cudaStream_t);                                     \
     template cudaError_t launch_validate_queries<T>(const T*, int64_t, const T*, int64_t, const T*, const T*, int64_t, \

@@ -67,7 +67,7 @@ template <class T>
 cudaError_t launch_interp2d_bilinear(const T* gx, int64_t n, SearchCfg scx, const T* gy, int64_t m, SearchCfg scy,
                                      const T* data, int64_t w, const T* qx, const T* qy, int64_t nq, int extrapolate,
                                      T* out, unsigned long long* err, const unsigned* perm, int fast_tables,
-                                     cudaStream_t st);
+                                     unsigned long long* next_task, cudaStream_t st);
 
 // ---- locality binning of 2-D query batches (ndi_bin.cu) --------------------------------------
 // The x-axis is cut into nbands bands of 2^band_shift intervals; launch_bin_queries groups the
@@ -81,7 +81,7 @@ size_t bin_scratch_bytes(int64_t nq, size_t elem);
 template <class T>
 cudaError_t launch_bin_queries(const T* gx, int64_t n, SearchCfg scx, const T* qx, const T* qy, int64_t nq,
                                BandPlan bp, void* scratch, const unsigned** perm, const T** bqx, const T** bqy,
-                               cudaStream_t st);
+                               unsigned long long** next_task, cudaStream_t st);
 
 // fast_tables (linear, bilinear; f32 only): 1 when launch_table_fast_div found every table value to
 // be 0 or in [2^-56, 2^30], which lets the kernels divide with a per-query reciprocal (ndi_device.cuh)
@@ -134,6 +134,7 @@ size_t spline_scratch_elems(int64_t n, int64_t w, int bc_kind, int levels);
 // not set, where the reference's order is kept (0); 0 also when the system is too short to split at all
 constexpr int kMaxRowsplitLevels = 6;
 constexpr int64_t kRowsplitAutoRows = 2048;
+constexpr int64_t kRowsplitAutoMaxColumns = 8192;   // AUTO keeps the reference order from this many columns on
 int rowsplit_levels_for(int64_t rows, int requested, bool force);
 
 }  // namespace ndi

@@ -25,6 +25,8 @@
 // (the CPU checker's rowsplit_thomas, see tests/test_rowsplit_gpu.py) and to north_star's 1e-12 (f64) / 1e-5 (f32) bars against the
 // reference-order checker.  Every product and sum is rounded on its own (no FMA),
 // the i-s term before the i+s term, exactly as the specification writes them.
+#include <map>
+
 #include "ndi_spline.cuh"
 
 namespace ndi {
@@ -159,8 +161,9 @@ __global__ void __launch_bounds__(64) rowsplit_chain_kernel(const RsFac<T> f) {
 // halo rows are computed as far as their inputs lie inside the buffer and never leave the block.
 // Non-periodic: R[0 .. n-1] = reduced right-hand sides.  Periodic: R[0 .. n-3] = reduced right-hand sides of the
 // condensed system, R[n-2] = the last condensed equation's right-hand side (:531-532), kept for k_m1.
+constexpr int kRsLoadAhead = 8;          // rows of y a warp requests before it waits for any of them
 template <class T>
-__global__ void __launch_bounds__(256) rowsplit_reduce_kernel(const T* __restrict__ x, int n, const T* __restrict__ y, long long w,
+__global__ void __launch_bounds__(512) rowsplit_reduce_kernel(const T* __restrict__ x, int n, const T* __restrict__ y, long long w,
                                                               int periodic, Side<T> left, Side<T> right, int levels, int rt,
                                                               int col_tiles, const T* __restrict__ fac, size_t fac_stride,
                                                               T* __restrict__ R, unsigned long long* err,
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(256) rowsplit_reduce_kernel(const T* __restric
     T* bufA = reinterpret_cast<T*>(rs_smem);
     T* bufB = bufA + (size_t)(nb + 2) * 32;
     const int slen = periodic ? n - 2 : n;
-    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int ty = blockIdx.x / col_tiles, tx = blockIdx.x - ty * col_tiles;
     const long long c = (long long)tx * 32 + lane;
     const bool colok = c < w;
@@ -190,14 +193,25 @@ __global__ void __launch_bounds__(256) rowsplit_reduce_kernel(const T* __restric
     const T* coef = fac + fo + 5 * (size_t)n;
     const T* ycol = y + (colok ? c : 0);
     auto Y = [&](int row) -> T { return __ldg(ycol + (long long)row * w); };
-    // y rows [i0 - 1, i0 + nb + 1) -> bufB
-    for (int rr = wi; rr < nb + 2; rr += 8) {
-        const int gi = i0 - 1 + rr;
-        bufB[rr * 32 + lane] = (gi >= 0 && gi < n && colok) ? Y(gi) : (T)0;
+    // y rows [i0 - 1, i0 + nb + 1) -> bufB; kRsLoadAhead independent loads in flight per thread (a block that waits
+    // for one row at a time spends its life in DRAM latency: 0.55 ms for the 65536 x 64 build, profiles/r02)
+    for (int r0 = wi; r0 < nb + 2; r0 += nw * kRsLoadAhead) {
+        T v[kRsLoadAhead];
+#pragma unroll
+        for (int k = 0; k < kRsLoadAhead; ++k) {
+            const int rr = r0 + k * nw, gi = i0 - 1 + rr;
+            v[k] = (rr < nb + 2 && gi >= 0 && gi < n && colok) ? Y(gi) : (T)0;
+        }
+#pragma unroll
+        for (int k = 0; k < kRsLoadAhead; ++k) {
+            const int rr = r0 + k * nw;
+            if (rr < nb + 2) bufB[rr * 32 + lane] = v[k];
+        }
     }
     __syncthreads();
     // right-hand sides (:456-471 interior, :599-669 boundary rows, :529-530 periodic first row) -> bufA
-    for (int rr = wi; rr < nb; rr += 8) {
+#pragma unroll 2
+    for (int rr = wi; rr < nb; rr += nw) {
         const int i = i0 + rr;
         T v = (T)0;
         if (i >= 0 && i < slen && colok) {
@@ -224,7 +238,8 @@ __global__ void __launch_bounds__(256) rowsplit_reduce_kernel(const T* __restric
     T *cur = bufA, *nxt = bufB;
     for (int lv = 0, s = 1; lv < levels; ++lv, s <<= 1) {
         const T* cf = coef + 2 * (size_t)lv * (size_t)n;
-        for (int rr = wi; rr < nb; rr += 8) {
+#pragma unroll 4
+        for (int rr = wi; rr < nb; rr += nw) {
             const int i = i0 + rr;
             T v = cur[rr * 32 + lane];
             if (i >= 0 && i < slen) {
@@ -237,7 +252,7 @@ __global__ void __launch_bounds__(256) rowsplit_reduce_kernel(const T* __restric
         __syncthreads();
         T* t = cur; cur = nxt; nxt = t;
     }
-    for (int rr = H + wi; rr < H + rt; rr += 8) {
+    for (int rr = H + wi; rr < H + rt; rr += nw) {
         const int i = i0 + rr;
         if (i < slen && colok) R[(long long)i * w + cout] = cur[rr * 32 + lane];
     }
@@ -247,6 +262,21 @@ __global__ void __launch_bounds__(256) rowsplit_reduce_kernel(const T* __restric
         const T slope_1 = DIV(SUB(Y(n - 1), yn2), dx_1), slope_2 = DIV(SUB(yn2, Y(n - 3)), dx_2);   // :526-527
         R[(long long)(n - 2) * w + cout] = MUL(ADD(MUL(slope_2, dx_1), MUL(slope_1, dx_2)), three);   // :531-532
     }
+}
+
+// second stream of the calling thread on the current device (chains beside the reduction)
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideStream& side_stream() {
+    static thread_local std::map<int, SideStream> per_dev;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SideStream& sd = per_dev[dev];
+    if (!sd.s) {
+        if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) != cudaSuccess) { sd.s = nullptr; cudaGetLastError(); }
+    }
+    return sd;
 }
 
 static int rowsplit_tile_rows(int levels, size_t elem) {
@@ -276,10 +306,17 @@ cudaError_t launch_rowsplit_front(const T* x, int64_t n, const T* data, int64_t 
         rowsplit_level_kernel<T><<<rows_grid, kRsBlock, 0, st>>>(f, lv);
         count_launch();
     }
-    rowsplit_chain_kernel<T><<<dim3((unsigned)(((1 << levels) + 63) / 64), individual ? 9 : 1), 64, 0, st>>>(f);
-    count_launch();
+    // The division chains of the matrix (a few threads, pure latency) and the reduction of the right-hand sides (the
+    // whole machine, bandwidth) need nothing from each other -- both follow the level kernels, the sweeps follow
+    // both -- so the chains run beside the reduction on a second stream of this thread.
+    SideStream& side = side_stream();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    const bool forked = side.s && cudaEventRecord(side.fork, st) == cudaSuccess && cudaStreamWaitEvent(side.s, side.fork, 0) == cudaSuccess;
+    rowsplit_chain_kernel<T><<<dim3((unsigned)(((1 << levels) + 63) / 64), individual ? 9 : 1), 64, 0, forked ? side.s : st>>>(f);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (forked && (e = cudaEventRecord(side.join, side.s)) != cudaSuccess) return e;
     const int rt = rowsplit_tile_rows(levels, sizeof(T));
     const int H = (1 << levels) - 1;
     const size_t smem = 2 * (size_t)(rt + 2 * H + 2) * 32 * sizeof(T);
@@ -289,11 +326,14 @@ cudaError_t launch_rowsplit_front(const T* x, int64_t n, const T* data, int64_t 
     const long long rows_total = periodic ? n - 1 : n;
     const long long col_tiles = (w + 31) / 32, row_tiles = (rows_total + rt - 1) / rt;
     if (col_tiles * row_tiles > 0x7fffffffll) return cudaErrorInvalidConfiguration;
-    rowsplit_reduce_kernel<T><<<(unsigned)(col_tiles * row_tiles), 256, smem, st>>>(
+    // a tile that leaves room for one block per SM only gets sixteen warps to hide its latencies with
+    const int threads = smem > 100 * 1024 ? 512 : 256;
+    rowsplit_reduce_kernel<T><<<(unsigned)(col_tiles * row_tiles), threads, smem, st>>>(
         x, (int)n, data, (long long)w, periodic, l, r, levels, rt, (int)col_tiles, fac, fac_stride, R, err,
         individual ? lk : nullptr, lv, rk, rv, pos);
     count_launch();
-    return cudaGetLastError();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return forked ? cudaStreamWaitEvent(st, side.join, 0) : cudaSuccess;
 }
 
 template cudaError_t launch_rowsplit_front<float>(const float*, int64_t, const float*, int64_t, int, int, const int32_t*,
