@@ -255,7 +255,7 @@ struct GridAids {
     }
 };
 
-static SearchCfg make_search(const GridMeta& gm, int mode, int64_t nq, size_t other_smem, bool stage_for_guess = true) {
+static SearchCfg make_search(const GridMeta& gm, int mode, int64_t nq, size_t other_smem) {
     SearchCfg sc{bisect_top_step(gm.n), 0, 0, 0, 0, nullptr, nullptr, 0, 0.0, 0.0, 0};
     auto use_lut = [&]() { if (gm.lut) { sc.lut = gm.lut; sc.lut_n = gm.lut_n; sc.g0d = gm.g0d; sc.scale = gm.scale; } };
     const size_t bytes = (size_t)gm.n * gm.elem;
@@ -276,16 +276,10 @@ static SearchCfg make_search(const GridMeta& gm, int mode, int64_t nq, size_t ot
     case NDI_SEARCH_MERGE: sc.merge = 1; break;
     default:   // AUTO: O(1) guess on grids where it always hits, else the bucket table;
                // without either (no handle), shared-memory bisection for big batches
-        if (gm.uniform_hint) {
-            // The guess is verified against g[mid], g[mid+1] -- two scattered 4-byte loads per query, each close to
-            // a whole L1TEX wavefront of its own, where the thin-row kernels are bound by exactly that pipe
-            // (profiles/r02: 10.8 wavefronts per query in the binned C5a evaluation).  From shared memory the same
-            // two reads cost bank conflicts only (about a tenth of a wavefront each), so a grid that fits is staged.
-            sc.guess = 1;
-            static const long stage_guess = env_long("NDI_STAGE_GUESS", 1);    // 0: A/B measurement
-            if (stage_for_guess && stage_guess && nq >= 32768) stage(kFullStageBytes);
-            if (sc.smem && sc.coarse_shift != 0) { sc.smem = 0; sc.stage_src = nullptr; sc.stage_n = 0; sc.coarse_shift = 0; }   // whole grid or nothing
-        }
+        // (Measured and dropped, profiles/r02/ab_eval_changes.md: staging an even grid in shared memory so that the
+        // guess's two verification reads come from there -- C5a 17.007 against 17.015 ms, C4 0.5408 / 0.5403: the
+        // 8 - 16 KB grids are L1-resident anyway.)
+        if (gm.uniform_hint) sc.guess = 1;
         else if (gm.lut) use_lut();
         else if (nq >= 32768) stage(kFullStageBytes);
         break;
@@ -1304,7 +1298,7 @@ ndi_status bilinear_on_device(const ndi_interp2d* h, const SearchCfg& sx, const 
     void* scratch = nullptr;
     CK(cudaMallocAsync(&scratch, bin_scratch_bytes(nq, sizeof(T)), s));
     // the scatter kernel keeps its chunk in static shared memory: leave room when staging the grid
-    const SearchCfg sbin = make_search(h->meta_x(), h->search_mode, nq, 48 * 1024, false);   // bands of an even grid are arithmetic: nothing to stage
+    const SearchCfg sbin = make_search(h->meta_x(), h->search_mode, nq, 48 * 1024);
     const unsigned* perm = nullptr; const T *bx = nullptr, *by = nullptr;
     unsigned long long* next_task = nullptr;
     cudaError_t e = launch_bin_queries<T>((const T*)h->x, h->n, sbin, qx, qy, nq, bp, scratch, &perm, &bx, &by, &next_task, s);

@@ -247,9 +247,6 @@ __global__ void __launch_bounds__(kBlock, (sizeof(T) == 4 && LPQ < 32) ? NDI_THI
 // lane's 32-byte load holds exactly the y1 / y2 values of the columns it produces -- already paired up for the
 // two-column arithmetic of lerp_vec.  Twice the table memory, so only built while P stays L2-resident
 // (ndi_api.cu: want_pair_table).  Same arithmetic, same bits.
-#ifndef NDI_PAIR_BATCH
-#define NDI_PAIR_BATCH 1
-#endif
 template <class T> struct alignas(32) Pair32 { T v[32 / sizeof(T)]; };
 template <class T>
 __device__ __forceinline__ Pair32<T> ld_pair(const T* p) {          // one 256-bit load (LDG.E.256), read-only path
@@ -267,11 +264,8 @@ __device__ __forceinline__ void unpair(const Pair32<T>& pr, Vec<T, V>& y1, Vec<T
     }
 }
 
-#ifndef NDI_PAIR_MINBLOCKS
-#define NDI_PAIR_MINBLOCKS 5
-#endif
 template <class T, int LPQ>
-__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? NDI_PAIR_MINBLOCKS : 0) interp1d_linear_pair_kernel(const Eval1<T> p) {
+__global__ void __launch_bounds__(kBlock) interp1d_linear_pair_kernel(const Eval1<T> p) {
     constexpr int V = 16 / (int)sizeof(T), QPR = 32 / LPQ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
@@ -308,34 +302,23 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? NDI_PAIR_MINBLOCKS : 
             recs[threadIdx.x >> 5][lane] = LinRec<T>{dxq, slope, skip ? -1 : idx[0]};
             __syncwarp();
         }
-        // the gathers of NDI_PAIR_BATCH rounds are issued before the first of them is consumed (more bytes in flight
-        // per warp at the price of 8 registers per round; measured in profiles/r02)
-        constexpr int kBatch = NDI_PAIR_BATCH < LPQ ? NDI_PAIR_BATCH : LPQ;
 #pragma unroll
-        for (int r0 = 0; r0 < LPQ; r0 += kBatch) {
-            int is[kBatch]; T dq[kBatch]; Slope<T> sl[kBatch]; Pair32<T> pr[kBatch];
-#pragma unroll
-            for (int k = 0; k < kBatch; ++k) {
-                const int src = (r0 + k) * QPR + qsel;
-                if constexpr (kBcast) {
-                    const LinRec<T> rc = recs[threadIdx.x >> 5][src];
-                    is[k] = rc.is; dq[k] = rc.dq; sl[k] = rc.sl;
-                } else if constexpr (LPQ == 1) {                               // one lane per query: nothing to hand round
-                    is[k] = skip ? -1 : idx[0]; dq[k] = dxq; sl[k] = slope;
-                } else {
-                    is[k] = __shfl_sync(0xffffffffu, skip ? -1 : idx[0], src);
-                    dq[k] = shfl_t(dxq, src);
-                    sl[k] = slope.from_lane(src, dq[k], p.fast_tables != 0);
-                }
-                if (is[k] >= 0 && !one_interval) pr[k] = ld_pair<T>(p.data + (long long)is[k] * pw + 2 * col);
+        for (int r = 0; r < LPQ; ++r) {
+            const int src = r * QPR + qsel;
+            int is; T dq; Slope<T> sl;
+            if constexpr (kBcast) {
+                const LinRec<T> rc = recs[threadIdx.x >> 5][src];
+                is = rc.is; dq = rc.dq; sl = rc.sl;
+            } else if constexpr (LPQ == 1) {                                   // one lane per query: nothing to hand round
+                is = skip ? -1 : idx[0]; dq = dxq; sl = slope;
+            } else {
+                is = __shfl_sync(0xffffffffu, skip ? -1 : idx[0], src);
+                dq = shfl_t(dxq, src);
+                sl = slope.from_lane(src, dq, p.fast_tables != 0);
             }
-#pragma unroll
-            for (int k = 0; k < kBatch; ++k) {
-                const int src = (r0 + k) * QPR + qsel;
-                if (is[k] >= 0) {
-                    if (!one_interval) unpair<T, V>(pr[k], y1, y2);
-                    st_stream<T, V>(p.out + (qbase + src) * p.w + col, lerp_vec<T, V>(y1, y2, sl[k], dq[k]));   // linear.rs:94-96
-                }
+            if (is >= 0) {
+                if (!one_interval) unpair<T, V>(ld_pair<T>(p.data + (long long)is * pw + 2 * col), y1, y2);
+                st_stream<T, V>(p.out + (qbase + src) * p.w + col, lerp_vec<T, V>(y1, y2, sl, dq));   // linear.rs:94-96
             }
         }
         if constexpr (kBcast) __syncwarp();
