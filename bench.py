@@ -459,16 +459,20 @@ def link_probes(ctx):
     for _ in range(4):
         pin_a.copy_(dev_buf, non_blocking=True)
     torch.cuda.synchronize()
-    d2h = 4 * nbytes / (time.perf_counter() - t0) / 1e9
+    d2h_s = time.perf_counter() - t0
     ctx.barrier()
     t0 = time.perf_counter()
     for _ in range(2):
         pin_b.copy_(pin_a)
-    h2h = 2 * nbytes / (time.perf_counter() - t0) / 1e9
-    out = {"d2h_link_GBps": d2h, "d2h_link_GBps_all_ranks": ctx.sum_over_ranks(d2h),
-           "host_sink_GBps": h2h, "host_sink_GBps_all_ranks": ctx.sum_over_ranks(h2h),
+    h2h_s = time.perf_counter() - t0
+    # whole-job figures the way the metric itself is timed: all ranks' bytes over the SLOWEST rank's time
+    out = {"d2h_link_GBps": 4 * nbytes / d2h_s / 1e9,
+           "d2h_link_GBps_all_ranks": ctx.world * 4 * nbytes / ctx.max_over_ranks(d2h_s) / 1e9,
+           "host_sink_GBps": 2 * nbytes / h2h_s / 1e9,
+           "host_sink_GBps_all_ranks": ctx.world * 2 * nbytes / ctx.max_over_ranks(h2h_s) / 1e9,
            "how": "256 MB pinned buffers; device-to-host: 4 async copies; host sink: 2 pinned-to-pinned CPU copies "
-                  f"(torch copy_, {torch.get_num_threads()} threads); all {ctx.world} rank(s) at the same time"}
+                  f"(torch copy_, {torch.get_num_threads()} thread(s) per rank); all {ctx.world} rank(s) at the same time, "
+                  "all-ranks figures = all ranks' bytes over the slowest rank's time (like the metric)"}
     del dev_buf, pin_a, pin_b
     return out
 
