@@ -331,7 +331,10 @@ struct BoundaryCondition {
 template <class T>
 class CubicSplineStrategy : public Interp1DStrategy<T> {
 public:
-    CubicSplineStrategy(BoundaryCondition<T> bc, int mode) : bc_(std::move(bc)), mode_(mode) {}
+    CubicSplineStrategy(BoundaryCondition<T> bc, int mode, int build_mode = NDI_BUILD_AUTO, int build_levels = 0)
+        : bc_(std::move(bc)), mode_(mode), build_mode_(build_mode), build_levels_(build_levels) {}
+    // depth of the row-split the coefficients were built with (0: the reference's elimination order)
+    int rowsplit_levels(const Interp1D<T>& ip) const;
     bool uses_device() const override { return true; }
     void bind(const Interp1D<T>& ip) const override;         // CubicSpline::calc_coefficients (:310-368) on the device
     void interp_batch_into(const Interp1D<T>& ip, const T* xs, size_t nq, T* out_rows) const override;
@@ -340,7 +343,7 @@ public:
     std::pair<Array<T>, Array<T>> coefficients(const Interp1D<T>& ip) const;
 private:
     BoundaryCondition<T> bc_;
-    int mode_;
+    int mode_, build_mode_, build_levels_;
 };
 // The CubicSpline 1d interpolation Strategy (Builder) (cubic_spline.rs:84-88, :723-772)
 template <class T>
@@ -350,6 +353,10 @@ public:
     static CubicSpline new_() { return CubicSpline(); }
     CubicSpline extrapolate(bool e) const { CubicSpline c(*this); c.extrapolate_ = e; return c; }
     CubicSpline boundary(BoundaryCondition<T> b) const { CubicSpline c(*this); c.boundary_ = std::move(b); return c; }
+    // NOT in the reference (ndi_interp1d_set_build_mode): NDI_BUILD_AUTO, NDI_BUILD_SEQUENTIAL -- the reference's
+    // elimination order, coefficients bit-identical to its arithmetic -- or NDI_BUILD_ROWSPLIT with `levels` steps of
+    // cyclic reduction (0: the library's choice)
+    CubicSpline solver(int mode, int levels = 0) const { CubicSpline c(*this); c.build_mode_ = mode; c.build_levels_ = levels; return c; }
     size_t MINIMUM_DATA_LENGHT() const override { return 3; }
     std::shared_ptr<const Interp1DStrategy<T>> build(const ArrayView<T>&, const ArrayView<T>& data) const override {
         if (boundary_.kind == NDI_BC_INDIVIDUAL) {           // calc_coefficients :332-347
@@ -360,10 +367,11 @@ public:
                                    detail::shape_str(expect) + ", got: " + detail::shape_str(boundary_.rows_shape));
         }
         const int mode = !extrapolate_ ? NDI_EXTRAP_NO : (boundary_.kind == NDI_BC_PERIODIC ? NDI_EXTRAP_PERIODIC : NDI_EXTRAP_YES);   // :763-769
-        return std::make_shared<CubicSplineStrategy<T>>(boundary_, mode);
+        return std::make_shared<CubicSplineStrategy<T>>(boundary_, mode, build_mode_, build_levels_);
     }
 private:
     bool extrapolate_ = false;
+    int build_mode_ = NDI_BUILD_AUTO, build_levels_ = 0;
     BoundaryCondition<T> boundary_ = BoundaryCondition<T>::NotAKnot();
 };
 
@@ -521,6 +529,7 @@ void CubicSplineStrategy<T>::bind(const Interp1D<T>& ip) const {
     for (const auto& r : bc_.rows) { lk.push_back(r.left.kind); lv.push_back(r.left.value); rk.push_back(r.right.kind); rv.push_back(r.right.value); }
     int64_t bad = -1;
     const bool ind = bc_.kind == NDI_BC_INDIVIDUAL;
+    detail::check(ndi_interp1d_set_build_mode(ip.handle(), build_mode_, build_levels_));
     const ndi_status st = ndi_interp1d_spline_build(ip.handle(), bc_.kind, ind ? lk.data() : nullptr, ind ? lv.data() : nullptr,
                                                     ind ? rk.data() : nullptr, ind ? rv.data() : nullptr, &bad);
     detail::check(st);
@@ -536,6 +545,12 @@ void CubicSplineStrategy<T>::interp_batch_into(const Interp1D<T>& ip, const T* x
 }
 template <class T>
 void CubicSplineStrategy<T>::interp_into(const Interp1D<T>& ip, ArrayViewMut<T> target, T x) const { detail::single_into<T>(*this, ip, target, x); }
+template <class T>
+int CubicSplineStrategy<T>::rowsplit_levels(const Interp1D<T>& ip) const {
+    int32_t lv = -1;
+    detail::check(ndi_interp1d_build_info(ip.handle(), &lv));
+    return lv;
+}
 template <class T>
 std::pair<Array<T>, Array<T>> CubicSplineStrategy<T>::coefficients(const Interp1D<T>& ip) const {
     std::vector<size_t> sh = ip.data().shape();

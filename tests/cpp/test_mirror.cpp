@@ -157,6 +157,22 @@ static void cubic_doc_example() {
     auto good = BoundaryCondition<double>::Individual({1, 2}, {RowBoundary<double>::Natural(), RowBoundary<double>::Mixed(SingleBoundary<double>::FirstDeriv(0.5), SingleBoundary<double>::NotAKnot())});
     auto ind = Interp1DBuilder<double>(d2).strategy(CubicSpline<double>().boundary(good)).build();
     CHECK(close(ind.interp(2.0)[0], 4.0, 8 * EPS) && close(ind.interp(2.0)[1], 1.0, 8 * EPS));
+    // the two build modes of the device-side solve (NOT in the reference): the reference's elimination order and
+    // the row-split (cyclic reduction + Thomas) build agree far inside 1e-12 and both reproduce the knots
+    std::vector<double> yl(4096);
+    for (size_t i = 0; i < yl.size(); ++i) yl[i] = std::sin(0.01 * (double)i) + 0.001 * (double)((i * 2654435761u) % 1000);
+    A ylong(std::vector<size_t>{yl.size()}, yl);
+    auto seq = Interp1DBuilder<double>(ylong).strategy(CubicSpline<double>().solver(NDI_BUILD_SEQUENTIAL)).build();
+    auto split = Interp1DBuilder<double>(ylong).strategy(CubicSpline<double>().solver(NDI_BUILD_ROWSPLIT, 3)).build();
+    auto aut = Interp1DBuilder<double>(ylong).strategy(CubicSpline<double>()).build();
+    CHECK(static_cast<const CubicSplineStrategy<double>&>(seq.strategy()).rowsplit_levels(seq) == 0);
+    CHECK(static_cast<const CubicSplineStrategy<double>&>(split.strategy()).rowsplit_levels(split) == 3);
+    CHECK(static_cast<const CubicSplineStrategy<double>&>(aut.strategy()).rowsplit_levels(aut) == 4);   // AUTO: 4096 rows -> 4 levels
+    for (double x : {0.5, 17.25, 2047.5, 4094.75}) {
+        CHECK(close(seq.interp_scalar(x), split.interp_scalar(x), 1e-12));
+        CHECK(close(seq.interp_scalar(x), aut.interp_scalar(x), 1e-12));
+    }
+    CHECK(close(split.interp_scalar(100.0), yl[100], 8 * EPS));
 }
 
 // tests/interp2d.rs: interp_scalar values, data with trailing axes, range errors with x before y
