@@ -121,16 +121,9 @@ __global__ void __launch_bounds__(kBinBlock) bin_scatter_kernel(const BinArgs<T>
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ unsigned hist[kMaxBands + 1], lbase[kMaxBands], gbase[kMaxBands], band_base[kMaxBands], warp_sums[kBinBlock / 32];
-    // the chunk sorted by band.  4-byte types: ONE 16-byte record per query {index, x, y, band} -- one STS.128 and one
-    // LDS.128 per query where four separate arrays cost four of each, on a kernel that is bound by the shared-memory
-    // (MIO) pipe (profiles/r02/ncu_c5a_bin_scatter.txt: mio_throttle 3.2 per issue).  8-byte types keep the arrays
-    // (32-byte records would not fit the 48 KB of static shared memory).
-    constexpr bool kPacked = sizeof(T) == 4;
-    struct alignas(16) Rec { unsigned idx; T x, y; unsigned band; };
-    __shared__ Rec srec[kPacked ? kBinChunk : 1];
-    __shared__ unsigned sidx[kPacked ? 1 : kBinChunk];
-    __shared__ T sx[kPacked ? 1 : kBinChunk], sy[kPacked ? 1 : kBinChunk];
-    __shared__ unsigned char sband[kPacked ? 1 : kBinChunk];
+    __shared__ unsigned sidx[kBinChunk];
+    __shared__ T sx[kBinChunk], sy[kBinChunk];
+    __shared__ unsigned char sband[kBinChunk];
     static_assert(kMaxBands <= kBinBlock, "one thread per band in the scans");
     const GridView<T> g = make_grid_view<T>(p.gx, p.n, p.scx, smem_raw, &bar);
     {   // first slot of every band = exclusive scan of the totals of pass 1
@@ -168,22 +161,15 @@ __global__ void __launch_bounds__(kBinBlock) bin_scatter_kernel(const BinArgs<T>
             const long long i = base + k * kBinBlock + threadIdx.x;
             if (i < p.nq) {
                 const unsigned pos = lbase[band[k]] + rank[k];
-                if constexpr (kPacked) srec[pos] = Rec{(unsigned)i, x[k], y[k], (unsigned)band[k]};
-                else { sidx[pos] = (unsigned)i; sx[pos] = x[k]; sy[pos] = y[k]; sband[pos] = (unsigned char)band[k]; }
+                sidx[pos] = (unsigned)i; sx[pos] = x[k]; sy[pos] = y[k]; sband[pos] = (unsigned char)band[k];
             }
         }
         __syncthreads();
         const int cnt = (int)min((long long)kBinChunk, p.nq - base);
         for (int s = threadIdx.x; s < cnt; s += kBinBlock) {
-            if constexpr (kPacked) {
-                const Rec r = srec[s];
-                const unsigned dst = gbase[r.band] + ((unsigned)s - lbase[r.band]);
-                p.perm[dst] = r.idx; p.bqx[dst] = r.x; p.bqy[dst] = r.y;
-            } else {
-                const int b = sband[s];
-                const unsigned dst = gbase[b] + ((unsigned)s - lbase[b]);
-                p.perm[dst] = sidx[s]; p.bqx[dst] = sx[s]; p.bqy[dst] = sy[s];
-            }
+            const int b = sband[s];
+            const unsigned dst = gbase[b] + ((unsigned)s - lbase[b]);
+            p.perm[dst] = sidx[s]; p.bqx[dst] = sx[s]; p.bqy[dst] = sy[s];
         }
         __syncthreads();
         if (threadIdx.x < kMaxBands) hist[threadIdx.x] = 0;

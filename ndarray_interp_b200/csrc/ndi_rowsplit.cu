@@ -25,7 +25,6 @@
 // (the CPU checker's rowsplit_thomas, see tests/test_rowsplit_gpu.py) and to north_star's 1e-12 (f64) / 1e-5 (f32) bars against the
 // reference-order checker.  Every product and sum is rounded on its own (no FMA),
 // the i-s term before the i+s term, exactly as the specification writes them.
-#include <cstdlib>
 #include <map>
 
 #include "ndi_spline.cuh"
@@ -37,8 +36,7 @@ namespace ndi {
 //   [4n, 5n)            k2, the shared second solution of the periodic system
 //   [5n, 5n + 2Ln)      {alpha, gamma} per (level, row)
 //   [.., .. + 8n)       two sets of (low, mid, up, rhs2) for the level-by-level reduction of the matrix
-//   [.., .. + n)        refined reciprocals of the grid steps x[i+1] - x[i] (the divisions of the right-hand side)
-size_t rowsplit_fac_elems(int64_t n, int levels) { return ((size_t)(14 + 2 * levels) * (size_t)n + 3) & ~(size_t)3; }
+size_t rowsplit_fac_elems(int64_t n, int levels) { return ((size_t)(13 + 2 * levels) * (size_t)n + 3) & ~(size_t)3; }
 
 int rowsplit_levels_for(int64_t rows, int requested, bool force) {
     int most = 0;
@@ -61,7 +59,6 @@ struct RsFac {
     T* fac; size_t fac_stride; int n, len, levels, periodic, lk, rk;
     __device__ __forceinline__ T* base() const { return fac + blockIdx.y * fac_stride; }
     __device__ __forceinline__ T* set(int which) const { return base() + (5 + 2 * (size_t)levels) * (size_t)n + (size_t)which * 4 * (size_t)n; }
-    __device__ __forceinline__ T* rdx() const { return set(2); }      // after the two sets
 };
 
 // level 0: the matrix of solve_for_k (:440-451, boundary rows :599-669; periodic: the condensed system :512-518)
@@ -74,10 +71,6 @@ __global__ void __launch_bounds__(kRsBlock) rowsplit_matrix_kernel(const T* __re
     int lk = f.lk, rk = f.rk;
     if (gridDim.y > 1) { lk = ind_kind(blockIdx.y / 3); rk = ind_kind(blockIdx.y % 3); }
     T* cur = f.set(0);
-    // 1 / (x[i+1] - x[i]), refined as IEEE division refines it: the right-hand side divides by two grid steps per
-    // element, the same for all columns (Hoisted::div: the same quotient bits in 3 operations instead of ~25)
-    if (i + 1 < n) f.rdx()[i] = Hoisted<T>::rcp(SUB(x[i + 1], x[i]));
-    if (f.periodic && i == f.len - 1) { f.rdx()[n - 3] = Hoisted<T>::rcp(SUB(x[n - 2], x[n - 3])); f.rdx()[n - 2] = Hoisted<T>::rcp(SUB(x[n - 1], x[n - 2])); }
     T u, m, l;
     if (f.periodic) matrix_row_periodic<T>(x, n, i, u, m, l); else matrix_row<T>(x, n, i, lk, rk, false, u, m, l);
     cur[i] = l; cur[N + i] = m; cur[2 * N + i] = u;
@@ -198,7 +191,6 @@ __global__ void __launch_bounds__(512) rowsplit_reduce_kernel(const T* __restric
         cout = pos[c];
     }
     const T* coef = fac + fo + 5 * (size_t)n;
-    const T* rdx = fac + (13 + 2 * (size_t)levels) * (size_t)n;      // the first matrix's copy serves every column (x only)
     const T* ycol = y + (colok ? c : 0);
     auto Y = [&](int row) -> T { return __ldg(ycol + (long long)row * w); };
     // y rows [i0 - 1, i0 + nb + 1) -> bufB; kRsLoadAhead independent loads in flight per thread (a block that waits
@@ -226,11 +218,7 @@ __global__ void __launch_bounds__(512) rowsplit_reduce_kernel(const T* __restric
             const bool interior = periodic ? i > 0 : (i > 0 && i < n - 1);
             if (interior) {
                 const T xm = __ldg(x + i - 1), xi = __ldg(x + i), xp = __ldg(x + i + 1);
-                const T dxn = SUB(xp, xi), dxn_1 = SUB(xi, xm);
-                const T yl = bufB[rr * 32 + lane], ym = bufB[(rr + 1) * 32 + lane], yr = bufB[(rr + 2) * 32 + lane];
-                // :468, the two divisions through the per-row reciprocals (same bits as DIV)
-                v = MUL(three, ADD(Hoisted<T>::div(MUL(dxn, SUB(ym, yl)), dxn_1, __ldg(rdx + i - 1)),
-                                   Hoisted<T>::div(MUL(dxn_1, SUB(yr, ym)), dxn, __ldg(rdx + i))));
+                v = rhs_interior<T>(bufB[rr * 32 + lane], bufB[(rr + 1) * 32 + lane], bufB[(rr + 2) * 32 + lane], SUB(xp, xi), SUB(xi, xm));
             } else if (periodic) {
                 const T dx0 = SUB(x[1], x[0]), dx_1 = SUB(x[n - 1], x[n - 2]);
                 const T y0 = Y(0), yN = Y(n - 1);
@@ -293,8 +281,7 @@ static SideStream& side_stream() {
 
 static int rowsplit_tile_rows(int levels, size_t elem) {
     const int H = (1 << levels) - 1;
-    static const int shift = [] { const char* e = getenv("NDI_RS_TILE_SHIFT"); return e && *e ? atoi(e) : 2; }();   // A/B: rows = 2^shift halos
-    int rt = (1 << shift) << levels;
+    int rt = 4 << levels;
     if (rt < 64) rt = 64;
     while (rt > 8 && 2 * (size_t)(rt + 2 * H + 2) * 32 * elem > (size_t)200 * 1024) rt >>= 1;
     return rt;
