@@ -1255,7 +1255,7 @@ static void search2(const ndi_interp2d* h, size_t es, int64_t nq, SearchCfg* sx,
 }
 
 ndi_status ndi_interp2d_set_binning(ndi_interp2d* h, int32_t mode, int32_t band_rows) {
-    if (!h || mode < NDI_BIN_AUTO || mode > NDI_BIN_ON || band_rows < 0) return fail(NDI_INVALID_ARGUMENT, "bad binning mode");
+    if (!h || mode < NDI_BIN_AUTO || mode > NDI_BIN_SWEEP || band_rows < 0) return fail(NDI_INVALID_ARGUMENT, "bad binning mode");
     h->bin_mode = mode; h->band_rows = band_rows;
     return NDI_OK;
 }
@@ -1272,7 +1272,7 @@ namespace {
 bool want_binning(const ndi_interp2d* h, int64_t nq, size_t es, BandPlan* bp) {
     static const long env_mode = env_long("NDI_BIN_MODE", -1), env_band_mb = env_long("NDI_BAND_MB", 16);
     const int mode = env_mode >= 0 ? (int)env_mode : h->bin_mode;
-    if (mode == NDI_BIN_OFF || nq < 2 || nq > 0xffffffffll) return false;
+    if (mode == NDI_BIN_OFF || mode == NDI_BIN_SWEEP || nq < 2 || nq > 0xffffffffll) return false;
     const double table = (double)h->n * (double)h->m * (double)h->w * (double)es;
     *bp = plan_bands(h->n, h->m, h->w, es, (size_t)env_band_mb << 20, h->band_rows);
     if (bp->nbands < 2) return false;
@@ -1285,10 +1285,37 @@ bool want_binning(const ndi_interp2d* h, int64_t nq, size_t es, BandPlan* bp) {
     return direct > 1.5 * binned;
 }
 
-// one bilinear evaluation of a device-resident batch: direct, or binned by table band
+// Band sweeps (ndi_sweep.cu): the batch stays where it is and is walked once per table band.  Built for thin rows on a
+// table a few times the size of L2 (C4: 134 MB, four sweeps of 32 MB).  MEASURED, AND NOT CHOSEN BY AUTO: the sweeps cut
+// C4's DRAM traffic from 3.14 to 1.36 GB as designed, but the compaction, the scattered 32-byte output rows and the lower
+// occupancy cost more than the DRAM time they save -- 0.580 ms against 0.537 ms for the direct kernel, which already runs
+// at the DRAM ceiling of its access pattern (profiles/r02/sweeps_and_probes.md).  The mode stays selectable
+// (NDI_BIN_SWEEP, or NDI_SWEEP_MODE=1 for measurements) and is covered by the parity tests.
+bool want_sweeps(const ndi_interp2d* h, int64_t nq, size_t es, const void* out, SweepPlan* sp) {
+    static const long env_mode = env_long("NDI_SWEEP_MODE", -1), env_band_mb = env_long("NDI_SWEEP_MB", 32);
+    const bool forced = env_mode > 0 && h->bin_mode == NDI_BIN_AUTO && nq >= (1 << 18);
+    if (h->bin_mode != NDI_BIN_SWEEP && !forced) return false;
+    if (!sweep_shape_ok(h->n, h->m, h->w, es, h->data, out, nq)) return false;
+    *sp = plan_sweeps(h->n, h->m, h->w, es, (size_t)env_band_mb << 20, h->bin_mode == NDI_BIN_SWEEP ? h->band_rows : 0);
+    return true;
+}
+
+// one bilinear evaluation of a device-resident batch: direct, in band sweeps, or binned by table band
 template <class T>
 ndi_status bilinear_on_device(const ndi_interp2d* h, const SearchCfg& sx, const SearchCfg& sy, const T* qx, const T* qy,
                               int64_t nq, int extrapolate, T* out, unsigned long long* err, cudaStream_t s) {
+    SweepPlan sp;
+    if (want_sweeps(h, nq, sizeof(T), out, &sp)) {
+        unsigned long long* ticket = nullptr;
+        CK(cudaMallocAsync((void**)&ticket, sizeof(unsigned long long), s));
+        cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s);
+        if (e == cudaSuccess)
+            e = launch_interp2d_bilinear_sweep<T>((const T*)h->x, h->n, sx, (const T*)h->y, h->m, sy, (const T*)h->data, h->w, qx, qy,
+                                                  nq, extrapolate, out, err, h->fast_tables, sp, ticket, s);
+        cudaFreeAsync(ticket, s);
+        if (e != cudaSuccess) return cuda_fail(e, "swept bilinear launch");
+        return NDI_OK;
+    }
     BandPlan bp;
     if (!want_binning(h, nq, sizeof(T), &bp)) {
         CK(launch_interp2d_bilinear<T>((const T*)h->x, h->n, sx, (const T*)h->y, h->m, sy, (const T*)h->data, h->w, qx, qy, nq,

@@ -83,6 +83,20 @@ cudaError_t launch_bin_queries(const T* gx, int64_t n, SearchCfg scx, const T* q
                                BandPlan bp, void* scratch, const unsigned** perm, const T** bqx, const T** bqy,
                                unsigned long long** next_task, cudaStream_t st);
 
+// ---- bilinear in band sweeps (ndi_sweep.cu) ----------------------------------------------------
+// The launch walks the batch nsweeps times; sweep b evaluates the queries whose x-interval lies in
+// [b * band_rows, (b + 1) * band_rows), compacted into full tiles, so that the band's table rows stay in L2.
+// Rows of 16 / 32 / 64 / 128 bytes only (sweep_shape_ok).  next_task: a zeroed 8-byte device word.
+constexpr int kMaxSweeps = 16;
+struct SweepPlan { int band_rows; int nsweeps; };
+SweepPlan plan_sweeps(int64_t n, int64_t m, int64_t w, size_t elem, size_t band_bytes, int band_rows);
+bool sweep_shape_ok(int64_t n, int64_t m, int64_t w, size_t elem, const void* data, const void* out, int64_t nq);
+template <class T>
+cudaError_t launch_interp2d_bilinear_sweep(const T* gx, int64_t n, SearchCfg scx, const T* gy, int64_t m, SearchCfg scy,
+                                           const T* data, int64_t w, const T* qx, const T* qy, int64_t nq, int extrapolate,
+                                           T* out, unsigned long long* err, int fast_tables, SweepPlan sp,
+                                           unsigned long long* next_task, cudaStream_t st);
+
 // fast_tables (linear, bilinear; f32 only): 1 when launch_table_fast_div found every table value to
 // be 0 or in [2^-56, 2^30], which lets the kernels divide with a per-query reciprocal (ndi_device.cuh)
 cudaError_t launch_table_fast_div(const float* data, size_t count, int32_t* flag_dev, cudaStream_t st);

@@ -45,7 +45,7 @@ extern "C" {
     pub fn ndi_interp2d_create_strided(dtype: i32, x: *const c_void, n: i64, x_stride: i64, y: *const c_void, m: i64, y_stride: i64, data: *const c_void, ndim: i32, shape: *const i64, strides: *const i64, flags: u32, out: *mut *mut ndi_interp2d) -> ndi_status;
     pub fn ndi_interp2d_create(dtype: i32, x: *const c_void, n: i64, y: *const c_void, m: i64, data: *const c_void, w: i64, flags: u32, out: *mut *mut ndi_interp2d) -> ndi_status;
     pub fn ndi_interp2d_destroy(h: *mut ndi_interp2d) -> ndi_status;
-    /// locality binning of query batches by table band: 0 auto, 1 off, 2 on (csrc/ndi_bin.cu)
+    /// locality binning of query batches by table band: 0 auto, 1 off, 2 on (csrc/ndi_bin.cu), 3 band sweeps (csrc/ndi_sweep.cu)
     pub fn ndi_interp2d_set_binning(h: *mut ndi_interp2d, mode: i32, band_rows: i32) -> ndi_status;
     pub fn ndi_interp2d_bilinear(h: *const ndi_interp2d, qx: *const c_void, qy: *const c_void, nq: i64, extrapolate: i32, out: *mut c_void, first_bad: *mut i64, bad_axis: *mut i32) -> ndi_status;
 }

@@ -37,7 +37,7 @@ def test_fuzz_linear_and_bilinear(seed):
     qx, qy = make_queries(rng, g, nq, dt, extrap), make_queries(rng, gy, nq, dt, extrap)
     st, ref, _, _ = O.interp2d_bilinear(g, gy, d2, qx, qy, extrap)
     assert st == O.ST_OK
-    for mode, rows in [(L.BIN_OFF, 0), (L.BIN_ON, int(rng.choice([1, 2, 8])))]:
+    for mode, rows in [(L.BIN_OFF, 0), (L.BIN_ON, int(rng.choice([1, 2, 8]))), (L.BIN_SWEEP, int(rng.choice([1, 2, 8, 64])))]:
         ip = Interp2D.new_unchecked(g, gy, d2, Bilinear.new().extrapolate(extrap))
         L.check(L.load().ndi_interp2d_set_binning(ip._handle(), mode, rows))
         assert same(ip.interp_array(qx, qy), ref), (mode, rows)

@@ -380,7 +380,7 @@ def test_bilinear_binned_device_api_error_word_and_rows():
     assert (first, axis) == (77, 1)
     ip = D.DeviceInterp2D(torch.from_numpy(gx).cuda(), torch.from_numpy(gy).cuda(), torch.from_numpy(data).cuda())
     outs = []
-    for mode, rows in [(L.BIN_OFF, 0), (L.BIN_ON, 32), (L.BIN_ON, 1)]:
+    for mode, rows in [(L.BIN_OFF, 0), (L.BIN_ON, 32), (L.BIN_ON, 1), (L.BIN_SWEEP, 100), (L.BIN_SWEEP, 1)]:
         ip.set_binning(mode, rows)
         err = D.new_err_word()
         out = torch.zeros((nq, w), dtype=torch.float32, device="cuda")
@@ -392,6 +392,90 @@ def test_bilinear_binned_device_api_error_word_and_rows():
     for o in outs:
         assert same(o[good], full)                 # every passing row is written, failing rows are skipped
         assert not o[bad].any()
+
+
+# ---- K9: band sweeps (ndi_sweep.cu) ---------------------------------------------------------------------
+def _force_sweeps(interp, band_rows):
+    L.check(L.load().ndi_interp2d_set_binning(interp._handle(), L.BIN_SWEEP, band_rows))
+
+
+@pytest.mark.parametrize("dt", DTS, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("row_bytes", [16, 32, 64, 128, 48])
+@pytest.mark.parametrize("band_rows,xkind", [(1, "random"), (7, "uniform"), (40, "random"), (1000, "uniform")])
+def test_bilinear_sweeps_match_oracle(dt, row_bytes, band_rows, xkind):
+    """sweeps change the evaluation order only (and, for 32-byte rows, which lane holds which operand): same bits
+    as the oracle.  band_rows = 1 asks for more than 16 sweeps (the plan coarsens), 1000 gives a single sweep;
+    48-byte rows are not a sweep shape and must fall through to the direct kernel."""
+    rng = np.random.default_rng(901 + band_rows + row_bytes)
+    n, m, w = 300, 41, row_bytes // np.dtype(dt).itemsize
+    gx, gy = make_grid(rng, n, dt, xkind), make_grid(rng, m, dt, "random")
+    data = make_data(rng, (n, m, w), dt)
+    ex = Interp2D.new_unchecked(gx, gy, data, Bilinear.new().extrapolate(True))
+    strict = Interp2D.new_unchecked(gx, gy, data, Bilinear.new())
+    _force_sweeps(ex, band_rows)
+    _force_sweeps(strict, band_rows)
+    for nq in (1, 2, 33, 255, 256, 257, 2049, 30011):
+        qx, qy = make_queries(rng, gx, nq, dt, True), make_queries(rng, gy, nq, dt, True)
+        st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, True)
+        assert st == O.ST_OK
+        assert same(ex.interp_array(qx, qy), ref)
+        qx, qy = make_queries(rng, gx, nq, dt, False), make_queries(rng, gy, nq, dt, False)
+        st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, False)
+        assert same(strict.interp_array(qx, qy), ref)
+
+
+@pytest.mark.parametrize("mode", [L.SEARCH_AUTO, L.SEARCH_BINARY_SMEM, L.SEARCH_BINARY_GLOBAL, L.SEARCH_UNIFORM_GUESS, L.SEARCH_BUCKET_LUT, L.SEARCH_MERGE])
+def test_bilinear_sweeps_with_every_search_mode(mode):
+    rng = np.random.default_rng(77 + mode)
+    gx, gy = np.linspace(0, 1, 2048).astype(np.float32), np.cumsum(rng.uniform(0.5, 1.5, 777)).astype(np.float32)
+    data = rng.normal(size=(2048, 777, 8)).astype(np.float32)
+    interp = Interp2D.new_unchecked(gx, gy, data, Bilinear.new().extrapolate(True))
+    L.check(L.load().ndi_interp2d_set_search_mode(interp._handle(), mode))
+    _force_sweeps(interp, 512)
+    qx, qy = make_queries(rng, gx, 50000, np.float32, True), make_queries(rng, gy, 50000, np.float32, True)
+    st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, True)
+    assert same(interp.interp_array(qx, qy), ref)
+
+
+def test_bilinear_sweeps_extreme_values_take_the_slow_division():
+    """tables and queries outside the ranges of the hoisted-reciprocal division (tiny / huge values, far
+    extrapolation, zero differences) through the pair form of the 32-byte rows"""
+    rng = np.random.default_rng(5)
+    n, m, w = 64, 33, 8
+    gx, gy = np.cumsum(rng.uniform(0.5, 1.5, n)).astype(np.float32), np.linspace(0, 1, m).astype(np.float32)
+    data = (rng.normal(size=(n, m, w)) * np.exp(rng.uniform(-80, 60, (n, m, w)))).astype(np.float32)
+    data[rng.random((n, m, w)) < 0.2] = 0.0
+    data[10:20] = data[9]                                   # zero first-stage numerators
+    nq = 20000
+    qx = rng.uniform(gx[0] - 1e6, gx[-1] + 1e6, nq).astype(np.float32)
+    qy = rng.uniform(-3, 4, nq).astype(np.float32)
+    qx[::3] = rng.uniform(gx[0], gx[-1], len(qx[::3])).astype(np.float32)
+    ip = Interp2D.new_unchecked(gx, gy, data, Bilinear.new().extrapolate(True))
+    with np.errstate(all="ignore"):
+        st, ref, _, _ = O.interp2d_bilinear(gx, gy, data, qx, qy, True)
+    direct = ip.interp_array(qx, qy)
+    _force_sweeps(ip, 16)
+    assert same(direct, ref)
+    assert same(ip.interp_array(qx, qy), ref)
+
+
+def test_bilinear_sweeps_errors_like_the_reference():
+    rng = np.random.default_rng(24)
+    gx, gy = np.linspace(0, 1, 500), np.cumsum(rng.uniform(0.5, 1.5, 20))
+    data = rng.normal(size=(500, 20, 4))
+    interp = Interp2D.new_unchecked(gx, gy, data, Bilinear.new())
+    _force_sweeps(interp, 100)
+    for nq in (200, 70000):
+        qx, qy = rng.uniform(0, 1, nq), rng.uniform(gy[0], gy[-1], nq)
+        qy[nq // 2] = gy[-1] + 1
+        qx[nq // 2 + 5] = 2.0
+        qx[nq - 1] = np.nan
+        buf = np.full((nq, 4), 3.0)
+        with pytest.raises(InterpolateError.OutOfBounds, match="y = "):
+            interp.interp_array_into(qx, qy, buf)
+        st, ref, bad, ax = O.interp2d_bilinear(gx, gy, data, qx, qy, False, out=np.full((nq, 4), 3.0))
+        assert (st, bad, ax) == (O.ST_OUT_OF_BOUNDS, nq // 2, 1)
+        assert same(buf, ref)
 
 
 # ---- hoisted-reciprocal division (ndi_device.cuh: rcp_refined / div_by) ------------------------------
