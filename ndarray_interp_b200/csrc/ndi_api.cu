@@ -125,11 +125,13 @@ constexpr size_t kTinyQueryBytes = NDI_TINY_KB * 1024ull;
 struct Workspace {
     bool ready = false;
     cudaStream_t s[2] = {nullptr, nullptr};
+    cudaStream_t s_in = nullptr;              // copy-in stream of the streaming host pipeline (queries up + pre-pass, a few chunks ahead)
+    cudaEvent_t feed_ev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev = nullptr;
     void* d_q[2] = {nullptr, nullptr}; size_t d_q_cap[2] = {0, 0};
     void* d_out[2] = {nullptr, nullptr}; size_t d_out_cap[2] = {0, 0};
     void* d_build = nullptr; size_t d_build_cap = 0;       // spline-build scratch, kept between builds (up to kBuildKeepBytes)
-    unsigned long long* d_err = nullptr;      // 4 words
+    unsigned long long* d_err = nullptr;      // 8 words: [0] call, [1] tiny-batch path, [4..6] chunks of the streaming pipeline
     int32_t* d_res = nullptr;                 // 2 words (grid classify result)
     uint32_t* d_scr = nullptr;                // grid classify scratch
     unsigned char* h_pin = nullptr; size_t h_pin_cap = 0;   // pinned: [err word, flag | small outputs | tiny queries]
@@ -147,8 +149,11 @@ static Workspace* workspace(int dev, ndi_status* st) {
     cudaError_t e;
     for (int i = 0; i < 2; ++i)
         if ((e = cudaStreamCreateWithFlags(&w.s[i], cudaStreamNonBlocking)) != cudaSuccess) { *st = cuda_fail(e, "cudaStreamCreate"); return nullptr; }
+    if ((e = cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking)) != cudaSuccess) { *st = cuda_fail(e, "cudaStreamCreate"); return nullptr; }
     if ((e = cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming)) != cudaSuccess) { *st = cuda_fail(e, "cudaEventCreate"); return nullptr; }
-    if ((e = cudaMalloc(&w.d_err, 4 * sizeof(unsigned long long))) != cudaSuccess) { *st = cuda_fail(e, "cudaMalloc"); return nullptr; }
+    for (int i = 0; i < 3; ++i)
+        if ((e = cudaEventCreateWithFlags(&w.feed_ev[i], cudaEventDisableTiming)) != cudaSuccess) { *st = cuda_fail(e, "cudaEventCreate"); return nullptr; }
+    if ((e = cudaMalloc(&w.d_err, 8 * sizeof(unsigned long long))) != cudaSuccess) { *st = cuda_fail(e, "cudaMalloc"); return nullptr; }
     if ((e = cudaMalloc(&w.d_res, 2 * sizeof(int32_t))) != cudaSuccess) { *st = cuda_fail(e, "cudaMalloc"); return nullptr; }
     if ((e = cudaMalloc(&w.d_scr, grid_classify_scratch_words() * sizeof(uint32_t))) != cudaSuccess) { *st = cuda_fail(e, "cudaMalloc"); return nullptr; }
     w.h_pin_cap = 64 + kSmallBytes + 2 * kTinyQueryBytes;
@@ -783,14 +788,21 @@ ndi_status run_host_eval(const HostEval& he, Launch&& launch, Validate&& validat
         memcpy(he.out, ws->h_pin + 64, (size_t)nvalid * row);
         return NDI_OK;
     }
+    const size_t total = (size_t)he.nq * row;
+    // One call over a large batch STREAMS: the queries go up chunk by chunk on a copy-in stream, a few chunks ahead of
+    // the evaluation, each followed by the pre-pass over that chunk, so the upload (host -> device) runs beside the
+    // copy-out of earlier chunks (device -> host) instead of in front of it -- PCIe is full duplex, and for thin rows
+    // the queries are a fifth of the bytes on the link (C4: 134 MB up, 537 MB down).  Chunks are consumed in order, so
+    // stopping at the first chunk whose pre-pass reports a failure is the reference's "first Err" exactly.
+    static const bool stream_upload = [] { const char* e = getenv("NDI_STREAM_UPLOAD"); return !(e && *e == '0'); }();   // A/B switch
+    const bool streaming = stream_upload && he.phase == 0 && total > kSmallBytes;
     for (int c = 0; c < he.ncoord && he.phase != 2; ++c) {    // phase 2: this thread uploaded them in phase 1
         if ((st = grow(&ws->d_q[c], &ws->d_q_cap[c], qbytes)) != NDI_OK) return st;
-        CK(cudaMemcpyAsync(ws->d_q[c], he.q[c], qbytes, cudaMemcpyHostToDevice, ws->s[0]));
+        if (!streaming) CK(cudaMemcpyAsync(ws->d_q[c], he.q[c], qbytes, cudaMemcpyHostToDevice, ws->s[0]));
     }
     const void* dq0 = ws->d_q[0];
     const void* dq1 = he.ncoord > 1 ? ws->d_q[1] : nullptr;
     unsigned long long* d_err = ws->d_err;
-    const size_t total = (size_t)he.nq * row;
 
     if (he.phase == 0 && total <= kSmallBytes) {
         // latency path: fused launch, one synchronisation
@@ -809,7 +821,9 @@ ndi_status run_host_eval(const HostEval& he, Launch&& launch, Validate&& validat
 
     // K7 pre-pass: where would the reference stop?
     int64_t nvalid = he.nq;
-    if (he.phase != 2) {
+    if (streaming) {
+        // decided chunk by chunk below
+    } else if (he.phase != 2) {
         CK(cudaMemsetAsync(d_err, 0xff, sizeof(uint64_t), ws->s[0]));
         if ((st = validate(dq0, dq1, he.nq, d_err, ws->s[0])) != NDI_OK) return st;
         CK(cudaMemcpyAsync(ws->h_pin, d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws->s[0]));
@@ -822,6 +836,41 @@ ndi_status run_host_eval(const HostEval& he, Launch&& launch, Validate&& validat
         if (nvalid <= 0) return NDI_OK;
     }
 
+    // the copy-in side of the streaming pipeline: chunk i = queries [i * per, (i + 1) * per)
+    constexpr int kFeedDepth = 3;
+    auto feed = [&](int64_t i, int64_t per) -> ndi_status {
+        const int64_t lo = i * per;
+        if (!streaming || lo >= he.nq) return NDI_OK;
+        const int64_t cnt = he.nq - lo < per ? he.nq - lo : per;
+        const int k = (int)(i % kFeedDepth);
+        for (int c = 0; c < he.ncoord; ++c)
+            CK(cudaMemcpyAsync((unsigned char*)ws->d_q[c] + (size_t)lo * he.es, (const unsigned char*)he.q[c] + (size_t)lo * he.es,
+                               (size_t)cnt * he.es, cudaMemcpyHostToDevice, ws->s_in));
+        CK(cudaMemsetAsync(d_err + 4 + k, 0xff, sizeof(uint64_t), ws->s_in));
+        ndi_status fs = validate((const unsigned char*)dq0 + (size_t)lo * he.es, dq1 ? (const unsigned char*)dq1 + (size_t)lo * he.es : nullptr,
+                                 cnt, d_err + 4 + k, ws->s_in);
+        if (fs != NDI_OK) return fs;
+        CK(cudaMemcpyAsync(ws->h_pin + 16 + 8 * k, d_err + 4 + k, sizeof(uint64_t), cudaMemcpyDeviceToHost, ws->s_in));
+        CK(cudaEventRecord(ws->feed_ev[k], ws->s_in));
+        return NDI_OK;
+    };
+    // chunk i has arrived: how many of its rows does the reference write?  (fewer than all: the batch ends there)
+    auto fed = [&](int64_t i, int64_t per, int64_t cnt, int64_t* cnt_valid) -> ndi_status {
+        *cnt_valid = cnt;
+        if (!streaming) return NDI_OK;
+        const int k = (int)(i % kFeedDepth);
+        CK(cudaEventSynchronize(ws->feed_ev[k]));
+        uint64_t word; memcpy(&word, ws->h_pin + 16 + 8 * k, sizeof(word));
+        if (word != NDI_ERR_WORD_NONE) {
+            const uint64_t lo = (uint64_t)(i * per);
+            *cnt_valid = (int64_t)(he.ncoord > 1 ? word >> 1 : word);
+            *err_word = he.ncoord > 1 ? word + 2 * lo : word + lo;
+        }
+        return NDI_OK;
+    };
+    // never return while a copy from (or into) the caller's memory is in flight
+    auto drain = [&]() { if (streaming) cudaStreamSynchronize(ws->s_in); cudaStreamSynchronize(ws->s[0]); cudaStreamSynchronize(ws->s[1]); };
+
     static const bool stage_pageable = [] { const char* e = getenv("NDI_STAGE_PAGEABLE"); return !(e && *e == '0'); }();
     if (stage_pageable && row <= kStageBytes / 32 && is_pageable_host(he.out)) {
         // pageable output: device -> pinned staging (three buffers in flight) -> caller memory by the copy pool
@@ -832,46 +881,68 @@ ndi_status run_host_eval(const HostEval& he, Launch&& launch, Validate&& validat
         }
         CopyPool& pool = CopyPool::get();
         uint64_t ticket[3] = {0, 0, 0};
+        int64_t staged_cnt[3] = {0, 0, 0};
         const int64_t nch = (nvalid + per - 1) / per;
         auto finish = [&](int64_t j) -> ndi_status {           // chunk j has landed in its staging buffer: hand it to the pool
             const int k = (int)(j % 3);
             CK(cudaEventSynchronize(ws->stage_ev[k]));
-            const int64_t lo = j * per, cnt = nvalid - lo < per ? nvalid - lo : per;
-            ticket[k] = pool.submit((unsigned char*)he.out + (size_t)lo * row, ws->h_stage[k], (size_t)cnt * row);
+            ticket[k] = pool.submit((unsigned char*)he.out + (size_t)(j * per) * row, ws->h_stage[k], (size_t)staged_cnt[k] * row);
             return NDI_OK;
         };
         ndi_status pst = NDI_OK;
+        for (int64_t i = 0; i < kFeedDepth && pst == NDI_OK; ++i) pst = feed(i, per);
+        int64_t launched = 0;                                    // chunks whose copy-out was issued
         for (int64_t i = 0; i < nch && pst == NDI_OK; ++i) {
             const int k = (int)(i % 3), sl = (int)(i & 1);
-            const int64_t lo = i * per, cnt = nvalid - lo < per ? nvalid - lo : per;
+            const int64_t lo = i * per;
+            int64_t cnt = nvalid - lo < per ? nvalid - lo : per;
+            const int64_t full = cnt;
+            if ((pst = fed(i, per, cnt, &cnt)) != NDI_OK) break;
+            if ((pst = feed(i + kFeedDepth, per)) != NDI_OK) break;
             pool.wait(ticket[k]);                                // the host copy that last used this staging buffer is done
-            if ((pst = grow(&ws->d_out[sl], &ws->d_out_cap[sl], (size_t)per * row)) != NDI_OK) break;
-            const void* c0 = (const unsigned char*)dq0 + (size_t)lo * he.es;
-            const void* c1 = dq1 ? (const unsigned char*)dq1 + (size_t)lo * he.es : nullptr;
-            if ((pst = launch(c0, c1, cnt, ws->d_out[sl], nullptr, ws->s[sl])) != NDI_OK) break;
-            cudaError_t ce = cudaMemcpyAsync(ws->h_stage[k], ws->d_out[sl], (size_t)cnt * row, cudaMemcpyDeviceToHost, ws->s[sl]);
-            if (ce == cudaSuccess) ce = cudaEventRecord(ws->stage_ev[k], ws->s[sl]);
-            if (ce != cudaSuccess) { pst = cuda_fail(ce, "staged copy"); break; }
-            if (i >= 1) pst = finish(i - 1);
+            if (cnt > 0) {
+                if ((pst = grow(&ws->d_out[sl], &ws->d_out_cap[sl], (size_t)per * row)) != NDI_OK) break;
+                const void* c0 = (const unsigned char*)dq0 + (size_t)lo * he.es;
+                const void* c1 = dq1 ? (const unsigned char*)dq1 + (size_t)lo * he.es : nullptr;
+                if ((pst = launch(c0, c1, cnt, ws->d_out[sl], nullptr, ws->s[sl])) != NDI_OK) break;
+                cudaError_t ce = cudaMemcpyAsync(ws->h_stage[k], ws->d_out[sl], (size_t)cnt * row, cudaMemcpyDeviceToHost, ws->s[sl]);
+                if (ce == cudaSuccess) ce = cudaEventRecord(ws->stage_ev[k], ws->s[sl]);
+                if (ce != cudaSuccess) { pst = cuda_fail(ce, "staged copy"); break; }
+                staged_cnt[k] = cnt;
+                if (launched >= 1) pst = finish(launched - 1);
+                ++launched;
+            }
+            if (cnt < full) break;                               // the reference stopped inside this chunk
         }
-        if (pst == NDI_OK && nch >= 1) pst = finish(nch - 1);
+        if (pst == NDI_OK && launched >= 1) pst = finish(launched - 1);
         for (int k = 0; k < 3; ++k) pool.wait(ticket[k]);      // never leave with copies into the caller's memory in flight
-        if (pst != NDI_OK) { cudaStreamSynchronize(ws->s[0]); cudaStreamSynchronize(ws->s[1]); }
+        if (pst != NDI_OK || streaming) drain();
         return pst;
     }
     int64_t per_chunk = (int64_t)(kChunkBytes / row);
     per_chunk = per_chunk < 32 ? 32 : (per_chunk & ~31ll);
     const size_t chunk_bytes = (size_t)per_chunk * row;
     int slot = 0;
-    for (int64_t lo = 0; lo < nvalid; lo += per_chunk, slot ^= 1) {
-        const int64_t cnt = nvalid - lo < per_chunk ? nvalid - lo : per_chunk;
-        if ((st = grow(&ws->d_out[slot], &ws->d_out_cap[slot], chunk_bytes < total ? chunk_bytes : total)) != NDI_OK) return st;
-        const void* c0 = (const unsigned char*)dq0 + (size_t)lo * he.es;
-        const void* c1 = dq1 ? (const unsigned char*)dq1 + (size_t)lo * he.es : nullptr;
-        if ((st = launch(c0, c1, cnt, ws->d_out[slot], nullptr, ws->s[slot])) != NDI_OK) return st;
-        CK(cudaMemcpyAsync((unsigned char*)he.out + (size_t)lo * row, ws->d_out[slot], (size_t)cnt * row,
-                           cudaMemcpyDeviceToHost, ws->s[slot]));
+    st = NDI_OK;
+    for (int64_t i = 0; i < kFeedDepth && st == NDI_OK; ++i) st = feed(i, per_chunk);
+    for (int64_t lo = 0, i = 0; lo < nvalid && st == NDI_OK; lo += per_chunk, ++i, slot ^= 1) {
+        int64_t cnt = nvalid - lo < per_chunk ? nvalid - lo : per_chunk;
+        const int64_t full = cnt;
+        if ((st = fed(i, per_chunk, cnt, &cnt)) != NDI_OK) break;
+        if ((st = feed(i + kFeedDepth, per_chunk)) != NDI_OK) break;
+        if (cnt > 0) {
+            if ((st = grow(&ws->d_out[slot], &ws->d_out_cap[slot], chunk_bytes < total ? chunk_bytes : total)) != NDI_OK) break;
+            const void* c0 = (const unsigned char*)dq0 + (size_t)lo * he.es;
+            const void* c1 = dq1 ? (const unsigned char*)dq1 + (size_t)lo * he.es : nullptr;
+            if ((st = launch(c0, c1, cnt, ws->d_out[slot], nullptr, ws->s[slot])) != NDI_OK) break;
+            cudaError_t ce = cudaMemcpyAsync((unsigned char*)he.out + (size_t)lo * row, ws->d_out[slot], (size_t)cnt * row,
+                                             cudaMemcpyDeviceToHost, ws->s[slot]);
+            if (ce != cudaSuccess) { st = cuda_fail(ce, "copy-out"); break; }
+        }
+        if (cnt < full) break;                                   // the reference stopped inside this chunk
     }
+    if (st != NDI_OK) { drain(); return st; }
+    if (streaming) CK(cudaStreamSynchronize(ws->s_in));
     CK(cudaStreamSynchronize(ws->s[0]));
     CK(cudaStreamSynchronize(ws->s[1]));
     return NDI_OK;
