@@ -186,12 +186,19 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
  *                         column (csrc/ndi_rowsplit.cu); different rounding, inside north_star's 1e-12 (f64) /
  *                         1e-5 (f32) bars, bit-identical to the oracle's specification of the same scheme.
  *                         levels == 0 lets the library choose; a request is capped so every system keeps two rows.
+ *   NDI_BUILD_PARTITION   rows cut into blocks of `levels` rows (0: 32; 3 .. 32) by single separator rows: every
+ *                         (block, column) pair is solved in registers, the separators' equations form a system
+ *                         `levels` times shorter that is treated the same way (csrc/ndi_partition.cu); different
+ *                         rounding (fused multiply-adds), inside the same bars, bit-identical to the oracle's
+ *                         specification of the same scheme.
  *   NDI_BUILD_AUTO        row-split for systems of 2048 rows or more with fewer than 8192 columns (where the serial
  *                         chains bind), the reference's order otherwise (default).
- * ndi_interp1d_build_info reports the depth the current coefficients were built with (0: reference order). */
+ * ndi_interp1d_build_info reports how the current coefficients were built: 0 reference order, L > 0 row-split with L
+ * levels, -m < 0 partition with blocks of m rows. */
 #define NDI_BUILD_AUTO 0
 #define NDI_BUILD_SEQUENTIAL 1
 #define NDI_BUILD_ROWSPLIT 2
+#define NDI_BUILD_PARTITION 3
 ndi_status ndi_interp1d_set_build_mode(ndi_interp1d* h, int32_t mode, int32_t levels);
 ndi_status ndi_interp1d_build_info(const ndi_interp1d* h, int32_t* rowsplit_levels);
 /* spline coefficient arrays a, b: (n-1, w) each, copied to host (CubicSplineStrategy, cubic_spline.rs:94-102) */

@@ -20,7 +20,7 @@ ASSUME_VALID, DEVICE_POINTERS, BORROW = 1, 2, 4
 SEARCH_AUTO, SEARCH_BINARY_GLOBAL, SEARCH_BINARY_SMEM, SEARCH_UNIFORM_GUESS, SEARCH_BUCKET_LUT, SEARCH_MERGE = 0, 1, 2, 3, 4, 5
 EXTRAP_NO, EXTRAP_YES, EXTRAP_PERIODIC = 0, 1, 2
 BIN_AUTO, BIN_OFF, BIN_ON, BIN_SWEEP = 0, 1, 2, 3
-BUILD_AUTO, BUILD_SEQUENTIAL, BUILD_ROWSPLIT = 0, 1, 2
+BUILD_AUTO, BUILD_SEQUENTIAL, BUILD_ROWSPLIT, BUILD_PARTITION = 0, 1, 2, 3
 ERR_WORD_NONE = 2 ** 64 - 1
 
 DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32,

@@ -349,6 +349,7 @@ static ndi_status build_aids(ndi_dtype dtype, const void* grid, int64_t n, cudaS
 using namespace ndi;
 
 // ---- handles ---------------------------------------------------------------------------------------------
+constexpr int kNotBuilt = INT32_MIN;
 struct ndi_interp1d {
     ndi_dtype dtype; int device; int64_t n, w;
     void* x; void* data; void* a; void* b;
@@ -357,7 +358,7 @@ struct ndi_interp1d {
     int fast_tables = 0;             // f32: every data value is 0 or in [2^-56, 2^30] (hoisted-reciprocal division allowed)
     void* pair = nullptr;            // pair table for thin-row Linear (ndi_eval.cu: rows i, i+1 interleaved), owned
     int build_mode = NDI_BUILD_AUTO, build_levels = 0;   // spline solve: reference order or row-split (ndi_rowsplit.cu)
-    int built_levels = -1;           // depth of the row-split the current coefficients were built with (0: reference order)
+    int built_levels = kNotBuilt;    // how the current coefficients were built: 0 reference order, L > 0 row-split levels, -m partition blocks
     GridAids aids;
     GridMeta meta() const { return aids.meta(x, n, elem_size(dtype), uniform_hint); }
 };
@@ -1031,7 +1032,9 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
     // AUTO: the row-split build where the serial chains bind -- long systems of few columns.  With many columns the
     // reference-order sweeps already fill the machine and the extra passes of the reduction cost more than the
     // shorter chains save (4096 x 16384 f32: 1.21 ms against 1.34 ms; profiles/r02/spline_build.jsonl).
-    if (h->n >= 4 && mode != NDI_BUILD_SEQUENTIAL && (mode == NDI_BUILD_ROWSPLIT || h->w < kRowsplitAutoMaxColumns))
+    if (h->n >= 4 && mode == NDI_BUILD_PARTITION)
+        levels = -partition_block_for(want_levels);           // negative: partition build with blocks of that many rows
+    else if (h->n >= 4 && mode != NDI_BUILD_SEQUENTIAL && (mode == NDI_BUILD_ROWSPLIT || h->w < kRowsplitAutoMaxColumns))
         levels = rowsplit_levels_for(bc_kind == NDI_BC_PERIODIC ? h->n - 2 : h->n, want_levels, mode == NDI_BUILD_ROWSPLIT);
     return dispatch_float(h->dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
@@ -1115,13 +1118,13 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
 }
 
 ndi_status ndi_interp1d_set_build_mode(ndi_interp1d* h, int32_t mode, int32_t levels) {
-    if (!h || mode < NDI_BUILD_AUTO || mode > NDI_BUILD_ROWSPLIT || levels < 0) return fail(NDI_INVALID_ARGUMENT, "bad build mode");
+    if (!h || mode < NDI_BUILD_AUTO || mode > NDI_BUILD_PARTITION || levels < 0) return fail(NDI_INVALID_ARGUMENT, "bad build mode");
     h->build_mode = mode; h->build_levels = levels;
     return NDI_OK;
 }
 ndi_status ndi_interp1d_build_info(const ndi_interp1d* h, int32_t* rowsplit_levels) {
     if (!h || !rowsplit_levels) return fail(NDI_INVALID_ARGUMENT, "null pointer");
-    if (h->built_levels < 0) return fail(NDI_NO_SPLINE, "no spline coefficients built by this handle");
+    if (h->built_levels == kNotBuilt) return fail(NDI_NO_SPLINE, "no spline coefficients built by this handle");
     *rowsplit_levels = h->built_levels;
     return NDI_OK;
 }
@@ -1148,7 +1151,7 @@ ndi_status ndi_interp1d_spline_set_coeffs(ndi_interp1d* h, const void* a, const 
     if (st != NDI_OK) { if (oa) cudaFree(na); if (ob) cudaFree(nb); return st; }
     if (h->owns_coeffs) { cudaFree(h->a); cudaFree(h->b); }
     h->a = na; h->b = nb; h->owns_coeffs = oa;
-    h->built_levels = -1;
+    h->built_levels = kNotBuilt;
     return NDI_OK;
 }
 

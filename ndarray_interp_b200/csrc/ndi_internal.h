@@ -150,5 +150,7 @@ constexpr int kMaxRowsplitLevels = 6;
 constexpr int64_t kRowsplitAutoRows = 2048;
 constexpr int64_t kRowsplitAutoMaxColumns = 8192;   // AUTO keeps the reference order from this many columns on
 int rowsplit_levels_for(int64_t rows, int requested, bool force);
+// partition build (ndi_partition.cu): rows per block for a request (0: the default), passed on as levels = -block
+int partition_block_for(int requested);
 
 }  // namespace ndi

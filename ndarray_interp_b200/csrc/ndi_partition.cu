@@ -1,0 +1,366 @@
+// ndi_partition.cu -- K6, third build mode: block partition of the rows ("substructuring").
+//
+// The reference solves its tridiagonal system with one serial Thomas sweep per column
+// (cubic_spline.rs:678-721 under solve_for_k, :409-674).  The row-split mode (ndi_rowsplit.cu) shortens the chains by
+// 2^L at the price of L elementwise passes with a halo; it is bound by the latency of those passes (profiles/r02).
+// This mode cuts the rows into blocks of m - 1 rows separated by single rows (rows m-1, 2m-1, ...).  With the
+// separators' unknowns known the blocks are independent, so
+//   1. every (block, column) pair is ONE thread that keeps its 31 right-hand sides in registers and runs the two
+//      Thomas recurrences of the block on them (part_local_kernel): g = A_block^-1 rhs;
+//   2. the block's response to its two separators (the "spikes" p = A_block^-1 low[first] e_first,
+//      q = A_block^-1 up[last] e_last) depends on x only and is formed once per block (part_factor_kernel);
+//   3. the separators' equations  -low[s] p[s-1] k[s-m] + (mid[s] - low[s] q[s-1] - up[s] p[s+1]) k[s]
+//      - up[s] q[s+1] k[s+m] = rhs[s] - low[s] g[s-1] - up[s] g[s+1]  are again a tridiagonal system with a matrix
+//      shared by all columns, m times shorter: the same three steps are applied to it until at most 4 m rows are
+//      left, which one lane per column solves directly out of shared memory (part_top_kernel);
+//   4. k = g - p k_left - q k_right, elementwise, from the top level down (part_corr_kernel), then a, b as in the
+//      other modes.
+// Every chain is m - 1 = 31 steps of one fused multiply-add (+ one multiplication by a reciprocal formed once per
+// row), the passes move every element of the scratch matrix a fixed number of times, and no pass needs shared memory
+// or a halo.
+//
+// The rounding differs from the reference's elimination order, so this is NOT bit-identical to the reference
+// arithmetic; like the row-split mode it is held bit for bit to the checker's operation-by-operation specification
+// of the same scheme (partition_thomas; tests/test_partition_gpu.py) and to north_star's 1e-12 (f64) / 1e-5 (f32)
+// bars against the reference-order checker.
+#include <map>
+
+#include "ndi_spline.cuh"
+
+namespace ndi {
+
+#define FMA A<T>::fma
+
+constexpr int kPartLevelsMax = 16;
+constexpr int kPartTopMax = 4 * kPartBlockMax;       // rows of the directly solved system
+
+// Level l: a tridiagonal system of `len` rows; its row j lives in row (j + 1) * stride - 1 of the scratch matrix R
+// (level 0: stride 1; the rows of level l + 1 are the separators of level l).  Per level, at fac + off:
+//   FacRow[len] {up, eliminated mid, elimination weight, 1 / eliminated mid} of the block factorisations
+//   low[len] | mid[len] | up[len]   the level's matrix        p[len] | q[len]   the spikes
+struct PartLevel { int len, stride; unsigned long long off; };
+struct PartPlan { int nsplit, m; unsigned long long elems; PartLevel lv[kPartLevelsMax + 1]; };
+
+int partition_block_for(int requested) {
+    if (requested <= 0) return kPartBlockMax;
+    return requested < 3 ? 3 : (requested > kPartBlockMax ? kPartBlockMax : requested);
+}
+
+static PartPlan part_plan(int64_t n, int64_t len, int m) {
+    PartPlan p{};
+    p.m = m;
+    unsigned long long off = (5ull * (unsigned long long)n + 3) & ~3ull;   // [4n, 5n): k2, where the close and a / b kernels look for it
+    long long cur = len, stride = 1;
+    int l = 0;
+    auto put = [&](int at) {
+        p.lv[at] = PartLevel{(int)cur, (int)stride, off};
+        off += (9ull * (unsigned long long)cur + 3) & ~3ull;
+    };
+    while (cur > 4ll * m && l < kPartLevelsMax) { put(l); cur /= m; stride *= m; ++l; }
+    put(l);
+    p.nsplit = l;
+    p.elems = off;
+    return p;
+}
+size_t partition_fac_elems(int64_t n, int block) { return (size_t)part_plan(n, n, block).elems; }
+
+template <class T>
+struct PartArrays {
+    FacRow<T>* fr; T *low, *mid, *up, *p, *q;
+    __host__ __device__ PartArrays(T* facb, const PartLevel& L) {
+        T* b = facb + L.off;
+        fr = reinterpret_cast<FacRow<T>*>(b);
+        low = b + 4 * (size_t)L.len; mid = low + L.len; up = mid + L.len; p = up + L.len; q = p + L.len;
+    }
+};
+
+// matrix row j of level l: level 0 from x (solve_for_k :440-451, :599-669; periodic: the condensed system :512-518),
+// level l >= 1 from the spikes of level l - 1 (step 3 above)
+template <class T>
+__device__ __forceinline__ void part_row(const T* __restrict__ x, int n, int periodic, int lk, int rk, const PartPlan& pl,
+                                         T* facb, int l, int j, T& low, T& mid, T& up) {
+    if (l == 0) {
+        if (periodic) matrix_row_periodic<T>(x, n, j, up, mid, low); else matrix_row<T>(x, n, j, lk, rk, false, up, mid, low);
+        return;
+    }
+    const PartLevel& pv = pl.lv[l - 1];
+    const PartArrays<T> a(facb, pv);
+    const int s = j * pl.m + pl.m - 1, lastL = s - 1, firstR = s + 1;
+    const bool right = firstR < pv.len;
+    const T ls = a.low[s], us = a.up[s];
+    low = -MUL(ls, a.p[lastL]);
+    T md = FMA(-ls, a.q[lastL], a.mid[s]);
+    if (right) md = FMA(-us, a.p[firstR], md);
+    mid = md;
+    up = right ? -MUL(us, a.q[firstR]) : (T)0;
+}
+template <class T>
+__device__ __forceinline__ T part_rhs2(const T* __restrict__ x, int n, int len, int j) {          // :535-538
+    const T dx0 = SUB(x[1], x[0]), dx_3 = SUB(x[n - 3], x[n - 4]);
+    return j == 0 ? -dx0 : (j == len - 1 ? -dx_3 : (T)0);
+}
+
+// One thread per block of a split level: the block's matrix rows (and its separator's), the Thomas factors of the
+// block (:690-692 with the division by the eliminated diagonal kept as a reciprocal), the two spikes.
+template <class T>
+__global__ void __launch_bounds__(64) part_factor_kernel(const T* __restrict__ x, int n, int periodic, int lk, int rk,
+                                                         const PartPlan pl, int l, T* fac, size_t fac_stride) {
+    if (gridDim.y > 1) { lk = ind_kind(blockIdx.y / 3); rk = ind_kind(blockIdx.y % 3); }
+    T* facb = fac + blockIdx.y * fac_stride;
+    const PartLevel L = pl.lv[l];
+    const int m = pl.m, P = L.len / m, tail = L.len - P * m, nblk = P + (tail > 0 ? 1 : 0);
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c >= nblk) return;
+    const int first = c * m, cnt = c < P ? m - 1 : tail, rows = c < P ? m : tail;
+    const PartArrays<T> a(facb, L);
+    T lo[kPartBlockMax], mi[kPartBlockMax], uu[kPartBlockMax], wl[kPartBlockMax], rm[kPartBlockMax], f[kPartBlockMax];
+    for (int t = 0; t < rows; ++t) {
+        part_row<T>(x, n, periodic, lk, rk, pl, facb, l, first + t, lo[t], mi[t], uu[t]);
+        a.low[first + t] = lo[t]; a.mid[first + t] = mi[t]; a.up[first + t] = uu[t];
+        if (l == 0 && periodic) facb[4 * (size_t)n + first + t] = part_rhs2<T>(x, n, L.len, first + t);
+    }
+    const T one = (T)1;
+    T mp = mi[0];
+    wl[0] = (T)0; rm[0] = DIV(one, mp);
+    for (int t = 1; t < cnt; ++t) {
+        wl[t] = DIV(lo[t], mp);
+        mp = FMA(-wl[t], uu[t - 1], mi[t]);
+        rm[t] = DIV(one, mp);
+    }
+    for (int t = 0; t < cnt; ++t) a.fr[first + t] = FacRow<T>{uu[t], (T)0, wl[t], rm[t]};
+    if (c < P) a.fr[first + m - 1] = FacRow<T>{(T)0, (T)0, (T)0, (T)0};
+    // p = A^-1 (low[first] e_first)
+    f[0] = lo[0];
+    for (int t = 1; t < cnt; ++t) f[t] = -MUL(wl[t], f[t - 1]);
+    T v = MUL(f[cnt - 1], rm[cnt - 1]);
+    a.p[first + cnt - 1] = v;
+    for (int t = cnt - 2; t >= 0; --t) { v = MUL(FMA(-uu[t], v, f[t]), rm[t]); a.p[first + t] = v; }
+    // q = A^-1 (up[last] e_last)
+    v = MUL(uu[cnt - 1], rm[cnt - 1]);
+    a.q[first + cnt - 1] = v;
+    for (int t = cnt - 2; t >= 0; --t) { v = MUL(-MUL(uu[t], v), rm[t]); a.q[first + t] = v; }
+    if (c < P) { a.p[first + m - 1] = (T)0; a.q[first + m - 1] = (T)0; }
+}
+
+// The last level (at most kPartTopMax rows): rows formed by all threads, the elimination by one.
+template <class T>
+__global__ void __launch_bounds__(kPartTopMax) part_top_factor_kernel(const T* __restrict__ x, int n, int periodic, int lk, int rk,
+                                                                     const PartPlan pl, T* fac, size_t fac_stride) {
+    __shared__ T sl[kPartTopMax], sm[kPartTopMax], su[kPartTopMax];
+    if (gridDim.y > 1) { lk = ind_kind(blockIdx.y / 3); rk = ind_kind(blockIdx.y % 3); }
+    T* facb = fac + blockIdx.y * fac_stride;
+    const int l = pl.nsplit;
+    const PartLevel L = pl.lv[l];
+    const PartArrays<T> a(facb, L);
+    const int j = threadIdx.x;
+    if (j < L.len) {
+        T lo, mi, uu;
+        part_row<T>(x, n, periodic, lk, rk, pl, facb, l, j, lo, mi, uu);
+        sl[j] = lo; sm[j] = mi; su[j] = uu;
+        a.low[j] = lo; a.mid[j] = mi; a.up[j] = uu;
+        if (l == 0 && periodic) facb[4 * (size_t)n + j] = part_rhs2<T>(x, n, L.len, j);
+    }
+    __syncthreads();
+    if (j == 0) {
+        const T one = (T)1;
+        T mp = sm[0];
+        a.fr[0] = FacRow<T>{su[0], (T)0, (T)0, DIV(one, mp)};
+        for (int i = 1; i < L.len; ++i) {
+            const T w = DIV(sl[i], mp);
+            mp = FMA(-w, su[i - 1], sm[i]);
+            a.fr[i] = FacRow<T>{su[i], (T)0, w, DIV(one, mp)};
+        }
+    }
+}
+
+// ---- per column -------------------------------------------------------------------------------------------------
+// Individual boundaries: a column's matrix is one of nine (ndi_spline.cuh)
+__device__ __forceinline__ int part_group(const int32_t* __restrict__ lks, const int32_t* __restrict__ rks, long long col) {
+    auto var = [](int k) { return k == SB_NAK ? 0 : ((k == SB_FIRST || k == SB_CLAMPED) ? 1 : 2); };
+    return 3 * var(lks[col]) + var(rks[col]);
+}
+
+enum { PART_SRC_R = 0, PART_SRC_LOWER = 1 };
+// right-hand side of row j of level l for one column: level 0 reads it from R (written by the right-hand-side
+// kernel), level l >= 1 forms it from the block solutions g of level l - 1 around the separator (step 3)
+template <class T, int SRC>
+struct PartRhs {
+    const T* R; long long w, col; int stride;       // of level l
+    const T *plow, *pup; int plen, pstride, m;      // level l - 1
+    __device__ __forceinline__ PartRhs(const PartPlan& pl, int l, T* facb, const T* R_, long long w_, long long col_)
+        : R(R_), w(w_), col(col_), stride(pl.lv[l].stride), plow(nullptr), pup(nullptr), plen(0), pstride(0), m(pl.m) {
+        if (SRC == PART_SRC_LOWER) {
+            const PartArrays<T> a(facb, pl.lv[l - 1]);
+            plow = a.low; pup = a.up; plen = pl.lv[l - 1].len; pstride = pl.lv[l - 1].stride;
+        }
+    }
+    __device__ __forceinline__ long long at(int j) const { return ((long long)(j + 1) * stride - 1) * w + col; }
+    __device__ __forceinline__ T operator()(int j) const {
+        if (SRC == PART_SRC_R) return R[at(j)];
+        const int s = j * m + m - 1;
+        const long long rs = at(j), d = (long long)pstride * w;
+        T v = FMA(-__ldg(plow + s), R[rs - d], R[rs]);
+        if (s + 1 < plen) v = FMA(-__ldg(pup + s), R[rs + d], v);
+        return v;
+    }
+};
+
+// One thread per (block, column): g = A_block^-1 rhs, in registers, written over the right-hand sides in R.
+template <class T, int SRC>
+__global__ void __launch_bounds__(128) part_local_kernel(const PartPlan pl, int l, T* fac, size_t fac_stride, T* __restrict__ R,
+                                                         long long w, const int32_t* __restrict__ lks, const int32_t* __restrict__ rks) {
+    const PartLevel L = pl.lv[l];
+    const int m = pl.m, P = L.len / m, tail = L.len - P * m, nblk = P + (tail > 0 ? 1 : 0);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long c64 = gid / w, col = gid - c64 * w;
+    if (c64 >= nblk) return;
+    const int c = (int)c64;
+    T* facb = fac + (lks ? (size_t)part_group(lks, rks, col) * fac_stride : 0);
+    const int first = c * m, cnt = c < P ? m - 1 : tail;
+    const PartRhs<T, SRC> rhs(pl, l, facb, R, w, col);
+    const FacRow<T>* fr = PartArrays<T>(facb, L).fr + first;
+    T v[kPartBlockMax - 1];
+#pragma unroll
+    for (int t = 0; t < kPartBlockMax - 1; ++t) v[t] = t < cnt ? rhs(first + t) : (T)0;
+    if (SRC == PART_SRC_LOWER && c < P) R[rhs.at(first + m - 1)] = rhs(first + m - 1);   // the separator's own right-hand side, for the level above
+    // forward (:698) and backward (:704-720) recurrences of the block; the factors are warp-uniform loads out of L1
+#pragma unroll
+    for (int t = 1; t < kPartBlockMax - 1; ++t)
+        if (t < cnt) v[t] = FMA(-ld_fac<T>(fr + t).wl, v[t - 1], v[t]);
+    T nxt = (T)0;
+#pragma unroll
+    for (int t = kPartBlockMax - 2; t >= 0; --t) {
+        if (t < cnt) {
+            const FacRow<T> f = ld_fac<T>(fr + t);
+            const T val = MUL(t == cnt - 1 ? v[t] : FMA(-f.up, nxt, v[t]), f.rmid);
+            R[rhs.at(first + t)] = val;
+            nxt = val;
+        }
+    }
+}
+
+// The last level: a block takes 32 columns; all its threads form the right-hand sides into shared memory, one lane per
+// column runs the two recurrences there, all threads write k back.
+template <class T>
+__global__ void __launch_bounds__(256) part_top_kernel(const PartPlan pl, T* fac, size_t fac_stride, T* __restrict__ R, long long w,
+                                                       const int32_t* __restrict__ lks, const int32_t* __restrict__ rks) {
+    __shared__ T tile[kPartTopMax][33];
+    const int l = pl.nsplit;
+    const PartLevel L = pl.lv[l];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const long long col = (long long)blockIdx.x * 32 + cx;
+    const bool live = col < w;
+    T* facb = fac + ((lks && live) ? (size_t)part_group(lks, rks, col) * fac_stride : 0);
+    const FacRow<T>* fr = PartArrays<T>(facb, L).fr;
+    if (live) {
+        if (l == 0) { const PartRhs<T, PART_SRC_R> rhs(pl, l, facb, R, w, col); for (int j = ry; j < L.len; j += 8) tile[j][cx] = rhs(j); }
+        else { const PartRhs<T, PART_SRC_LOWER> rhs(pl, l, facb, R, w, col); for (int j = ry; j < L.len; j += 8) tile[j][cx] = rhs(j); }
+    }
+    __syncthreads();
+    if (ry == 0 && live) {
+        T prev = tile[0][cx];
+        for (int i = 1; i < L.len; ++i) { prev = FMA(-ld_fac<T>(fr + i).wl, prev, tile[i][cx]); tile[i][cx] = prev; }
+        T k = MUL(prev, ld_fac<T>(fr + L.len - 1).rmid);
+        tile[L.len - 1][cx] = k;
+        for (int i = L.len - 2; i >= 0; --i) {
+            const FacRow<T> f = ld_fac<T>(fr + i);
+            k = MUL(FMA(-f.up, k, tile[i][cx]), f.rmid);
+            tile[i][cx] = k;
+        }
+    }
+    __syncthreads();
+    if (live) {
+        const PartRhs<T, PART_SRC_R> at(pl, l, facb, R, w, col);
+        for (int j = ry; j < L.len; j += 8) R[at.at(j)] = tile[j][cx];
+    }
+}
+
+// k = g - p k_left - q k_right on the block rows of level l (separator rows hold their final k already)
+template <class T>
+__global__ void __launch_bounds__(256) part_corr_kernel(const PartPlan pl, int l, T* fac, size_t fac_stride, T* __restrict__ R, long long w,
+                                                        const int32_t* __restrict__ lks, const int32_t* __restrict__ rks) {
+    const PartLevel L = pl.lv[l];
+    const int m = pl.m, P = L.len / m;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long j64 = gid / w, col = gid - j64 * w;
+    if (j64 >= L.len) return;
+    const int j = (int)j64, c = j / m;
+    if (c < P && j - c * m == m - 1) return;
+    T* facb = fac + (lks ? (size_t)part_group(lks, rks, col) * fac_stride : 0);
+    const PartArrays<T> a(facb, L);
+    const PartRhs<T, PART_SRC_R> at(pl, l, facb, R, w, col);
+    const T kl = c > 0 ? R[at.at(c * m - 1)] : (T)0, kr = c < P ? R[at.at(c * m + m - 1)] : (T)0;
+    const long long o = at.at(j);
+    R[o] = FMA(-__ldg(a.q + j), kr, FMA(-__ldg(a.p + j), kl, R[o]));
+}
+
+template <class T>
+static cudaError_t part_solve(const PartPlan& pl, T* fac, size_t fac_stride, T* R, long long w, const int32_t* lk, const int32_t* rk,
+                              cudaStream_t st) {
+    cudaError_t e;
+    for (int l = 0; l < pl.nsplit; ++l) {
+        const PartLevel& L = pl.lv[l];
+        const long long nblk = L.len / pl.m + (L.len % pl.m ? 1 : 0);
+        const long long blocks = (nblk * w + 127) / 128;
+        if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
+        if (l == 0) part_local_kernel<T, PART_SRC_R><<<(unsigned)blocks, 128, 0, st>>>(pl, l, fac, fac_stride, R, w, lk, rk);
+        else part_local_kernel<T, PART_SRC_LOWER><<<(unsigned)blocks, 128, 0, st>>>(pl, l, fac, fac_stride, R, w, lk, rk);
+        count_launch();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    part_top_kernel<T><<<(unsigned)((w + 31) / 32), 256, 0, st>>>(pl, fac, fac_stride, R, w, lk, rk);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    for (int l = pl.nsplit - 1; l >= 0; --l) {
+        const long long blocks = ((long long)pl.lv[l].len * w + 255) / 256;
+        if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
+        part_corr_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(pl, l, fac, fac_stride, R, w, lk, rk);
+        count_launch();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// n >= 4.  scratch: ngroups * partition_fac_elems(n, block) elements of factorisations, then R (n x w).
+template <class T>
+cudaError_t launch_partition_build(const T* x, int64_t n, const T* data, int64_t w, int bc_kind, int block, const int32_t* lk,
+                                   const T* lv, const int32_t* rk, const T* rv, T* a, T* b, T* scratch, unsigned long long* err,
+                                   cudaStream_t st) {
+    const int periodic = bc_kind == BC_PERIODIC;
+    const bool individual = bc_kind == BC_INDIVIDUAL;
+    Side<T> l{SB_NAK, (T)0}, r{SB_NAK, (T)0};
+    if (bc_kind == BC_NATURAL) l = r = Side<T>{SB_NATURAL, (T)0};
+    if (bc_kind == BC_CLAMPED) l = r = Side<T>{SB_CLAMPED, (T)0};
+    const Side<T> ls = specialize(l), rs = specialize(r);
+    const int64_t len = periodic ? n - 2 : n;
+    const PartPlan pl = part_plan(n, len, block);
+    if (pl.lv[pl.nsplit].len > kPartTopMax) return cudaErrorInvalidConfiguration;
+    const size_t fac_stride = partition_fac_elems(n, block);
+    const int ngroups = individual ? 9 : 1;
+    T* fac = scratch;
+    T* R = scratch + (size_t)ngroups * fac_stride;
+    cudaError_t e;
+    // matrix side: depends on x only
+    for (int lvl = 0; lvl < pl.nsplit; ++lvl) {
+        const int nblk = pl.lv[lvl].len / pl.m + (pl.lv[lvl].len % pl.m ? 1 : 0);
+        part_factor_kernel<T><<<dim3((unsigned)((nblk + 63) / 64), ngroups), 64, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, pl, lvl, fac, fac_stride);
+        count_launch();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    part_top_factor_kernel<T><<<dim3(1, ngroups), kPartTopMax, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, pl, fac, fac_stride);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // periodic: the shared second solution k2 (:535-550) is one more column through the same solve, in place at fac + 4n
+    if (periodic && (e = part_solve<T>(pl, fac, fac_stride, fac + 4 * (size_t)n, 1, nullptr, nullptr, st)) != cudaSuccess) return e;
+    if ((e = launch_spline_rhs<T>(x, (int)n, data, (long long)w, periodic, l, r, R, err, individual ? lk : nullptr, lv, rk, rv, st)) != cudaSuccess) return e;
+    if ((e = part_solve<T>(pl, fac, fac_stride, R, (long long)w, individual ? lk : nullptr, rk, st)) != cudaSuccess) return e;
+    if (periodic && (e = launch_spline_periodic_close<T>(x, (int)n, (long long)w, fac, R, st)) != cudaSuccess) return e;
+    return launch_spline_ab<T>(x, (int)n, data, (long long)w, periodic, fac, R, a, b, nullptr, st);
+}
+
+template cudaError_t launch_partition_build<float>(const float*, int64_t, const float*, int64_t, int, int, const int32_t*, const float*,
+                                                   const int32_t*, const float*, float*, float*, float*, unsigned long long*, cudaStream_t);
+template cudaError_t launch_partition_build<double>(const double*, int64_t, const double*, int64_t, int, int, const int32_t*, const double*,
+                                                    const int32_t*, const double*, double*, double*, double*, unsigned long long*, cudaStream_t);
+
+}  // namespace ndi

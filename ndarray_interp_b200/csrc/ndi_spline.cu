@@ -583,7 +583,7 @@ template <class T>
 size_t spline_scratch_elems(int64_t n, int64_t w, int bc_kind, int levels) {
     // factorisation(s) (FacRow[n] + k2[n] (+ the row-split coefficients), padded) + the matrix R;
     // Individual: nine factorisations (n < 4: a diagonal per column)
-    const size_t fac = levels > 0 ? rowsplit_fac_elems(n, levels) : seq_fac_elems(n);
+    const size_t fac = levels > 0 ? rowsplit_fac_elems(n, levels) : (levels < 0 ? partition_fac_elems(n, -levels) : seq_fac_elems(n));
     if (bc_kind == BC_INDIVIDUAL) return n < 4 ? (size_t)n * (size_t)w : 9 * fac + (size_t)n * (size_t)w;
     return fac + (size_t)n * (size_t)w;
 }
@@ -629,6 +629,15 @@ cudaError_t launch_spline_ab(const T* x, int n, const T* y, long long w, int per
 }
 
 template <class T>
+cudaError_t launch_spline_rhs(const T* x, int n, const T* y, long long w, int periodic, Side<T> left, Side<T> right, T* R,
+                              unsigned long long* err, const int32_t* lks, const T* lvs, const int32_t* rks, const T* rvs,
+                              cudaStream_t st) {
+    spline_rhs_kernel<T><<<row_group_grid(w, periodic ? n - 1 : n), 256, 0, st>>>(x, n, y, w, periodic, left, right, R, err, lks, lvs, rks, rvs, nullptr);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <class T>
 cudaError_t launch_spline_periodic_close(const T* x, int n, long long w, const T* fac, T* R, cudaStream_t st) {
     spline_periodic_close_kernel<T><<<(int)((w + 255) / 256), 256, 0, st>>>(x, n, w, fac, R);
     count_launch();
@@ -636,6 +645,7 @@ cudaError_t launch_spline_periodic_close(const T* x, int n, long long w, const T
 }
 
 // levels == 0: the reference's elimination order (coefficients bit-identical to the reference arithmetic);
+// levels < 0: partition build with blocks of -levels rows (ndi_partition.cu);
 // levels > 0: row-split build -- `levels` steps of parallel cyclic reduction, then 2^levels interleaved systems
 // per column (ndi_rowsplit.cu); the caller has checked that the systems keep at least two rows.
 template <class T>
@@ -643,6 +653,9 @@ cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w,
                                 const T* lv, const int32_t* rk, const T* rv, const int32_t* pos, const int64_t* group_count,
                                 int levels, T* a, T* b, T* scratch, unsigned long long* err, cudaStream_t st) {
     if (w <= 0) return cudaSuccess;
+    if (levels < 0 && n >= 4)                                // partition build (ndi_partition.cu), blocks of -levels rows
+        return launch_partition_build<T>(x, n, data, w, bc_kind, -levels, lk, lv, rk, rv, a, b, scratch, err, st);
+    if (levels < 0) levels = 0;
     // few columns: small blocks so that more SMs take part; many columns: 128-thread blocks
     const int block = (w <= 32ll * 2 * device_info().sm_count) ? 32 : 128;
     const int grid = (int)((w + block - 1) / block);
@@ -709,6 +722,9 @@ cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w,
     template cudaError_t launch_spline_ab<T>(const T*, int, const T*, long long, int, const T*, const T*, T*, T*,            \
                                              const int32_t*, cudaStream_t);                                                  \
     template cudaError_t launch_spline_periodic_close<T>(const T*, int, long long, const T*, T*, cudaStream_t);              \
+    template cudaError_t launch_spline_rhs<T>(const T*, int, const T*, long long, int, Side<T>, Side<T>, T*,                \
+                                              unsigned long long*, const int32_t*, const T*, const int32_t*, const T*,        \
+                                              cudaStream_t);                                                                  \
     template size_t spline_scratch_elems<T>(int64_t, int64_t, int, int);
 NDI_INST_SPLINE(float)
 NDI_INST_SPLINE(double)

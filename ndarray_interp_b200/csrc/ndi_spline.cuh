@@ -146,6 +146,21 @@ cudaError_t launch_spline_ab(const T* x, int n, const T* y, long long w, int per
 template <class T>
 cudaError_t launch_spline_periodic_close(const T* x, int n, long long w, const T* fac, T* R, cudaStream_t st);
 
+template <class T>
+cudaError_t launch_spline_rhs(const T* x, int n, const T* y, long long w, int periodic, Side<T> left, Side<T> right, T* R,
+                              unsigned long long* err, const int32_t* lks, const T* lvs, const int32_t* rks, const T* rvs,
+                              cudaStream_t st);
+
+// partition build (ndi_partition.cu): blocks of `block` rows (separator included, 3 .. kPartBlockMax) solved in registers,
+// the separators' system recursively; right-hand sides, periodic close and a / b are the kernels above
+constexpr int kPartBlockMax = 32;
+int partition_block_for(int requested);
+size_t partition_fac_elems(int64_t n, int block);
+template <class T>
+cudaError_t launch_partition_build(const T* x, int64_t n, const T* data, int64_t w, int bc_kind, int block, const int32_t* lk,
+                                   const T* lv, const int32_t* rk, const T* rv, T* a, T* b, T* scratch, unsigned long long* err,
+                                   cudaStream_t st);
+
 // row-split build (ndi_rowsplit.cu): factorisation with `levels` steps of cyclic reduction, right-hand sides
 // reduced in shared memory; the sweeps, the periodic close and a / b are the kernels above
 size_t rowsplit_fac_elems(int64_t n, int levels);

@@ -80,11 +80,12 @@ class DeviceInterp1D:
 
     def set_build_mode(self, mode, levels=0):
         """how spline_build solves the tridiagonal system: L.BUILD_AUTO / BUILD_SEQUENTIAL (the reference's order,
-        bit-identical coefficients) / BUILD_ROWSPLIT (`levels` steps of cyclic reduction, 0: library's choice)"""
+        bit-identical coefficients) / BUILD_ROWSPLIT (`levels` steps of cyclic reduction, 0: library's choice) /
+        BUILD_PARTITION (blocks of `levels` rows, 0: 32)"""
         L.check(self.lib.ndi_interp1d_set_build_mode(self.h, int(mode), int(levels)))
 
     def build_levels(self):
-        """row-split depth the current coefficients were built with (0: the reference's order)"""
+        """how the current coefficients were built: 0 the reference's order, L > 0 row-split levels, -m partition blocks"""
         lv = C.c_int32(-1)
         L.check(self.lib.ndi_interp1d_build_info(self.h, C.byref(lv)))
         return lv.value

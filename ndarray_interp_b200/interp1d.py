@@ -192,9 +192,10 @@ class CubicSpline(Interp1DStrategyBuilder):
     def solver(self, mode, levels=0):
         """NOT in the reference (device-side knob, include/ndi_b200.h: ndi_interp1d_set_build_mode): "auto",
         "sequential" -- the reference's elimination order, coefficients bit-identical to its arithmetic -- or
-        "rowsplit" -- parallel cyclic reduction + Thomas, `levels` reduction steps (0: the library's choice)."""
-        self._solver = ({"auto": L.BUILD_AUTO, "sequential": L.BUILD_SEQUENTIAL, "rowsplit": L.BUILD_ROWSPLIT}[mode],
-                        int(levels))
+        "rowsplit" -- parallel cyclic reduction + Thomas, `levels` reduction steps (0: the library's choice) -- or
+        "partition" -- blocks of `levels` rows (0: 32) solved in registers, the separator rows' system recursively."""
+        self._solver = ({"auto": L.BUILD_AUTO, "sequential": L.BUILD_SEQUENTIAL, "rowsplit": L.BUILD_ROWSPLIT,
+                         "partition": L.BUILD_PARTITION}[mode], int(levels))
         return self
 
     def extrapolate(self, extrapolate):
@@ -260,7 +261,8 @@ class CubicSplineStrategy(Interp1DStrategy):
                 "for periodic boundary condition the first and last value must be equal. " + msg)
 
     def rowsplit_levels(self, interpolator):
-        """depth of the row-split the coefficients were built with (0: the reference's elimination order)"""
+        """how the coefficients were built (ndi_interp1d_build_info): 0 the reference's elimination order, L > 0
+        row-split with L levels, -m < 0 partition with blocks of m rows"""
         lv = C.c_int32(-1)
         L.check(L.load().ndi_interp1d_build_info(interpolator._handle(), C.byref(lv)))
         return lv.value

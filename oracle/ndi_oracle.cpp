@@ -268,6 +268,101 @@ void rowsplit_thomas(T* k, const T* a_up, const T* a_mid, const T* a_low, const 
             for (int64_t c = 0; c < w; ++c) k[(j + t * s) * w + c] = sk[t * w + c];
     }
 }
+// Partition (substructuring) variant of the solve -- like rowsplit_thomas NOT the reference's order, but the
+// operation-by-operation specification of the third build mode (csrc/ndi_partition.cu, NDI_BUILD_PARTITION), compared
+// with the kernels bit for bit.  The rows are cut into blocks of m-1 rows separated by single rows (rows m-1, 2m-1, ...):
+// with the separators' unknowns known the blocks are independent, so every block is solved on its own -- for the
+// right-hand side (g) and for its two couplings (the "spikes" p, q: the block's response to its left and right
+// separator) -- the separators' equations become a tridiagonal system of len / m rows, solved the same way
+// (recursively; directly once it has at most `top` rows), and k = g - p k_left - q k_right.  The matrix work (block
+// factorisations, spikes, reduced matrices) depends on x only and is shared by all columns.  Every multiply-add below is
+// ONE fused operation (std::fma), divisions by an eliminated diagonal are multiplications by its IEEE reciprocal.
+template <class T>
+void partition_thomas(T* k, const T* up, const T* mid, const T* low, const T* rhs, int64_t len, int64_t w, int32_t m,
+                      int32_t top) {
+    const T one = (T)1, zero = (T)0;
+    auto solve_block = [&](int64_t first, int64_t cnt, std::vector<T>& wl, std::vector<T>& rm) {   // Thomas factors of rows [first, first + cnt)
+        T mp = mid[first];
+        wl[first] = zero; rm[first] = one / mp;
+        for (int64_t i = first + 1; i < first + cnt; ++i) {
+            wl[i] = low[i] / mp;
+            mp = std::fma(-wl[i], up[i - 1], mid[i]);
+            rm[i] = one / mp;
+        }
+    };
+    std::vector<T> wl((size_t)len, zero), rm((size_t)len, zero);
+    if (len <= top) {                                                                          // direct
+        solve_block(0, len, wl, rm);
+        for (int64_t c = 0; c < w; ++c) {
+            std::vector<T> f((size_t)len);
+            f[0] = rhs[c];
+            for (int64_t i = 1; i < len; ++i) f[i] = std::fma(-wl[i], f[i - 1], rhs[i * w + c]);
+            T kr = f[len - 1] * rm[len - 1];
+            k[(len - 1) * w + c] = kr;
+            for (int64_t i = len - 2; i >= 0; --i) { kr = std::fma(-up[i], kr, f[i]) * rm[i]; k[i * w + c] = kr; }
+        }
+        return;
+    }
+    const int64_t P = len / m;                                   // separators s_c = c m + m - 1, c < P
+    const int64_t tail = len - P * m;                            // rows after the last separator
+    const int64_t nblk = P + (tail > 0 ? 1 : 0);
+    std::vector<T> p((size_t)len, zero), q((size_t)len, zero), g((size_t)len * w, zero);
+    for (int64_t c = 0; c < nblk; ++c) {
+        const int64_t first = c * m, cnt = c < P ? m - 1 : tail, last = first + cnt - 1;
+        solve_block(first, cnt, wl, rm);
+        {   // p = A^-1 (low[first] e_first)
+            std::vector<T> f((size_t)cnt);
+            f[0] = low[first];
+            for (int64_t t = 1; t < cnt; ++t) f[t] = -(wl[first + t] * f[t - 1]);
+            T v = f[cnt - 1] * rm[last];
+            p[last] = v;
+            for (int64_t t = cnt - 2; t >= 0; --t) { v = std::fma(-up[first + t], v, f[t]) * rm[first + t]; p[first + t] = v; }
+        }
+        {   // q = A^-1 (up[last] e_last)
+            T v = up[last] * rm[last];
+            q[last] = v;
+            for (int64_t t = cnt - 2; t >= 0; --t) { v = -(up[first + t] * v) * rm[first + t]; q[first + t] = v; }
+        }
+        for (int64_t col = 0; col < w; ++col) {                  // g = A^-1 rhs
+            std::vector<T> f((size_t)cnt);
+            f[0] = rhs[first * w + col];
+            for (int64_t t = 1; t < cnt; ++t) f[t] = std::fma(-wl[first + t], f[t - 1], rhs[(first + t) * w + col]);
+            T v = f[cnt - 1] * rm[last];
+            g[last * w + col] = v;
+            for (int64_t t = cnt - 2; t >= 0; --t) { v = std::fma(-up[first + t], v, f[t]) * rm[first + t]; g[(first + t) * w + col] = v; }
+        }
+    }
+    // the separators' equations
+    std::vector<T> rlow((size_t)P), rmid((size_t)P), rup((size_t)P), rrhs((size_t)P * w), ks((size_t)P * w);
+    for (int64_t c = 0; c < P; ++c) {
+        const int64_t s = c * m + m - 1, lastL = s - 1, firstR = s + 1;
+        const bool right = firstR < len;
+        rlow[c] = -(low[s] * p[lastL]);
+        T md = std::fma(-low[s], q[lastL], mid[s]);
+        if (right) md = std::fma(-up[s], p[firstR], md);
+        rmid[c] = md;
+        rup[c] = right ? -(up[s] * q[firstR]) : zero;
+        for (int64_t col = 0; col < w; ++col) {
+            T v = std::fma(-low[s], g[lastL * w + col], rhs[s * w + col]);
+            if (right) v = std::fma(-up[s], g[firstR * w + col], v);
+            rrhs[c * w + col] = v;
+        }
+    }
+    partition_thomas(ks.data(), rup.data(), rmid.data(), rlow.data(), rrhs.data(), P, w, m, top);
+    for (int64_t c = 0; c < nblk; ++c) {
+        const int64_t first = c * m, cnt = c < P ? m - 1 : tail;
+        for (int64_t col = 0; col < w; ++col) {
+            const T kl = c > 0 ? ks[(c - 1) * w + col] : zero, kr = c < P ? ks[c * w + col] : zero;
+            for (int64_t i = first; i < first + cnt; ++i)
+                k[i * w + col] = std::fma(-q[i], kr, std::fma(-p[i], kl, g[i * w + col]));
+            if (c < P) k[(first + m - 1) * w + col] = kr;
+        }
+    }
+}
+// > 0: solve_for_k's solves use partition_thomas with blocks of that many rows (separator included), direct solve from
+// 4 x that many rows down (set by ora_spline_build_partition_* for the duration of one call)
+thread_local int32_t g_partition_block = 0;
+
 // > 0: solve_for_k's full-system solve (:672) uses rowsplit_thomas with that many levels (set by
 // ora_spline_build_rowsplit_* for the duration of one call; periodic: both solves of the condensed system)
 thread_local int32_t g_rowsplit_levels = 0;
@@ -348,7 +443,10 @@ int32_t solve_for_k(T* k, const T* x, const T* data, int64_t len, int64_t w, int
         std::vector<T> k1((size_t)m * w, zero), k2((size_t)m * w, zero);
         {
             std::vector<T> mid1(a_mid.begin(), a_mid.begin() + m), mid2(mid1);
-            if (g_rowsplit_levels > 0) {                          // row-split specification: both solves of the condensed system
+            if (g_partition_block > 0) {                          // partition specification: both solves of the condensed system
+                partition_thomas(k1.data(), a_up.data(), mid1.data(), a_low.data(), rhs1.data(), m, w, g_partition_block, 4 * g_partition_block);
+                partition_thomas(k2.data(), a_up.data(), mid2.data(), a_low.data(), rhs2.data(), m, w, g_partition_block, 4 * g_partition_block);
+            } else if (g_rowsplit_levels > 0) {                   // row-split specification: both solves of the condensed system
                 rowsplit_thomas(k1.data(), a_up.data(), mid1.data(), a_low.data(), rhs1.data(), m, w, g_rowsplit_levels);
                 rowsplit_thomas(k2.data(), a_up.data(), mid2.data(), a_low.data(), rhs2.data(), m, w, g_rowsplit_levels);
             } else {
@@ -415,7 +513,8 @@ int32_t solve_for_k(T* k, const T* x, const T* data, int64_t len, int64_t w, int
     }
     // thomas on the full system (:672); k has row stride ld, so solve into a dense temp
     std::vector<T> kk((size_t)len * w);
-    if (g_rowsplit_levels > 0) rowsplit_thomas(kk.data(), a_up.data(), a_mid.data(), a_low.data(), rhs.data(), len, w, g_rowsplit_levels);
+    if (g_partition_block > 0) partition_thomas(kk.data(), a_up.data(), a_mid.data(), a_low.data(), rhs.data(), len, w, g_partition_block, 4 * g_partition_block);
+    else if (g_rowsplit_levels > 0) rowsplit_thomas(kk.data(), a_up.data(), a_mid.data(), a_low.data(), rhs.data(), len, w, g_rowsplit_levels);
     else thomas(kk.data(), a_up.data(), a_mid.data(), a_low.data(), rhs.data(), len, w);
     for (int64_t i = 0; i < len; ++i)
         for (int64_t c = 0; c < w; ++c) K(i, c) = kk[i * w + c];
@@ -594,6 +693,19 @@ int32_t shard_queries(int64_t nq, int32_t nthreads, int64_t* first_bad, F&& fn) 
         int32_t st = spline_build<T>(x, n, data, w, bc_kind, left_kind, left_val, right_kind,      \
                                      right_val, a, b);                                             \
         g_rowsplit_levels = 0;                                                                     \
+        return st;                                                                                 \
+    }                                                                                              \
+    extern "C" int32_t ora_spline_build_partition_##SFX(const T* x, int64_t n, const T* data,     \
+                                                        int64_t w, int32_t bc_kind,                \
+                                                        const int32_t* left_kind,                  \
+                                                        const T* left_val,                         \
+                                                        const int32_t* right_kind,                 \
+                                                        const T* right_val, int32_t block, T* a,   \
+                                                        T* b) {                                    \
+        g_partition_block = block;                                                                 \
+        int32_t st = spline_build<T>(x, n, data, w, bc_kind, left_kind, left_val, right_kind,      \
+                                     right_val, a, b);                                             \
+        g_partition_block = 0;                                                                     \
         return st;                                                                                 \
     }                                                                                              \
     extern "C" int32_t ora_interp1d_cubic_##SFX(const T* g, int64_t n, const T* data, const T* a, \

@@ -137,9 +137,10 @@ def bc_arrays(bc, w, dtype):
     return kind, lk, lv, rk, rv
 
 
-def spline_build(x, data, bc, rowsplit_levels=0):
-    """rowsplit_levels > 0: the row-split variant of the solve (NOT the reference's order; the specification a
-    future row-split build kernel is compared with -- ndi_oracle.cpp, rowsplit_thomas)"""
+def spline_build(x, data, bc, rowsplit_levels=0, partition_block=0):
+    """rowsplit_levels > 0: the row-split variant of the solve (NOT the reference's order; the specification the
+    row-split build kernels are compared with -- ndi_oracle.cpp, rowsplit_thomas); partition_block > 0: the
+    partition variant with blocks of that many rows (ndi_oracle.cpp, partition_thomas)"""
     x = np.ascontiguousarray(x)
     data = np.ascontiguousarray(data, dtype=x.dtype)
     n = len(x)
@@ -147,6 +148,11 @@ def spline_build(x, data, bc, rowsplit_levels=0):
     kind, lk, lv, rk, rv = bc_arrays(bc, w, x.dtype)
     a = np.zeros((n - 1,) + data.shape[1:], dtype=x.dtype)
     b = np.zeros_like(a)
+    if partition_block:
+        st = getattr(lib(), f"ora_spline_build_partition_{_sfx(x)}")(
+            _p(x), C.c_int64(n), _p(data), C.c_int64(w), C.c_int32(kind), _p(lk), _p(lv), _p(rk), _p(rv),
+            C.c_int32(partition_block), _p(a), _p(b))
+        return st, a, b
     if rowsplit_levels:
         st = getattr(lib(), f"ora_spline_build_rowsplit_{_sfx(x)}")(
             _p(x), C.c_int64(n), _p(data), C.c_int64(w), C.c_int32(kind), _p(lk), _p(lv), _p(rk), _p(rv),
@@ -155,6 +161,11 @@ def spline_build(x, data, bc, rowsplit_levels=0):
     st = getattr(lib(), f"ora_spline_build_{_sfx(x)}")(_p(x), C.c_int64(n), _p(data), C.c_int64(w), C.c_int32(kind),
                                                        _p(lk), _p(lv), _p(rk), _p(rv), _p(a), _p(b))
     return st, a, b
+
+
+def spline_build_as(x, data, bc, build_info):
+    """the specification matching ndi_interp1d_build_info's value: 0 reference order, L > 0 row-split, -m partition"""
+    return spline_build(x, data, bc, rowsplit_levels=max(int(build_info), 0), partition_block=max(-int(build_info), 0))
 
 
 def interp1d_cubic(x, data, a, b, q, extrap_mode, nthreads=0, out=None):

@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
 """K6 timing: CubicSpline coefficient construction for a few table shapes, in both build modes -- the reference's
-elimination order ("sequential") and the row-split PCR + Thomas build at several depths (one JSON line each).
+elimination order ("sequential"), the row-split PCR + Thomas build at several depths and the partition build at several
+block sizes (one JSON line each).
 
-    python scripts/bench_spline_build.py [shape ...] [--levels 1,2,3,4,5,6] [--bc Natural,Periodic]
+    python scripts/bench_spline_build.py [shape ...] [--levels 1,2,3,4,5,6] [--blocks 0,16] [--bc Natural,Periodic]
 """
 import json
 import os
@@ -25,17 +26,21 @@ def main():
     D.set_device(0)
     args = sys.argv[1:]
     levels = [0]
+    blocks = []
     bcs = list(BC)
     only = []
     i = 0
     while i < len(args):
         if args[i] == "--levels":
             levels = [int(v) for v in args[i + 1].split(",")]; i += 2
+        elif args[i] == "--blocks":
+            blocks = [int(v) for v in args[i + 1].split(",")]; i += 2
         elif args[i] == "--bc":
             bcs = args[i + 1].split(","); i += 2
         else:
             only.append(args[i]); i += 1
-    modes = [("sequential", L.BUILD_SEQUENTIAL, 0)] + [("rowsplit", L.BUILD_ROWSPLIT, lv) for lv in levels]
+    modes = ([("sequential", L.BUILD_SEQUENTIAL, 0)] + [("rowsplit", L.BUILD_ROWSPLIT, lv) for lv in levels]
+             + [("partition", L.BUILD_PARTITION, bl) for bl in blocks])
     for name, n, w, dt in SHAPES:
         if only and name not in only:
             continue

@@ -249,3 +249,34 @@ def test_row_split_study_solves_the_same_system_as_the_oracle():
             spl = P.evaluate(x, y, ra2, rb2, q)
             sc = np.maximum(np.abs(seq), np.abs(y).max(axis=0)[None, :])
             assert float((np.abs(spl - seq) / sc).max()) < bar / 10
+
+
+def test_partition_specification_stays_inside_the_bars():
+    """partition_thomas (the operation-by-operation specification of the partition build kernels,
+    csrc/ndi_partition.cu) against the reference-order restatement: every boundary kind, direct solve, one, two and
+    three split levels, tails of every length -- evaluated splines agree to a tenth of north_star's bars, and the
+    f64 result agrees with scipy like the reference-order one does"""
+    from scipy.interpolate import CubicSpline as SciSpline
+    rng = np.random.default_rng(17)
+    ind = {"kind": "Individual", "rows": [
+        {"kind": "Mixed", "left": {"kind": "FirstDeriv", "value": 0.5}, "right": {"kind": "Natural"}},
+        {"kind": "NotAKnot"},
+        {"kind": "Mixed", "left": {"kind": "SecondDeriv", "value": -1.0}, "right": {"kind": "Clamped"}}]}
+    for dt, bar in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        for n, block in ((10, 3), (97, 3), (300, 4), (1000, 5), (1025, 32), (4096, 32), (4127, 32)):
+            x = np.cumsum(rng.uniform(0.5, 1.5, n)).astype(dt)
+            y = rng.normal(size=(n, 3)).astype(dt)
+            yp = y.copy(); yp[-1] = yp[0]
+            q = np.sort(rng.uniform(x[0], x[-1], 1500)).astype(dt)
+            for bc in ({"kind": "Natural"}, {"kind": "NotAKnot"}, {"kind": "Clamped"}, ind, {"kind": "Periodic"}):
+                yy = yp if bc["kind"] == "Periodic" else y
+                st, sa, sb = O.spline_build(x, yy, bc)
+                st2, pa, pb = O.spline_build(x, yy, bc, partition_block=block)
+                assert st == O.ST_OK and st2 == O.ST_OK
+                _, seq, _ = O.interp1d_cubic(x, yy, sa, sb, q, 0)
+                _, par, _ = O.interp1d_cubic(x, yy, pa, pb, q, 0)
+                sc = np.maximum(np.abs(seq), np.abs(yy).max(axis=0)[None, :]).astype(np.float64)
+                assert float((np.abs(par.astype(np.float64) - seq) / sc).max()) < bar / 10, (dt, n, block, bc["kind"])
+                if dt is np.float64 and bc["kind"] == "Natural":
+                    sci = SciSpline(x, yy, bc_type="natural")(q)
+                    assert float((np.abs(par - sci) / sc).max()) < 1e-12
