@@ -5,19 +5,19 @@
 // 2^L at the price of L elementwise passes with a halo; it is bound by the latency of those passes (profiles/r02).
 // This mode cuts the rows into blocks of m - 1 rows separated by single rows (rows m-1, 2m-1, ...).  With the
 // separators' unknowns known the blocks are independent, so
-//   1. every (block, column) pair is ONE thread that keeps its 31 right-hand sides in registers and runs the two
-//      Thomas recurrences of the block on them (part_local_kernel): g = A_block^-1 rhs;
+//   1. every (block, column) pair is ONE thread that forms its right-hand sides from y, keeps them in registers and runs
+//      the two Thomas recurrences of the block on them (part_local_kernel): g = A_block^-1 rhs;
 //   2. the block's response to its two separators (the "spikes" p = A_block^-1 low[first] e_first,
 //      q = A_block^-1 up[last] e_last) depends on x only and is formed once per block (part_factor_kernel);
 //   3. the separators' equations  -low[s] p[s-1] k[s-m] + (mid[s] - low[s] q[s-1] - up[s] p[s+1]) k[s]
 //      - up[s] q[s+1] k[s+m] = rhs[s] - low[s] g[s-1] - up[s] g[s+1]  are again a tridiagonal system with a matrix
 //      shared by all columns, m times shorter: the same three steps are applied to it until at most 4 m rows are
 //      left, which one lane per column solves directly out of shared memory (part_top_kernel);
-//   4. k = g - p k_left - q k_right, elementwise, from the top level down (part_corr_kernel), then a, b as in the
-//      other modes.
-// Every chain is m - 1 = 31 steps of one fused multiply-add (+ one multiplication by a reciprocal formed once per
-// row), the passes move every element of the scratch matrix a fixed number of times, and no pass needs shared memory
-// or a halo.
+//   4. k = g - p k_left - q k_right, elementwise, from the top level down (part_corr_kernel); on level 0 that
+//      correction is part of the kernel that writes a and b (part_ab_kernel), so k itself is never stored.
+// Every chain is m - 1 steps of one fused multiply-add (+ one multiplication by a reciprocal formed once per row); y is
+// read twice, g written and read once, a and b written once; no pass needs a halo.  The matrix work of the upper
+// levels runs on a second stream beside the block solves of level 0.
 //
 // The rounding differs from the reference's elimination order, so this is NOT bit-identical to the reference
 // arithmetic; like the row-split mode it is held bit for bit to the checker's operation-by-operation specification
@@ -32,31 +32,34 @@ namespace ndi {
 #define FMA A<T>::fma
 
 constexpr int kPartLevelsMax = 16;
-constexpr int kPartTopMax = 4 * kPartBlockMax;       // rows of the directly solved system
+constexpr int kPartTopMax = 128;                     // rows of the directly solved system: min(kPartTopMax, 4 m)
 
 // Level l: a tridiagonal system of `len` rows; its row j lives in row (j + 1) * stride - 1 of the scratch matrix R
 // (level 0: stride 1; the rows of level l + 1 are the separators of level l).  Per level, at fac + off:
 //   FacRow[len] {up, eliminated mid, elimination weight, 1 / eliminated mid} of the block factorisations
 //   low[len] | mid[len] | up[len]   the level's matrix        p[len] | q[len]   the spikes
+// fac[0, n): the grid steps dx[i] = x[i+1] - x[i], fac[n, 2n): their reciprocals as Hoisted<T>::rcp forms them,
+// fac[4n, 5n): k2 (periodic), where the close and a / b kernels of ndi_spline.cu look for it.
 struct PartLevel { int len, stride; unsigned long long off; };
 struct PartPlan { int nsplit, m; unsigned long long elems; PartLevel lv[kPartLevelsMax + 1]; };
 
 int partition_block_for(int requested) {
-    if (requested <= 0) return kPartBlockMax;
+    if (requested <= 0) return kPartBlockDefault;
     return requested < 3 ? 3 : (requested > kPartBlockMax ? kPartBlockMax : requested);
 }
+static int part_top_rows(int m) { return 4 * m < kPartTopMax ? 4 * m : kPartTopMax; }
 
 static PartPlan part_plan(int64_t n, int64_t len, int m) {
     PartPlan p{};
     p.m = m;
-    unsigned long long off = (5ull * (unsigned long long)n + 3) & ~3ull;   // [4n, 5n): k2, where the close and a / b kernels look for it
+    unsigned long long off = (5ull * (unsigned long long)n + 3) & ~3ull;
     long long cur = len, stride = 1;
     int l = 0;
     auto put = [&](int at) {
         p.lv[at] = PartLevel{(int)cur, (int)stride, off};
         off += (9ull * (unsigned long long)cur + 3) & ~3ull;
     };
-    while (cur > 4ll * m && l < kPartLevelsMax) { put(l); cur /= m; stride *= m; ++l; }
+    while (cur > part_top_rows(m) && l < kPartLevelsMax) { put(l); cur /= m; stride *= m; ++l; }
     put(l);
     p.nsplit = l;
     p.elems = off;
@@ -99,50 +102,79 @@ __device__ __forceinline__ T part_rhs2(const T* __restrict__ x, int n, int len, 
     const T dx0 = SUB(x[1], x[0]), dx_3 = SUB(x[n - 3], x[n - 4]);
     return j == 0 ? -dx0 : (j == len - 1 ? -dx_3 : (T)0);
 }
-
-// One thread per block of a split level: the block's matrix rows (and its separator's), the Thomas factors of the
-// block (:690-692 with the division by the eliminated diagonal kept as a reciprocal), the two spikes.
+// what every level-0 row leaves behind besides its matrix row: rhs2 of the periodic system, the grid step and its reciprocal
 template <class T>
-__global__ void __launch_bounds__(64) part_factor_kernel(const T* __restrict__ x, int n, int periodic, int lk, int rk,
-                                                         const PartPlan pl, int l, T* fac, size_t fac_stride) {
+__device__ __forceinline__ void part_row_extras(const T* __restrict__ x, int n, int periodic, int len, T* fac0, T* facb, int j) {
+    if (periodic) facb[4 * (size_t)n + j] = part_rhs2<T>(x, n, len, j);
+    if (blockIdx.y == 0 && j + 1 < n) {
+        const T d = SUB(x[j + 1], x[j]);
+        fac0[j] = d; fac0[(size_t)n + j] = Hoisted<T>::rcp(d);
+    }
+}
+
+// One warp per block of a split level: the lanes form the block's matrix rows (and its separator's); lane 0 runs the
+// Thomas elimination of the block (:690-692), a chain of divisions; the reciprocals of the eliminated diagonal are
+// formed by all lanes; lanes 0 and 1 run the two spikes.
+constexpr int kPfWarps = 4;
+template <class T>
+__global__ void __launch_bounds__(32 * kPfWarps) part_factor_kernel(const T* __restrict__ x, int n, int periodic, int lk, int rk,
+                                                                    const PartPlan pl, int l, T* fac, size_t fac_stride) {
+    __shared__ T s_lo[kPfWarps][kPartBlockMax], s_mi[kPfWarps][kPartBlockMax], s_uu[kPfWarps][kPartBlockMax],
+        s_wl[kPfWarps][kPartBlockMax], s_rm[kPfWarps][kPartBlockMax];
     if (gridDim.y > 1) { lk = ind_kind(blockIdx.y / 3); rk = ind_kind(blockIdx.y % 3); }
     T* facb = fac + blockIdx.y * fac_stride;
     const PartLevel L = pl.lv[l];
     const int m = pl.m, P = L.len / m, tail = L.len - P * m, nblk = P + (tail > 0 ? 1 : 0);
-    const int c = blockIdx.x * 64 + threadIdx.x;
-    if (c >= nblk) return;
+    const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kPfWarps + wi;
+    if (c >= nblk) return;                                            // whole warps leave; only warp-level barriers below
     const int first = c * m, cnt = c < P ? m - 1 : tail, rows = c < P ? m : tail;
     const PartArrays<T> a(facb, L);
-    T lo[kPartBlockMax], mi[kPartBlockMax], uu[kPartBlockMax], wl[kPartBlockMax], rm[kPartBlockMax], f[kPartBlockMax];
-    for (int t = 0; t < rows; ++t) {
-        part_row<T>(x, n, periodic, lk, rk, pl, facb, l, first + t, lo[t], mi[t], uu[t]);
-        a.low[first + t] = lo[t]; a.mid[first + t] = mi[t]; a.up[first + t] = uu[t];
-        if (l == 0 && periodic) facb[4 * (size_t)n + first + t] = part_rhs2<T>(x, n, L.len, first + t);
+    T *lo = s_lo[wi], *mi = s_mi[wi], *uu = s_uu[wi], *wl = s_wl[wi], *rm = s_rm[wi];
+    for (int t = lane; t < rows; t += 32) {
+        T vl, vm, vu;
+        part_row<T>(x, n, periodic, lk, rk, pl, facb, l, first + t, vl, vm, vu);
+        lo[t] = vl; mi[t] = vm; uu[t] = vu;
+        a.low[first + t] = vl; a.mid[first + t] = vm; a.up[first + t] = vu;
+        if (l == 0) part_row_extras<T>(x, n, periodic, L.len, fac, facb, first + t);
+        if (t == m - 1) { a.fr[first + t] = FacRow<T>{(T)0, (T)0, (T)0, (T)0}; a.p[first + t] = (T)0; a.q[first + t] = (T)0; }
     }
+    __syncwarp();
+    if (lane == 0) {
+        T mp = mi[0];
+        wl[0] = (T)0;
+        for (int t = 1; t < cnt; ++t) {
+            const T w = DIV(lo[t], mp);
+            mi[t - 1] = mp;                                           // mi[] becomes the eliminated diagonal
+            mp = FMA(-w, uu[t - 1], mi[t]);
+            wl[t] = w;
+        }
+        mi[cnt - 1] = mp;
+    }
+    __syncwarp();
     const T one = (T)1;
-    T mp = mi[0];
-    wl[0] = (T)0; rm[0] = DIV(one, mp);
-    for (int t = 1; t < cnt; ++t) {
-        wl[t] = DIV(lo[t], mp);
-        mp = FMA(-wl[t], uu[t - 1], mi[t]);
-        rm[t] = DIV(one, mp);
+    for (int t = lane; t < cnt; t += 32) {
+        const T r = DIV(one, mi[t]);
+        rm[t] = r;
+        a.fr[first + t] = FacRow<T>{uu[t], mi[t], wl[t], r};
     }
-    for (int t = 0; t < cnt; ++t) a.fr[first + t] = FacRow<T>{uu[t], (T)0, wl[t], rm[t]};
-    if (c < P) a.fr[first + m - 1] = FacRow<T>{(T)0, (T)0, (T)0, (T)0};
-    // p = A^-1 (low[first] e_first)
-    f[0] = lo[0];
-    for (int t = 1; t < cnt; ++t) f[t] = -MUL(wl[t], f[t - 1]);
-    T v = MUL(f[cnt - 1], rm[cnt - 1]);
-    a.p[first + cnt - 1] = v;
-    for (int t = cnt - 2; t >= 0; --t) { v = MUL(FMA(-uu[t], v, f[t]), rm[t]); a.p[first + t] = v; }
-    // q = A^-1 (up[last] e_last)
-    v = MUL(uu[cnt - 1], rm[cnt - 1]);
-    a.q[first + cnt - 1] = v;
-    for (int t = cnt - 2; t >= 0; --t) { v = MUL(-MUL(uu[t], v), rm[t]); a.q[first + t] = v; }
-    if (c < P) { a.p[first + m - 1] = (T)0; a.q[first + m - 1] = (T)0; }
+    __syncwarp();
+    if (lane == 0) {                                                  // p = A^-1 (low[first] e_first); wl[] becomes its forward sweep
+        T f = lo[0];
+        T* fw = s_lo[wi];
+        fw[0] = f;
+        for (int t = 1; t < cnt; ++t) { f = -MUL(wl[t], f); fw[t] = f; }
+        T v = MUL(f, rm[cnt - 1]);
+        a.p[first + cnt - 1] = v;
+        for (int t = cnt - 2; t >= 0; --t) { v = MUL(FMA(-uu[t], v, fw[t]), rm[t]); a.p[first + t] = v; }
+    } else if (lane == 1) {                                           // q = A^-1 (up[last] e_last)
+        T v = MUL(uu[cnt - 1], rm[cnt - 1]);
+        a.q[first + cnt - 1] = v;
+        for (int t = cnt - 2; t >= 0; --t) { v = MUL(-MUL(uu[t], v), rm[t]); a.q[first + t] = v; }
+    }
 }
 
-// The last level (at most kPartTopMax rows): rows formed by all threads, the elimination by one.
+// The last level (at most kPartTopMax rows): rows formed by all threads, the elimination by one, the reciprocals by all.
 template <class T>
 __global__ void __launch_bounds__(kPartTopMax) part_top_factor_kernel(const T* __restrict__ x, int n, int periodic, int lk, int rk,
                                                                      const PartPlan pl, T* fac, size_t fac_stride) {
@@ -158,19 +190,22 @@ __global__ void __launch_bounds__(kPartTopMax) part_top_factor_kernel(const T* _
         part_row<T>(x, n, periodic, lk, rk, pl, facb, l, j, lo, mi, uu);
         sl[j] = lo; sm[j] = mi; su[j] = uu;
         a.low[j] = lo; a.mid[j] = mi; a.up[j] = uu;
-        if (l == 0 && periodic) facb[4 * (size_t)n + j] = part_rhs2<T>(x, n, L.len, j);
+        if (l == 0) part_row_extras<T>(x, n, periodic, L.len, fac, facb, j);
     }
     __syncthreads();
     if (j == 0) {
-        const T one = (T)1;
         T mp = sm[0];
-        a.fr[0] = FacRow<T>{su[0], (T)0, (T)0, DIV(one, mp)};
+        sl[0] = (T)0;
         for (int i = 1; i < L.len; ++i) {
             const T w = DIV(sl[i], mp);
+            sm[i - 1] = mp;
             mp = FMA(-w, su[i - 1], sm[i]);
-            a.fr[i] = FacRow<T>{su[i], (T)0, w, DIV(one, mp)};
+            sl[i] = w;
         }
+        sm[L.len - 1] = mp;
     }
+    __syncthreads();
+    if (j < L.len) a.fr[j] = FacRow<T>{su[j], sm[j], sl[j], DIV((T)1, sm[j])};
 }
 
 // ---- per column -------------------------------------------------------------------------------------------------
@@ -180,9 +215,9 @@ __device__ __forceinline__ int part_group(const int32_t* __restrict__ lks, const
     return 3 * var(lks[col]) + var(rks[col]);
 }
 
-enum { PART_SRC_R = 0, PART_SRC_LOWER = 1 };
-// right-hand side of row j of level l for one column: level 0 reads it from R (written by the right-hand-side
-// kernel), level l >= 1 forms it from the block solutions g of level l - 1 around the separator (step 3)
+enum { PART_SRC_R = 0, PART_SRC_LOWER = 1, PART_SRC_Y = 2 };
+// right-hand side of row j of level l for one column: read from R (PART_SRC_R), or, on level l >= 1, formed from
+// the block solutions g of level l - 1 around the separator (step 3)
 template <class T, int SRC>
 struct PartRhs {
     const T* R; long long w, col; int stride;       // of level l
@@ -196,7 +231,7 @@ struct PartRhs {
     }
     __device__ __forceinline__ long long at(int j) const { return ((long long)(j + 1) * stride - 1) * w + col; }
     __device__ __forceinline__ T operator()(int j) const {
-        if (SRC == PART_SRC_R) return R[at(j)];
+        if (SRC != PART_SRC_LOWER) return R[at(j)];
         const int s = j * m + m - 1;
         const long long rs = at(j), d = (long long)pstride * w;
         T v = FMA(-__ldg(plow + s), R[rs - d], R[rs]);
@@ -205,10 +240,20 @@ struct PartRhs {
     }
 };
 
+// what part_local_kernel<.., PART_SRC_Y> needs to form the right-hand sides of level 0 itself
+template <class T>
+struct PartData {
+    const T* x; const T* y; int n, periodic; Side<T> left, right; const T* lvs; const T* rvs; unsigned long long* err;
+};
+
 // One thread per (block, column): g = A_block^-1 rhs, in registers, written over the right-hand sides in R.
-template <class T, int SRC>
+// PART_SRC_Y (level 0): the right-hand sides are formed here from y (solve_for_k :456-471 interior rows, :599-669 boundary
+// rows, :521-532 periodic), divisions by a grid step through its reciprocal (ndi_device.cuh, Hoisted: the IEEE quotient),
+// and the separator's right-hand side is left in R for the level above.
+template <class T, int SRC, int MAXB>
 __global__ void __launch_bounds__(128) part_local_kernel(const PartPlan pl, int l, T* fac, size_t fac_stride, T* __restrict__ R,
-                                                         long long w, const int32_t* __restrict__ lks, const int32_t* __restrict__ rks) {
+                                                         long long w, const int32_t* __restrict__ lks, const int32_t* __restrict__ rks,
+                                                         const PartData<T> dt) {
     const PartLevel L = pl.lv[l];
     const int m = pl.m, P = L.len / m, tail = L.len - P * m, nblk = P + (tail > 0 ? 1 : 0);
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,17 +264,85 @@ __global__ void __launch_bounds__(128) part_local_kernel(const PartPlan pl, int 
     const int first = c * m, cnt = c < P ? m - 1 : tail;
     const PartRhs<T, SRC> rhs(pl, l, facb, R, w, col);
     const FacRow<T>* fr = PartArrays<T>(facb, L).fr + first;
-    T v[kPartBlockMax - 1];
+    T v[MAXB + 1];
+    if (SRC == PART_SRC_Y) {
+        const int n = dt.n, rows = c < P ? m : tail;
+        const T* ycol = dt.y + col;
+        auto Y = [&](int row) -> T { return __ldg(ycol + (long long)row * w); };
+        // v[j] = y[first - 1 + j], j <= rows + 1 (rows outside the table: 0, they only reach right-hand sides that are
+        // replaced below), then the differences of neighbours in place: v[t] = y[first + t] - y[first + t - 1]
 #pragma unroll
-    for (int t = 0; t < kPartBlockMax - 1; ++t) v[t] = t < cnt ? rhs(first + t) : (T)0;
-    if (SRC == PART_SRC_LOWER && c < P) R[rhs.at(first + m - 1)] = rhs(first + m - 1);   // the separator's own right-hand side, for the level above
+        for (int j = 0; j < MAXB + 1; ++j) {
+            const int gi = first - 1 + j;
+            v[j] = (j <= rows + 1 && gi >= 0 && gi < n) ? Y(gi) : (T)0;
+        }
+        const int gl = first + MAXB;
+        const T ylast = (rows == MAXB && gl < n) ? Y(gl) : (T)0;
+#pragma unroll
+        for (int j = 0; j < MAXB; ++j) v[j] = SUB(v[j + 1], v[j]);
+        v[MAXB] = SUB(ylast, v[MAXB]);
+        // boundary rows of the system, where this thread owns them
+        Side<T> sl = specialize(dt.left), sr = specialize(dt.right);
+        if (lks) { sl = specialize(Side<T>{lks[col], dt.lvs[col]}); sr = specialize(Side<T>{rks[col], dt.rvs[col]}); }
+        const T three = (T)3;
+        T first_rhs = (T)0, last_rhs = (T)0;
+        const bool own_last = !dt.periodic && first + rows == n;
+        if (c == 0) {
+            if (dt.periodic) {
+                const T* x = dt.x;
+                const T dx0 = SUB(x[1], x[0]), dx_1 = SUB(x[n - 1], x[n - 2]);
+                const T y0 = Y(0), yN = Y(n - 1);
+                if (y0 != yN) atomicMin(dt.err, (unsigned long long)col);                         // :499-507
+                const T slope0 = DIV(SUB(Y(1), y0), dx0);                                         // :521
+                const T slope_1 = DIV(SUB(yN, Y(n - 2)), dx_1);                                   // :526
+                first_rhs = MUL(ADD(MUL(slope_1, dx0), MUL(slope0, dx_1)), three);                // :529-530
+            } else {
+                first_rhs = rhs_left<T>(dt.x, sl, Y(0), Y(1), Y(2));
+            }
+        }
+        if (own_last) last_rhs = rhs_right<T>(dt.x, n, sr, Y(n - 1), Y(n - 2), Y(n - 3));
+        if (dt.periodic && c == nblk - 1) {                                                       // :531-532, kept for k_m1
+            const T* x = dt.x;
+            const T dx_1 = SUB(x[n - 1], x[n - 2]), dx_2 = SUB(x[n - 2], x[n - 3]);
+            const T yn2 = Y(n - 2);
+            const T slope_1 = DIV(SUB(Y(n - 1), yn2), dx_1), slope_2 = DIV(SUB(yn2, Y(n - 3)), dx_2);
+            R[(long long)(n - 2) * w + col] = MUL(ADD(MUL(slope_2, dx_1), MUL(slope_1, dx_2)), three);
+        }
+        // interior rows: 3 (d_i e_{i-1} / d_{i-1} + d_{i-1} e_i / d_i), e_i = y[i+1] - y[i], d_i = x[i+1] - x[i]   (:468)
+        const T* dx = fac;
+        const T* rdx = fac + (size_t)n;
+        T dp = first > 0 ? __ldg(dx + first - 1) : (T)1, rp = first > 0 ? __ldg(rdx + first - 1) : (T)0;
+#pragma unroll
+        for (int t = 0; t < MAXB; ++t) {
+            if (t < rows) {
+                const int i = first + t;
+                const bool has = i + 1 < n;
+                const T di = has ? __ldg(dx + i) : (T)1, ri = has ? __ldg(rdx + i) : (T)0;
+                T val = MUL(three, ADD(Hoisted<T>::div(MUL(di, v[t]), dp, rp), Hoisted<T>::div(MUL(dp, v[t + 1]), di, ri)));
+                if (t == 0 && c == 0) val = first_rhs;
+                if (own_last && t == rows - 1) val = last_rhs;
+                v[t] = val;
+                dp = di; rp = ri;
+            }
+        }
+        if (c < P) {                                                  // the separator's right-hand side, for the level above
+            T sep = v[0];
+#pragma unroll
+            for (int t = 1; t < MAXB; ++t) if (t == m - 1) sep = v[t];
+            R[rhs.at(first + m - 1)] = sep;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < MAXB - 1; ++t) v[t] = t < cnt ? rhs(first + t) : (T)0;
+        if (SRC == PART_SRC_LOWER && c < P) R[rhs.at(first + m - 1)] = rhs(first + m - 1);
+    }
     // forward (:698) and backward (:704-720) recurrences of the block; the factors are warp-uniform loads out of L1
 #pragma unroll
-    for (int t = 1; t < kPartBlockMax - 1; ++t)
+    for (int t = 1; t < MAXB - 1; ++t)
         if (t < cnt) v[t] = FMA(-ld_fac<T>(fr + t).wl, v[t - 1], v[t]);
     T nxt = (T)0;
 #pragma unroll
-    for (int t = kPartBlockMax - 2; t >= 0; --t) {
+    for (int t = MAXB - 2; t >= 0; --t) {
         if (t < cnt) {
             const FacRow<T> f = ld_fac<T>(fr + t);
             const T val = MUL(t == cnt - 1 ? v[t] : FMA(-f.up, nxt, v[t]), f.rmid);
@@ -240,11 +353,13 @@ __global__ void __launch_bounds__(128) part_local_kernel(const PartPlan pl, int 
 }
 
 // The last level: a block takes 32 columns; all its threads form the right-hand sides into shared memory, one lane per
-// column runs the two recurrences there, all threads write k back.
+// column runs the two recurrences there (factors staged in shared memory unless the columns have matrices of their
+// own), all threads write k back.
 template <class T>
 __global__ void __launch_bounds__(256) part_top_kernel(const PartPlan pl, T* fac, size_t fac_stride, T* __restrict__ R, long long w,
                                                        const int32_t* __restrict__ lks, const int32_t* __restrict__ rks) {
     __shared__ T tile[kPartTopMax][33];
+    __shared__ T s_wl[kPartTopMax], s_up[kPartTopMax], s_rm[kPartTopMax];
     const int l = pl.nsplit;
     const PartLevel L = pl.lv[l];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -252,20 +367,33 @@ __global__ void __launch_bounds__(256) part_top_kernel(const PartPlan pl, T* fac
     const bool live = col < w;
     T* facb = fac + ((lks && live) ? (size_t)part_group(lks, rks, col) * fac_stride : 0);
     const FacRow<T>* fr = PartArrays<T>(facb, L).fr;
+    if (!lks)
+        for (int j = threadIdx.x; j < L.len; j += 256) { const FacRow<T> f = ld_fac<T>(fr + j); s_wl[j] = f.wl; s_up[j] = f.up; s_rm[j] = f.rmid; }
     if (live) {
         if (l == 0) { const PartRhs<T, PART_SRC_R> rhs(pl, l, facb, R, w, col); for (int j = ry; j < L.len; j += 8) tile[j][cx] = rhs(j); }
         else { const PartRhs<T, PART_SRC_LOWER> rhs(pl, l, facb, R, w, col); for (int j = ry; j < L.len; j += 8) tile[j][cx] = rhs(j); }
     }
     __syncthreads();
     if (ry == 0 && live) {
-        T prev = tile[0][cx];
-        for (int i = 1; i < L.len; ++i) { prev = FMA(-ld_fac<T>(fr + i).wl, prev, tile[i][cx]); tile[i][cx] = prev; }
-        T k = MUL(prev, ld_fac<T>(fr + L.len - 1).rmid);
-        tile[L.len - 1][cx] = k;
-        for (int i = L.len - 2; i >= 0; --i) {
-            const FacRow<T> f = ld_fac<T>(fr + i);
-            k = MUL(FMA(-f.up, k, tile[i][cx]), f.rmid);
-            tile[i][cx] = k;
+        const int len = L.len;
+        if (!lks) {
+            T prev = tile[0][cx];
+#pragma unroll 4
+            for (int i = 1; i < len; ++i) { prev = FMA(-s_wl[i], prev, tile[i][cx]); tile[i][cx] = prev; }
+            T k = MUL(prev, s_rm[len - 1]);
+            tile[len - 1][cx] = k;
+#pragma unroll 4
+            for (int i = len - 2; i >= 0; --i) { k = MUL(FMA(-s_up[i], k, tile[i][cx]), s_rm[i]); tile[i][cx] = k; }
+        } else {
+            T prev = tile[0][cx];
+            for (int i = 1; i < len; ++i) { prev = FMA(-ld_fac<T>(fr + i).wl, prev, tile[i][cx]); tile[i][cx] = prev; }
+            T k = MUL(prev, ld_fac<T>(fr + len - 1).rmid);
+            tile[len - 1][cx] = k;
+            for (int i = len - 2; i >= 0; --i) {
+                const FacRow<T> f = ld_fac<T>(fr + i);
+                k = MUL(FMA(-f.up, k, tile[i][cx]), f.rmid);
+                tile[i][cx] = k;
+            }
         }
     }
     __syncthreads();
@@ -294,24 +422,75 @@ __global__ void __launch_bounds__(256) part_corr_kernel(const PartPlan pl, int l
     R[o] = FMA(-__ldg(a.q + j), kr, FMA(-__ldg(a.p + j), kl, R[o]));
 }
 
+// Level 0, non-periodic: the correction of step 4 and a[i] = k[i] dx - dy, b[i] = dy - k[i+1] dx (calc_coefficients
+// :354-365) in one pass, one thread per (block with its separator, column); k is formed in registers only.
+template <class T>
+__global__ void __launch_bounds__(256) part_ab_kernel(const PartPlan pl, T* fac, size_t fac_stride, const T* __restrict__ R,
+                                                      const T* __restrict__ y, int n, long long w, T* __restrict__ a, T* __restrict__ b,
+                                                      const int32_t* __restrict__ lks, const int32_t* __restrict__ rks) {
+    const PartLevel L = pl.lv[0];
+    const int m = pl.m, P = L.len / m, tail = L.len - P * m, nblk = P + (tail > 0 ? 1 : 0);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long c64 = gid / w, col = gid - c64 * w;
+    if (c64 >= nblk) return;
+    const int c = (int)c64;
+    T* facb = fac + (lks ? (size_t)part_group(lks, rks, col) * fac_stride : 0);
+    const PartArrays<T> pa(facb, L);
+    const T* dx = fac;
+    const int first = c * m, rows = c < P ? m : tail, sep = c < P ? first + m - 1 : -1;
+    auto Rat = [&](int i) -> T { return R[(long long)i * w + col]; };
+    const T kl = c > 0 ? Rat(first - 1) : (T)0, kr = c < P ? Rat(sep) : (T)0;
+    const T kr2 = (c + 1 < P) ? Rat(sep + m) : (T)0;                 // right separator of the next block
+    auto K = [&](int i, T g) -> T {                                   // final k of row i of this block or the first row of the next
+        if (i == sep) return kr;
+        if (i > sep && sep >= 0) return FMA(-__ldg(pa.q + i), kr2, FMA(-__ldg(pa.p + i), kr, g));
+        return FMA(-__ldg(pa.q + i), kr, FMA(-__ldg(pa.p + i), kl, g));
+    };
+    T k_i = K(first, Rat(first)), y_i = __ldg(y + (long long)first * w + col);
+#pragma unroll 8
+    for (int t = 0; t < rows; ++t) {
+        const int i = first + t;
+        if (i >= n - 1) break;
+        const T k_n = K(i + 1, Rat(i + 1)), y_n = __ldg(y + (long long)(i + 1) * w + col);
+        const T d = __ldg(dx + i), dy = SUB(y_n, y_i);
+        a[(long long)i * w + col] = SUB(MUL(k_i, d), dy);
+        b[(long long)i * w + col] = SUB(dy, MUL(k_n, d));
+        k_i = k_n; y_i = y_n;
+    }
+}
+
+template <class T, int SRC>
+static void part_launch_local(const PartPlan& pl, int l, T* fac, size_t fac_stride, T* R, long long w, const int32_t* lk,
+                              const int32_t* rk, const PartData<T>& dt, unsigned blocks, cudaStream_t st) {
+    if (pl.m <= 32) part_local_kernel<T, SRC, 32><<<blocks, 128, 0, st>>>(pl, l, fac, fac_stride, R, w, lk, rk, dt);
+    else part_local_kernel<T, SRC, kPartBlockMax><<<blocks, 128, 0, st>>>(pl, l, fac, fac_stride, R, w, lk, rk, dt);
+    count_launch();
+}
+
+// the solve on R, whose level-0 rows hold the right-hand sides (from_y: they are formed from dt.y by the first kernel).
+// final0: 0 leaves level 0 uncorrected (g in the block rows, k in the separator rows) for part_ab_kernel.
+// join: waited for before the first kernel that needs the factorisations of the levels above 0.
 template <class T>
 static cudaError_t part_solve(const PartPlan& pl, T* fac, size_t fac_stride, T* R, long long w, const int32_t* lk, const int32_t* rk,
-                              cudaStream_t st) {
+                              const PartData<T>* dt, bool final0, cudaEvent_t join, cudaStream_t st) {
     cudaError_t e;
+    const PartData<T> none{};
     for (int l = 0; l < pl.nsplit; ++l) {
         const PartLevel& L = pl.lv[l];
         const long long nblk = L.len / pl.m + (L.len % pl.m ? 1 : 0);
         const long long blocks = (nblk * w + 127) / 128;
         if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
-        if (l == 0) part_local_kernel<T, PART_SRC_R><<<(unsigned)blocks, 128, 0, st>>>(pl, l, fac, fac_stride, R, w, lk, rk);
-        else part_local_kernel<T, PART_SRC_LOWER><<<(unsigned)blocks, 128, 0, st>>>(pl, l, fac, fac_stride, R, w, lk, rk);
-        count_launch();
+        if (l == 1 && join && (e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
+        if (l == 0 && dt) part_launch_local<T, PART_SRC_Y>(pl, l, fac, fac_stride, R, w, lk, rk, *dt, (unsigned)blocks, st);
+        else if (l == 0) part_launch_local<T, PART_SRC_R>(pl, l, fac, fac_stride, R, w, lk, rk, none, (unsigned)blocks, st);
+        else part_launch_local<T, PART_SRC_LOWER>(pl, l, fac, fac_stride, R, w, lk, rk, none, (unsigned)blocks, st);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
+    if (pl.nsplit <= 1 && join && (e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
     part_top_kernel<T><<<(unsigned)((w + 31) / 32), 256, 0, st>>>(pl, fac, fac_stride, R, w, lk, rk);
     count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    for (int l = pl.nsplit - 1; l >= 0; --l) {
+    for (int l = pl.nsplit - 1; l >= (final0 ? 0 : 1); --l) {
         const long long blocks = ((long long)pl.lv[l].len * w + 255) / 256;
         if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
         part_corr_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(pl, l, fac, fac_stride, R, w, lk, rk);
@@ -319,6 +498,21 @@ static cudaError_t part_solve(const PartPlan& pl, T* fac, size_t fac_stride, T* 
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+// second stream of the calling thread on the current device (matrix work of the upper levels beside the block solves)
+struct PartSide { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static PartSide& part_side() {
+    static thread_local std::map<int, PartSide> per_dev;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    PartSide& sd = per_dev[dev];
+    if (!sd.s) {
+        if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) != cudaSuccess) { sd.s = nullptr; cudaGetLastError(); }
+    }
+    return sd;
 }
 
 // n >= 4.  scratch: ngroups * partition_fac_elems(n, block) elements of factorisations, then R (n x w).
@@ -339,23 +533,52 @@ cudaError_t launch_partition_build(const T* x, int64_t n, const T* data, int64_t
     const int ngroups = individual ? 9 : 1;
     T* fac = scratch;
     T* R = scratch + (size_t)ngroups * fac_stride;
+    const int32_t* ilk = individual ? lk : nullptr;
     cudaError_t e;
-    // matrix side: depends on x only
-    for (int lvl = 0; lvl < pl.nsplit; ++lvl) {
+    auto factor = [&](int lvl, cudaStream_t s) -> cudaError_t {
         const int nblk = pl.lv[lvl].len / pl.m + (pl.lv[lvl].len % pl.m ? 1 : 0);
-        part_factor_kernel<T><<<dim3((unsigned)((nblk + 63) / 64), ngroups), 64, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, pl, lvl, fac, fac_stride);
+        part_factor_kernel<T><<<dim3((unsigned)((nblk + kPfWarps - 1) / kPfWarps), ngroups), 32 * kPfWarps, 0, s>>>(
+            x, (int)n, periodic, ls.kind, rs.kind, pl, lvl, fac, fac_stride);
         count_launch();
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        return cudaGetLastError();
+    };
+    auto top_factor = [&](cudaStream_t s) -> cudaError_t {
+        part_top_factor_kernel<T><<<dim3(1, ngroups), kPartTopMax, 0, s>>>(x, (int)n, periodic, ls.kind, rs.kind, pl, fac, fac_stride);
+        count_launch();
+        return cudaGetLastError();
+    };
+    if (pl.nsplit == 0) {
+        // a system short enough to be solved directly: right-hand sides by the kernel of the other modes
+        if ((e = top_factor(st)) != cudaSuccess) return e;
+        if (periodic && (e = part_solve<T>(pl, fac, fac_stride, fac + 4 * (size_t)n, 1, nullptr, nullptr, nullptr, true, nullptr, st)) != cudaSuccess) return e;
+        if ((e = launch_spline_rhs<T>(x, (int)n, data, (long long)w, periodic, l, r, R, err, ilk, lv, rk, rv, st)) != cudaSuccess) return e;
+        if ((e = part_solve<T>(pl, fac, fac_stride, R, (long long)w, ilk, rk, nullptr, true, nullptr, st)) != cudaSuccess) return e;
+        if (periodic && (e = launch_spline_periodic_close<T>(x, (int)n, (long long)w, fac, R, st)) != cudaSuccess) return e;
+        return launch_spline_ab<T>(x, (int)n, data, (long long)w, periodic, fac, R, a, b, nullptr, st);
     }
-    part_top_factor_kernel<T><<<dim3(1, ngroups), kPartTopMax, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, pl, fac, fac_stride);
+    // matrix side (depends on x only): level 0 first, the levels above it -- and, periodic, the shared second solution
+    // k2 (:535-550: one more column through the same solve, in place at fac + 4n) -- beside the block solves of level 0
+    if ((e = factor(0, st)) != cudaSuccess) return e;
+    PartSide& side = part_side();
+    const bool forked = side.s && cudaEventRecord(side.fork, st) == cudaSuccess && cudaStreamWaitEvent(side.s, side.fork, 0) == cudaSuccess;
+    cudaStream_t ms = forked ? side.s : st;
+    for (int lvl = 1; lvl < pl.nsplit; ++lvl)
+        if ((e = factor(lvl, ms)) != cudaSuccess) return e;
+    if ((e = top_factor(ms)) != cudaSuccess) return e;
+    if (periodic && (e = part_solve<T>(pl, fac, fac_stride, fac + 4 * (size_t)n, 1, nullptr, nullptr, nullptr, true, nullptr, ms)) != cudaSuccess) return e;
+    if (forked && (e = cudaEventRecord(side.join, side.s)) != cudaSuccess) return e;
+    const PartData<T> dt{x, data, (int)n, periodic, l, r, lv, rv, err};
+    if ((e = part_solve<T>(pl, fac, fac_stride, R, (long long)w, ilk, rk, &dt, periodic != 0, forked ? side.join : nullptr, st)) != cudaSuccess) return e;
+    if (periodic) {
+        if ((e = launch_spline_periodic_close<T>(x, (int)n, (long long)w, fac, R, st)) != cudaSuccess) return e;
+        return launch_spline_ab<T>(x, (int)n, data, (long long)w, periodic, fac, R, a, b, nullptr, st);
+    }
+    const long long nblk0 = pl.lv[0].len / pl.m + (pl.lv[0].len % pl.m ? 1 : 0);
+    const long long blocks = (nblk0 * w + 255) / 256;
+    if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
+    part_ab_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(pl, fac, fac_stride, R, data, (int)n, (long long)w, a, b, ilk, rk);
     count_launch();
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    // periodic: the shared second solution k2 (:535-550) is one more column through the same solve, in place at fac + 4n
-    if (periodic && (e = part_solve<T>(pl, fac, fac_stride, fac + 4 * (size_t)n, 1, nullptr, nullptr, st)) != cudaSuccess) return e;
-    if ((e = launch_spline_rhs<T>(x, (int)n, data, (long long)w, periodic, l, r, R, err, individual ? lk : nullptr, lv, rk, rv, st)) != cudaSuccess) return e;
-    if ((e = part_solve<T>(pl, fac, fac_stride, R, (long long)w, individual ? lk : nullptr, rk, st)) != cudaSuccess) return e;
-    if (periodic && (e = launch_spline_periodic_close<T>(x, (int)n, (long long)w, fac, R, st)) != cudaSuccess) return e;
-    return launch_spline_ab<T>(x, (int)n, data, (long long)w, periodic, fac, R, a, b, nullptr, st);
+    return cudaGetLastError();
 }
 
 template cudaError_t launch_partition_build<float>(const float*, int64_t, const float*, int64_t, int, int, const int32_t*, const float*,

@@ -152,8 +152,9 @@ cudaError_t launch_spline_rhs(const T* x, int n, const T* y, long long w, int pe
                               cudaStream_t st);
 
 // partition build (ndi_partition.cu): blocks of `block` rows (separator included, 3 .. kPartBlockMax) solved in registers,
-// the separators' system recursively; right-hand sides, periodic close and a / b are the kernels above
-constexpr int kPartBlockMax = 32;
+// the separators' system recursively; the periodic close (and, for the short systems solved directly, right-hand sides and
+// a / b) are the kernels above
+constexpr int kPartBlockMax = 64, kPartBlockDefault = 32;
 int partition_block_for(int requested);
 size_t partition_fac_elems(int64_t n, int block);
 template <class T>

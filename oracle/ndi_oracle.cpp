@@ -360,8 +360,9 @@ void partition_thomas(T* k, const T* up, const T* mid, const T* low, const T* rh
     }
 }
 // > 0: solve_for_k's solves use partition_thomas with blocks of that many rows (separator included), direct solve from
-// 4 x that many rows down (set by ora_spline_build_partition_* for the duration of one call)
+// min(128, 4 x that many) rows down (set by ora_spline_build_partition_* for the duration of one call)
 thread_local int32_t g_partition_block = 0;
+inline int32_t partition_top(int32_t block) { return 4 * block < 128 ? 4 * block : 128; }
 
 // > 0: solve_for_k's full-system solve (:672) uses rowsplit_thomas with that many levels (set by
 // ora_spline_build_rowsplit_* for the duration of one call; periodic: both solves of the condensed system)
@@ -444,8 +445,8 @@ int32_t solve_for_k(T* k, const T* x, const T* data, int64_t len, int64_t w, int
         {
             std::vector<T> mid1(a_mid.begin(), a_mid.begin() + m), mid2(mid1);
             if (g_partition_block > 0) {                          // partition specification: both solves of the condensed system
-                partition_thomas(k1.data(), a_up.data(), mid1.data(), a_low.data(), rhs1.data(), m, w, g_partition_block, 4 * g_partition_block);
-                partition_thomas(k2.data(), a_up.data(), mid2.data(), a_low.data(), rhs2.data(), m, w, g_partition_block, 4 * g_partition_block);
+                partition_thomas(k1.data(), a_up.data(), mid1.data(), a_low.data(), rhs1.data(), m, w, g_partition_block, partition_top(g_partition_block));
+                partition_thomas(k2.data(), a_up.data(), mid2.data(), a_low.data(), rhs2.data(), m, w, g_partition_block, partition_top(g_partition_block));
             } else if (g_rowsplit_levels > 0) {                   // row-split specification: both solves of the condensed system
                 rowsplit_thomas(k1.data(), a_up.data(), mid1.data(), a_low.data(), rhs1.data(), m, w, g_rowsplit_levels);
                 rowsplit_thomas(k2.data(), a_up.data(), mid2.data(), a_low.data(), rhs2.data(), m, w, g_rowsplit_levels);
@@ -513,7 +514,7 @@ int32_t solve_for_k(T* k, const T* x, const T* data, int64_t len, int64_t w, int
     }
     // thomas on the full system (:672); k has row stride ld, so solve into a dense temp
     std::vector<T> kk((size_t)len * w);
-    if (g_partition_block > 0) partition_thomas(kk.data(), a_up.data(), a_mid.data(), a_low.data(), rhs.data(), len, w, g_partition_block, 4 * g_partition_block);
+    if (g_partition_block > 0) partition_thomas(kk.data(), a_up.data(), a_mid.data(), a_low.data(), rhs.data(), len, w, g_partition_block, partition_top(g_partition_block));
     else if (g_rowsplit_levels > 0) rowsplit_thomas(kk.data(), a_up.data(), a_mid.data(), a_low.data(), rhs.data(), len, w, g_rowsplit_levels);
     else thomas(kk.data(), a_up.data(), a_mid.data(), a_low.data(), rhs.data(), len, w);
     for (int64_t i = 0; i < len; ++i)

@@ -21,11 +21,11 @@ pytestmark = pytest.mark.gpu
 # (rows, columns, requested block): direct solve only (8, 9), one split level, two and three split levels, tails of
 # every kind (none, one row, a full block), the default block at the sizes the mode exists for
 SHAPES = [(8, 3, 3), (9, 5, 3), (37, 33, 4), (100, 1, 3), (257, 40, 8), (1000, 7, 5), (1031, 64, 32), (4096, 65, 0),
-          (5000, 2, 32), (1024, 31, 16), (129, 200, 32)]
+          (5000, 2, 32), (1024, 31, 16), (129, 200, 32), (4100, 12, 64), (8191, 3, 48), (640, 70, 100)]
 
 
 def block_used(requested):
-    return min(max(requested, 3), 32) if requested else 32
+    return min(max(requested, 3), 64) if requested else 32
 
 
 def case(dt, bc, n, w, block):
@@ -76,9 +76,9 @@ def test_partition_long_columns_f64_and_many_columns_f32():
     for n, w, dt in [(65536, 8, np.float64), (4096, 3000, np.float32), (70001, 3, np.float64)]:
         g = grid(rng, n, dt)
         y = rng.normal(size=(n, w)).astype(dt)
-        interp = build(g, y, BoundaryCondition.NotAKnot, "partition")
+        interp = build(g, y, BoundaryCondition.NotAKnot, "partition", 64 if n == 70001 else 0)
         used = interp.strategy.rowsplit_levels(interp)
-        assert used == -32
+        assert used == (-64 if n == 70001 else -32)
         a, b = interp.strategy.coefficients(interp)
         st, a_spec, b_spec = O.spline_build_as(g, y, {"kind": "NotAKnot"}, used)
         assert same(a, a_spec) and same(b, b_spec)
