@@ -5,8 +5,8 @@
 // 2^L at the price of L elementwise passes with a halo; it is bound by the latency of those passes (profiles/r02).
 // This mode cuts the rows into blocks of m - 1 rows separated by single rows (rows m-1, 2m-1, ...).  With the
 // separators' unknowns known the blocks are independent, so
-//   1. every (block, column) pair is ONE thread that forms its right-hand sides from y, keeps them in registers and runs
-//      the two Thomas recurrences of the block on them (part_local_kernel): g = A_block^-1 rhs;
+//   1. every (block, column) pair is ONE thread that keeps its right-hand sides in registers and runs the two Thomas
+//      recurrences of the block on them (part_local_kernel): g = A_block^-1 rhs;
 //   2. the block's response to its two separators (the "spikes" p = A_block^-1 low[first] e_first,
 //      q = A_block^-1 up[last] e_last) depends on x only and is formed once per block (part_factor_kernel);
 //   3. the separators' equations  -low[s] p[s-1] k[s-m] + (mid[s] - low[s] q[s-1] - up[s] p[s+1]) k[s]
@@ -15,9 +15,10 @@
 //      left, which one lane per column solves directly out of shared memory (part_top_kernel);
 //   4. k = g - p k_left - q k_right, elementwise, from the top level down (part_corr_kernel); on level 0 that
 //      correction is part of the kernel that writes a and b (part_ab_kernel), so k itself is never stored.
-// Every chain is m - 1 steps of one fused multiply-add (+ one multiplication by a reciprocal formed once per row); y is
-// read twice, g written and read once, a and b written once; no pass needs a halo.  The matrix work of the upper
-// levels runs on a second stream beside the block solves of level 0.
+// Every chain is m - 1 steps of one fused multiply-add (+ one multiplication by a reciprocal formed once per row); no
+// pass needs a halo.  All matrix work runs on a second stream beside the right-hand-side kernel.  (Forming the
+// right-hand sides inside the block solve was measured and dropped: 67 us against 30 + 15 us at the C2 shape, 192
+// registers per thread; profiles/r02/partition_build.md.)
 //
 // The rounding differs from the reference's elimination order, so this is NOT bit-identical to the reference
 // arithmetic; like the row-split mode it is held bit for bit to the checker's operation-by-operation specification
@@ -215,7 +216,7 @@ __device__ __forceinline__ int part_group(const int32_t* __restrict__ lks, const
     return 3 * var(lks[col]) + var(rks[col]);
 }
 
-enum { PART_SRC_R = 0, PART_SRC_LOWER = 1, PART_SRC_Y = 2 };
+enum { PART_SRC_R = 0, PART_SRC_LOWER = 1 };
 // right-hand side of row j of level l for one column: read from R (PART_SRC_R), or, on level l >= 1, formed from
 // the block solutions g of level l - 1 around the separator (step 3)
 template <class T, int SRC>
@@ -240,20 +241,10 @@ struct PartRhs {
     }
 };
 
-// what part_local_kernel<.., PART_SRC_Y> needs to form the right-hand sides of level 0 itself
-template <class T>
-struct PartData {
-    const T* x; const T* y; int n, periodic; Side<T> left, right; const T* lvs; const T* rvs; unsigned long long* err;
-};
-
 // One thread per (block, column): g = A_block^-1 rhs, in registers, written over the right-hand sides in R.
-// PART_SRC_Y (level 0): the right-hand sides are formed here from y (solve_for_k :456-471 interior rows, :599-669 boundary
-// rows, :521-532 periodic), divisions by a grid step through its reciprocal (ndi_device.cuh, Hoisted: the IEEE quotient),
-// and the separator's right-hand side is left in R for the level above.
 template <class T, int SRC, int MAXB>
 __global__ void __launch_bounds__(128) part_local_kernel(const PartPlan pl, int l, T* fac, size_t fac_stride, T* __restrict__ R,
-                                                         long long w, const int32_t* __restrict__ lks, const int32_t* __restrict__ rks,
-                                                         const PartData<T> dt) {
+                                                         long long w, const int32_t* __restrict__ lks, const int32_t* __restrict__ rks) {
     const PartLevel L = pl.lv[l];
     const int m = pl.m, P = L.len / m, tail = L.len - P * m, nblk = P + (tail > 0 ? 1 : 0);
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -264,78 +255,10 @@ __global__ void __launch_bounds__(128) part_local_kernel(const PartPlan pl, int 
     const int first = c * m, cnt = c < P ? m - 1 : tail;
     const PartRhs<T, SRC> rhs(pl, l, facb, R, w, col);
     const FacRow<T>* fr = PartArrays<T>(facb, L).fr + first;
-    T v[MAXB + 1];
-    if (SRC == PART_SRC_Y) {
-        const int n = dt.n, rows = c < P ? m : tail;
-        const T* ycol = dt.y + col;
-        auto Y = [&](int row) -> T { return __ldg(ycol + (long long)row * w); };
-        // v[j] = y[first - 1 + j], j <= rows + 1 (rows outside the table: 0, they only reach right-hand sides that are
-        // replaced below), then the differences of neighbours in place: v[t] = y[first + t] - y[first + t - 1]
+    T v[MAXB - 1];
 #pragma unroll
-        for (int j = 0; j < MAXB + 1; ++j) {
-            const int gi = first - 1 + j;
-            v[j] = (j <= rows + 1 && gi >= 0 && gi < n) ? Y(gi) : (T)0;
-        }
-        const int gl = first + MAXB;
-        const T ylast = (rows == MAXB && gl < n) ? Y(gl) : (T)0;
-#pragma unroll
-        for (int j = 0; j < MAXB; ++j) v[j] = SUB(v[j + 1], v[j]);
-        v[MAXB] = SUB(ylast, v[MAXB]);
-        // boundary rows of the system, where this thread owns them
-        Side<T> sl = specialize(dt.left), sr = specialize(dt.right);
-        if (lks) { sl = specialize(Side<T>{lks[col], dt.lvs[col]}); sr = specialize(Side<T>{rks[col], dt.rvs[col]}); }
-        const T three = (T)3;
-        T first_rhs = (T)0, last_rhs = (T)0;
-        const bool own_last = !dt.periodic && first + rows == n;
-        if (c == 0) {
-            if (dt.periodic) {
-                const T* x = dt.x;
-                const T dx0 = SUB(x[1], x[0]), dx_1 = SUB(x[n - 1], x[n - 2]);
-                const T y0 = Y(0), yN = Y(n - 1);
-                if (y0 != yN) atomicMin(dt.err, (unsigned long long)col);                         // :499-507
-                const T slope0 = DIV(SUB(Y(1), y0), dx0);                                         // :521
-                const T slope_1 = DIV(SUB(yN, Y(n - 2)), dx_1);                                   // :526
-                first_rhs = MUL(ADD(MUL(slope_1, dx0), MUL(slope0, dx_1)), three);                // :529-530
-            } else {
-                first_rhs = rhs_left<T>(dt.x, sl, Y(0), Y(1), Y(2));
-            }
-        }
-        if (own_last) last_rhs = rhs_right<T>(dt.x, n, sr, Y(n - 1), Y(n - 2), Y(n - 3));
-        if (dt.periodic && c == nblk - 1) {                                                       // :531-532, kept for k_m1
-            const T* x = dt.x;
-            const T dx_1 = SUB(x[n - 1], x[n - 2]), dx_2 = SUB(x[n - 2], x[n - 3]);
-            const T yn2 = Y(n - 2);
-            const T slope_1 = DIV(SUB(Y(n - 1), yn2), dx_1), slope_2 = DIV(SUB(yn2, Y(n - 3)), dx_2);
-            R[(long long)(n - 2) * w + col] = MUL(ADD(MUL(slope_2, dx_1), MUL(slope_1, dx_2)), three);
-        }
-        // interior rows: 3 (d_i e_{i-1} / d_{i-1} + d_{i-1} e_i / d_i), e_i = y[i+1] - y[i], d_i = x[i+1] - x[i]   (:468)
-        const T* dx = fac;
-        const T* rdx = fac + (size_t)n;
-        T dp = first > 0 ? __ldg(dx + first - 1) : (T)1, rp = first > 0 ? __ldg(rdx + first - 1) : (T)0;
-#pragma unroll
-        for (int t = 0; t < MAXB; ++t) {
-            if (t < rows) {
-                const int i = first + t;
-                const bool has = i + 1 < n;
-                const T di = has ? __ldg(dx + i) : (T)1, ri = has ? __ldg(rdx + i) : (T)0;
-                T val = MUL(three, ADD(Hoisted<T>::div(MUL(di, v[t]), dp, rp), Hoisted<T>::div(MUL(dp, v[t + 1]), di, ri)));
-                if (t == 0 && c == 0) val = first_rhs;
-                if (own_last && t == rows - 1) val = last_rhs;
-                v[t] = val;
-                dp = di; rp = ri;
-            }
-        }
-        if (c < P) {                                                  // the separator's right-hand side, for the level above
-            T sep = v[0];
-#pragma unroll
-            for (int t = 1; t < MAXB; ++t) if (t == m - 1) sep = v[t];
-            R[rhs.at(first + m - 1)] = sep;
-        }
-    } else {
-#pragma unroll
-        for (int t = 0; t < MAXB - 1; ++t) v[t] = t < cnt ? rhs(first + t) : (T)0;
-        if (SRC == PART_SRC_LOWER && c < P) R[rhs.at(first + m - 1)] = rhs(first + m - 1);
-    }
+    for (int t = 0; t < MAXB - 1; ++t) v[t] = t < cnt ? rhs(first + t) : (T)0;
+    if (SRC == PART_SRC_LOWER && c < P) R[rhs.at(first + m - 1)] = rhs(first + m - 1);   // the separator's own right-hand side, for the level above
     // forward (:698) and backward (:704-720) recurrences of the block; the factors are warp-uniform loads out of L1
 #pragma unroll
     for (int t = 1; t < MAXB - 1; ++t)
@@ -352,26 +275,28 @@ __global__ void __launch_bounds__(128) part_local_kernel(const PartPlan pl, int 
     }
 }
 
-// The last level: a block takes 32 columns; all its threads form the right-hand sides into shared memory, one lane per
-// column runs the two recurrences there (factors staged in shared memory unless the columns have matrices of their
-// own), all threads write k back.
+// The last level: a block takes kTopCols columns (few, so that many SMs take part: the kernel is a chain of 2 len
+// dependent steps per column whatever the block does); all its threads form the right-hand sides into shared memory,
+// one lane per column runs the two recurrences there (factors staged in shared memory unless the columns have
+// matrices of their own), all threads write k back.
+constexpr int kTopCols = 8, kTopThreads = 256, kTopRowLanes = kTopThreads / kTopCols;
 template <class T>
-__global__ void __launch_bounds__(256) part_top_kernel(const PartPlan pl, T* fac, size_t fac_stride, T* __restrict__ R, long long w,
-                                                       const int32_t* __restrict__ lks, const int32_t* __restrict__ rks) {
-    __shared__ T tile[kPartTopMax][33];
+__global__ void __launch_bounds__(kTopThreads) part_top_kernel(const PartPlan pl, T* fac, size_t fac_stride, T* __restrict__ R, long long w,
+                                                               const int32_t* __restrict__ lks, const int32_t* __restrict__ rks) {
+    __shared__ T tile[kPartTopMax][kTopCols + 1];
     __shared__ T s_wl[kPartTopMax], s_up[kPartTopMax], s_rm[kPartTopMax];
     const int l = pl.nsplit;
     const PartLevel L = pl.lv[l];
-    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-    const long long col = (long long)blockIdx.x * 32 + cx;
+    const int cx = threadIdx.x % kTopCols, ry = threadIdx.x / kTopCols;
+    const long long col = (long long)blockIdx.x * kTopCols + cx;
     const bool live = col < w;
     T* facb = fac + ((lks && live) ? (size_t)part_group(lks, rks, col) * fac_stride : 0);
     const FacRow<T>* fr = PartArrays<T>(facb, L).fr;
     if (!lks)
-        for (int j = threadIdx.x; j < L.len; j += 256) { const FacRow<T> f = ld_fac<T>(fr + j); s_wl[j] = f.wl; s_up[j] = f.up; s_rm[j] = f.rmid; }
+        for (int j = threadIdx.x; j < L.len; j += kTopThreads) { const FacRow<T> f = ld_fac<T>(fr + j); s_wl[j] = f.wl; s_up[j] = f.up; s_rm[j] = f.rmid; }
     if (live) {
-        if (l == 0) { const PartRhs<T, PART_SRC_R> rhs(pl, l, facb, R, w, col); for (int j = ry; j < L.len; j += 8) tile[j][cx] = rhs(j); }
-        else { const PartRhs<T, PART_SRC_LOWER> rhs(pl, l, facb, R, w, col); for (int j = ry; j < L.len; j += 8) tile[j][cx] = rhs(j); }
+        if (l == 0) { const PartRhs<T, PART_SRC_R> rhs(pl, l, facb, R, w, col); for (int j = ry; j < L.len; j += kTopRowLanes) tile[j][cx] = rhs(j); }
+        else { const PartRhs<T, PART_SRC_LOWER> rhs(pl, l, facb, R, w, col); for (int j = ry; j < L.len; j += kTopRowLanes) tile[j][cx] = rhs(j); }
     }
     __syncthreads();
     if (ry == 0 && live) {
@@ -399,7 +324,7 @@ __global__ void __launch_bounds__(256) part_top_kernel(const PartPlan pl, T* fac
     __syncthreads();
     if (live) {
         const PartRhs<T, PART_SRC_R> at(pl, l, facb, R, w, col);
-        for (int j = ry; j < L.len; j += 8) R[at.at(j)] = tile[j][cx];
+        for (int j = ry; j < L.len; j += kTopRowLanes) R[at.at(j)] = tile[j][cx];
     }
 }
 
@@ -423,71 +348,85 @@ __global__ void __launch_bounds__(256) part_corr_kernel(const PartPlan pl, int l
 }
 
 // Level 0, non-periodic: the correction of step 4 and a[i] = k[i] dx - dy, b[i] = dy - k[i+1] dx (calc_coefficients
-// :354-365) in one pass, one thread per (block with its separator, column); k is formed in registers only.
+// :354-365) in one pass; k is formed in registers only.  A thread takes kRowGroup consecutive intervals of one column (the
+// task layout of spline_ab_kernel) and the k of their kRowGroup + 1 rows; the separator rows it needs are read by every
+// thread of the block's eight row groups, out of L2.
 template <class T>
 __global__ void __launch_bounds__(256) part_ab_kernel(const PartPlan pl, T* fac, size_t fac_stride, const T* __restrict__ R,
                                                       const T* __restrict__ y, int n, long long w, T* __restrict__ a, T* __restrict__ b,
                                                       const int32_t* __restrict__ lks, const int32_t* __restrict__ rks) {
     const PartLevel L = pl.lv[0];
-    const int m = pl.m, P = L.len / m, tail = L.len - P * m, nblk = P + (tail > 0 ? 1 : 0);
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long c64 = gid / w, col = gid - c64 * w;
-    if (c64 >= nblk) return;
-    const int c = (int)c64;
-    T* facb = fac + (lks ? (size_t)part_group(lks, rks, col) * fac_stride : 0);
-    const PartArrays<T> pa(facb, L);
+    const int m = pl.m, P = L.len / m;
     const T* dx = fac;
-    const int first = c * m, rows = c < P ? m : tail, sep = c < P ? first + m - 1 : -1;
-    auto Rat = [&](int i) -> T { return R[(long long)i * w + col]; };
-    const T kl = c > 0 ? Rat(first - 1) : (T)0, kr = c < P ? Rat(sep) : (T)0;
-    const T kr2 = (c + 1 < P) ? Rat(sep + m) : (T)0;                 // right separator of the next block
-    auto K = [&](int i, T g) -> T {                                   // final k of row i of this block or the first row of the next
-        if (i == sep) return kr;
-        if (i > sep && sep >= 0) return FMA(-__ldg(pa.q + i), kr2, FMA(-__ldg(pa.p + i), kr, g));
-        return FMA(-__ldg(pa.q + i), kr, FMA(-__ldg(pa.p + i), kl, g));
-    };
-    T k_i = K(first, Rat(first)), y_i = __ldg(y + (long long)first * w + col);
-#pragma unroll 8
-    for (int t = 0; t < rows; ++t) {
-        const int i = first + t;
-        if (i >= n - 1) break;
-        const T k_n = K(i + 1, Rat(i + 1)), y_n = __ldg(y + (long long)(i + 1) * w + col);
-        const T d = __ldg(dx + i), dy = SUB(y_n, y_i);
-        a[(long long)i * w + col] = SUB(MUL(k_i, d), dy);
-        b[(long long)i * w + col] = SUB(dy, MUL(k_n, d));
-        k_i = k_n; y_i = y_n;
+    const long long chunks = (w + blockDim.x - 1) / blockDim.x;
+    const long long ntasks = chunks * ((n - 1 + kRowGroup - 1) / kRowGroup);
+    for (long long task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        const long long g = task / chunks;
+        const long long col = (task - g * chunks) * blockDim.x + threadIdx.x;
+        if (col >= w) continue;
+        const int row = (int)g * kRowGroup;
+        T* facb = fac + (lks ? (size_t)part_group(lks, rks, col) * fac_stride : 0);
+        const PartArrays<T> pa(facb, L);
+        auto Rat = [&](int i) -> T { return R[(long long)i * w + col]; };
+        T kv[kRowGroup + 1], yv[kRowGroup + 1];
+#pragma unroll
+        for (int j = 0; j <= kRowGroup; ++j) {
+            const int i = min(row + j, n - 1);
+            kv[j] = Rat(i);
+            yv[j] = __ldg(y + (long long)i * w + col);
+        }
+        // the rows of a group lie in at most two blocks: separators of the first row's block, and the one after them
+        const int c0 = row / m;
+        const T s0 = c0 > 0 ? Rat(c0 * m - 1) : (T)0, s1 = c0 < P ? Rat(c0 * m + m - 1) : (T)0,
+                s2 = c0 + 1 < P ? Rat(c0 * m + 2 * m - 1) : (T)0;
+#pragma unroll
+        for (int j = 0; j <= kRowGroup; ++j) {
+            const int i = min(row + j, n - 1);
+            const int c = i / m;
+            if (!(c < P && i - c * m == m - 1)) {
+                const T kl = c == c0 ? s0 : s1, kr = c == c0 ? s1 : s2;
+                kv[j] = FMA(-__ldg(pa.q + i), kr, FMA(-__ldg(pa.p + i), kl, kv[j]));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kRowGroup; ++j) {
+            const int i = row + j;
+            if (i >= n - 1) break;
+            const T d = __ldg(dx + i), dy = SUB(yv[j + 1], yv[j]);
+            a[(long long)i * w + col] = SUB(MUL(kv[j], d), dy);
+            b[(long long)i * w + col] = SUB(dy, MUL(kv[j + 1], d));
+        }
     }
 }
 
 template <class T, int SRC>
 static void part_launch_local(const PartPlan& pl, int l, T* fac, size_t fac_stride, T* R, long long w, const int32_t* lk,
-                              const int32_t* rk, const PartData<T>& dt, unsigned blocks, cudaStream_t st) {
-    if (pl.m <= 32) part_local_kernel<T, SRC, 32><<<blocks, 128, 0, st>>>(pl, l, fac, fac_stride, R, w, lk, rk, dt);
-    else part_local_kernel<T, SRC, kPartBlockMax><<<blocks, 128, 0, st>>>(pl, l, fac, fac_stride, R, w, lk, rk, dt);
+                              const int32_t* rk, unsigned blocks, cudaStream_t st) {
+    if (pl.m <= 32) part_local_kernel<T, SRC, 32><<<blocks, 128, 0, st>>>(pl, l, fac, fac_stride, R, w, lk, rk);
+    else part_local_kernel<T, SRC, kPartBlockMax><<<blocks, 128, 0, st>>>(pl, l, fac, fac_stride, R, w, lk, rk);
     count_launch();
 }
 
-// the solve on R, whose level-0 rows hold the right-hand sides (from_y: they are formed from dt.y by the first kernel).
+// the solve on R, whose level-0 rows hold the right-hand sides.
 // final0: 0 leaves level 0 uncorrected (g in the block rows, k in the separator rows) for part_ab_kernel.
-// join: waited for before the first kernel that needs the factorisations of the levels above 0.
+// ev0 / join: waited for before the first kernel that needs the factorisation of level 0 / of the levels above it.
 template <class T>
 static cudaError_t part_solve(const PartPlan& pl, T* fac, size_t fac_stride, T* R, long long w, const int32_t* lk, const int32_t* rk,
-                              const PartData<T>* dt, bool final0, cudaEvent_t join, cudaStream_t st) {
+                              bool final0, cudaEvent_t ev0, cudaEvent_t join, cudaStream_t st) {
     cudaError_t e;
-    const PartData<T> none{};
+    if (ev0 && (e = cudaStreamWaitEvent(st, ev0, 0)) != cudaSuccess) return e;
     for (int l = 0; l < pl.nsplit; ++l) {
         const PartLevel& L = pl.lv[l];
         const long long nblk = L.len / pl.m + (L.len % pl.m ? 1 : 0);
         const long long blocks = (nblk * w + 127) / 128;
         if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
         if (l == 1 && join && (e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
-        if (l == 0 && dt) part_launch_local<T, PART_SRC_Y>(pl, l, fac, fac_stride, R, w, lk, rk, *dt, (unsigned)blocks, st);
-        else if (l == 0) part_launch_local<T, PART_SRC_R>(pl, l, fac, fac_stride, R, w, lk, rk, none, (unsigned)blocks, st);
-        else part_launch_local<T, PART_SRC_LOWER>(pl, l, fac, fac_stride, R, w, lk, rk, none, (unsigned)blocks, st);
+        if (l == 0) part_launch_local<T, PART_SRC_R>(pl, l, fac, fac_stride, R, w, lk, rk, (unsigned)blocks, st);
+        else part_launch_local<T, PART_SRC_LOWER>(pl, l, fac, fac_stride, R, w, lk, rk, (unsigned)blocks, st);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (pl.nsplit <= 1 && join && (e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
-    part_top_kernel<T><<<(unsigned)((w + 31) / 32), 256, 0, st>>>(pl, fac, fac_stride, R, w, lk, rk);
+    part_top_kernel<T><<<(unsigned)((w + kTopCols - 1) / kTopCols), kTopThreads, 0, st>>>(pl, fac, fac_stride, R, w, lk, rk);
     count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     for (int l = pl.nsplit - 1; l >= (final0 ? 0 : 1); --l) {
@@ -501,7 +440,7 @@ static cudaError_t part_solve(const PartPlan& pl, T* fac, size_t fac_stride, T* 
 }
 
 // second stream of the calling thread on the current device (matrix work of the upper levels beside the block solves)
-struct PartSide { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+struct PartSide { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, lvl0 = nullptr, join = nullptr; };
 static PartSide& part_side() {
     static thread_local std::map<int, PartSide> per_dev;
     int dev = 0;
@@ -510,6 +449,7 @@ static PartSide& part_side() {
     if (!sd.s) {
         if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sd.lvl0, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) != cudaSuccess) { sd.s = nullptr; cudaGetLastError(); }
     }
     return sd;
@@ -547,36 +487,29 @@ cudaError_t launch_partition_build(const T* x, int64_t n, const T* data, int64_t
         count_launch();
         return cudaGetLastError();
     };
-    if (pl.nsplit == 0) {
-        // a system short enough to be solved directly: right-hand sides by the kernel of the other modes
-        if ((e = top_factor(st)) != cudaSuccess) return e;
-        if (periodic && (e = part_solve<T>(pl, fac, fac_stride, fac + 4 * (size_t)n, 1, nullptr, nullptr, nullptr, true, nullptr, st)) != cudaSuccess) return e;
-        if ((e = launch_spline_rhs<T>(x, (int)n, data, (long long)w, periodic, l, r, R, err, ilk, lv, rk, rv, st)) != cudaSuccess) return e;
-        if ((e = part_solve<T>(pl, fac, fac_stride, R, (long long)w, ilk, rk, nullptr, true, nullptr, st)) != cudaSuccess) return e;
-        if (periodic && (e = launch_spline_periodic_close<T>(x, (int)n, (long long)w, fac, R, st)) != cudaSuccess) return e;
-        return launch_spline_ab<T>(x, (int)n, data, (long long)w, periodic, fac, R, a, b, nullptr, st);
-    }
-    // matrix side (depends on x only): level 0 first, the levels above it -- and, periodic, the shared second solution
-    // k2 (:535-550: one more column through the same solve, in place at fac + 4n) -- beside the block solves of level 0
-    if ((e = factor(0, st)) != cudaSuccess) return e;
+    // All matrix work (it depends on x only) -- and, periodic, the shared second solution k2 (:535-550: one more column
+    // through the same solve, in place at fac + 4n) -- runs on a second stream of this thread beside the right-hand sides.
     PartSide& side = part_side();
     const bool forked = side.s && cudaEventRecord(side.fork, st) == cudaSuccess && cudaStreamWaitEvent(side.s, side.fork, 0) == cudaSuccess;
     cudaStream_t ms = forked ? side.s : st;
-    for (int lvl = 1; lvl < pl.nsplit; ++lvl)
+    for (int lvl = 0; lvl < pl.nsplit; ++lvl) {
         if ((e = factor(lvl, ms)) != cudaSuccess) return e;
+        if (lvl == 0 && forked && (e = cudaEventRecord(side.lvl0, ms)) != cudaSuccess) return e;
+    }
     if ((e = top_factor(ms)) != cudaSuccess) return e;
-    if (periodic && (e = part_solve<T>(pl, fac, fac_stride, fac + 4 * (size_t)n, 1, nullptr, nullptr, nullptr, true, nullptr, ms)) != cudaSuccess) return e;
-    if (forked && (e = cudaEventRecord(side.join, side.s)) != cudaSuccess) return e;
-    const PartData<T> dt{x, data, (int)n, periodic, l, r, lv, rv, err};
-    if ((e = part_solve<T>(pl, fac, fac_stride, R, (long long)w, ilk, rk, &dt, periodic != 0, forked ? side.join : nullptr, st)) != cudaSuccess) return e;
-    if (periodic) {
-        if ((e = launch_spline_periodic_close<T>(x, (int)n, (long long)w, fac, R, st)) != cudaSuccess) return e;
+    if (periodic && (e = part_solve<T>(pl, fac, fac_stride, fac + 4 * (size_t)n, 1, nullptr, nullptr, true, nullptr, nullptr, ms)) != cudaSuccess) return e;
+    if (forked && (e = cudaEventRecord(side.join, ms)) != cudaSuccess) return e;
+    if ((e = launch_spline_rhs<T>(x, (int)n, data, (long long)w, periodic, l, r, R, err, ilk, lv, rk, rv, st)) != cudaSuccess) return e;
+    const bool fused_ab = !periodic && pl.nsplit > 0 && pl.m >= 5;   // part_ab_kernel: a row group lies in at most two blocks
+    if ((e = part_solve<T>(pl, fac, fac_stride, R, (long long)w, ilk, rk, !fused_ab, (forked && pl.nsplit > 0) ? side.lvl0 : nullptr,
+                           forked ? side.join : nullptr, st)) != cudaSuccess) return e;
+    if (!fused_ab) {
+        if (periodic && (e = launch_spline_periodic_close<T>(x, (int)n, (long long)w, fac, R, st)) != cudaSuccess) return e;
         return launch_spline_ab<T>(x, (int)n, data, (long long)w, periodic, fac, R, a, b, nullptr, st);
     }
-    const long long nblk0 = pl.lv[0].len / pl.m + (pl.lv[0].len % pl.m ? 1 : 0);
-    const long long blocks = (nblk0 * w + 255) / 256;
-    if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
-    part_ab_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(pl, fac, fac_stride, R, data, (int)n, (long long)w, a, b, ilk, rk);
+    const long long chunks = (w + 255) / 256, tasks = chunks * ((n - 1 + kRowGroup - 1) / kRowGroup);
+    const long long cap = (long long)device_info().sm_count * 8;
+    part_ab_kernel<T><<<(unsigned)(tasks < cap ? tasks : cap), 256, 0, st>>>(pl, fac, fac_stride, R, data, (int)n, (long long)w, a, b, ilk, rk);
     count_launch();
     return cudaGetLastError();
 }
