@@ -1095,9 +1095,12 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
                 CK(cudaMemcpyAsync(rv, right_val, h->w * sizeof(T), cudaMemcpyHostToDevice, bs));
                 CK(cudaMemcpyAsync(pos, pos_host.data(), h->w * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
             }
-            CK(cudaMemsetAsync(ws->d_err, 0xff, sizeof(uint64_t), bs));
+            // the error word (first column whose ends differ) only exists for Periodic: the other kinds save its round trip
+            const bool has_err = bc_kind == NDI_BC_PERIODIC;
+            if (has_err) CK(cudaMemsetAsync(ws->d_err, 0xff, sizeof(uint64_t), bs));
             CK(launch_spline_build<T>((const T*)h->x, h->n, (const T*)h->data, h->w, bc_kind, lk, lv, rk, rv, pos, group_count, levels, a, b, scratch, ws->d_err, bs));
-            CK(cudaMemcpyAsync(ws->h_pin, ws->d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, bs));
+            if (has_err) CK(cudaMemcpyAsync(ws->h_pin, ws->d_err, sizeof(uint64_t), cudaMemcpyDeviceToHost, bs));
+            else { const uint64_t none = NDI_ERR_WORD_NONE; memcpy(ws->h_pin, &none, sizeof(none)); }
             CK(cudaStreamSynchronize(bs));
             return NDI_OK;
         };

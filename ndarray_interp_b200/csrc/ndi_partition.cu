@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(256) part_corr_kernel(const PartPlan pl, int l
 
 // Level 0, non-periodic: the correction of step 4 and a[i] = k[i] dx - dy, b[i] = dy - k[i+1] dx (calc_coefficients
 // :354-365) in one pass; k is formed in registers only.  A thread takes kRowGroup consecutive intervals of one column (the
-// task layout of spline_ab_kernel) and the k of their kRowGroup + 1 rows; the separator rows it needs are read by every
+// item layout of spline_ab_kernel) and the k of their kRowGroup + 1 rows; the separator rows it needs are read by every
 // thread of the block's eight row groups, out of L2.
 template <class T>
 __global__ void __launch_bounds__(256) part_ab_kernel(const PartPlan pl, T* fac, size_t fac_stride, const T* __restrict__ R,
@@ -358,12 +358,12 @@ __global__ void __launch_bounds__(256) part_ab_kernel(const PartPlan pl, T* fac,
     const PartLevel L = pl.lv[0];
     const int m = pl.m, P = L.len / m;
     const T* dx = fac;
-    const long long chunks = (w + blockDim.x - 1) / blockDim.x;
-    const long long ntasks = chunks * ((n - 1 + kRowGroup - 1) / kRowGroup);
+    const long long groups = (n - 1 + kRowGroup - 1) / kRowGroup;
+    const long long ntasks = (groups * w + blockDim.x - 1) / blockDim.x;
     for (long long task = blockIdx.x; task < ntasks; task += gridDim.x) {
-        const long long g = task / chunks;
-        const long long col = (task - g * chunks) * blockDim.x + threadIdx.x;
-        if (col >= w) continue;
+        const long long item = task * blockDim.x + threadIdx.x;        // consecutive threads: consecutive columns, then the next row group
+        const long long g = item / w, col = item - g * w;
+        if (g >= groups) continue;
         const int row = (int)g * kRowGroup;
         T* facb = fac + (lks ? (size_t)part_group(lks, rks, col) * fac_stride : 0);
         const PartArrays<T> pa(facb, L);
@@ -507,7 +507,7 @@ cudaError_t launch_partition_build(const T* x, int64_t n, const T* data, int64_t
         if (periodic && (e = launch_spline_periodic_close<T>(x, (int)n, (long long)w, fac, R, st)) != cudaSuccess) return e;
         return launch_spline_ab<T>(x, (int)n, data, (long long)w, periodic, fac, R, a, b, nullptr, st);
     }
-    const long long chunks = (w + 255) / 256, tasks = chunks * ((n - 1 + kRowGroup - 1) / kRowGroup);
+    const long long tasks = (((n - 1 + kRowGroup - 1) / kRowGroup) * (long long)w + 255) / 256;
     const long long cap = (long long)device_info().sm_count * 8;
     part_ab_kernel<T><<<(unsigned)(tasks < cap ? tasks : cap), 256, 0, st>>>(pl, fac, fac_stride, R, data, (int)n, (long long)w, a, b, ilk, rk);
     count_launch();

@@ -236,12 +236,18 @@ __device__ __forceinline__ T lds_elem(unsigned smem_addr) {
     return v;
 }
 
-// a block works on (group of kRowGroup rows, chunk of blockDim.x columns) tasks; grid-stride over the tasks
+// a thread works on (group of kRowGroup rows, column) items, consecutive threads on consecutive columns -- wrapping
+// into the next row group, so that narrow tables keep every thread busy too (a block of 256 threads per 64 columns
+// left three quarters of them idle: 65536 x 64 f64, right-hand sides 69 us); a task is blockDim.x consecutive
+// items, `chunks` the number of tasks; grid-stride over the tasks
 struct RowTask { int row; long long col; bool live; };
-__device__ __forceinline__ RowTask row_task(long long task, long long chunks, long long w) {
-    const long long g = task / chunks;
-    const long long col = (task - g * chunks) * blockDim.x + threadIdx.x;
-    return RowTask{(int)g * kRowGroup, col, col < w};
+__device__ __forceinline__ long long row_task_count(long long w, long long nrows) {
+    return (((nrows + kRowGroup - 1) / kRowGroup) * w + blockDim.x - 1) / blockDim.x;
+}
+__device__ __forceinline__ RowTask row_task(long long task, long long w, long long nrows) {
+    const long long item = task * blockDim.x + threadIdx.x;
+    const long long g = item / w;
+    return RowTask{(int)g * kRowGroup, item - g * w, g * kRowGroup < nrows};
 }
 
 // launch 1: right-hand sides.  Non-periodic: R[0] = left boundary row, R[1..n-2] = interior rows (:468),
@@ -256,11 +262,10 @@ __global__ void __launch_bounds__(256) spline_rhs_kernel(const T* __restrict__ x
                                                          const T* __restrict__ rvs = nullptr, const int32_t* __restrict__ pos = nullptr) {
     Side<T> l = specialize(left), r = specialize(right);
     const T three = (T)3;
-    const long long chunks = (w + blockDim.x - 1) / blockDim.x;
     const int rows = periodic ? n - 1 : n;
-    const long long ntasks = chunks * ((rows + kRowGroup - 1) / kRowGroup);
+    const long long ntasks = row_task_count(w, rows);
     for (long long task = blockIdx.x; task < ntasks; task += gridDim.x) {
-        const RowTask t = row_task(task, chunks, w);
+        const RowTask t = row_task(task, w, rows);
         if (!t.live) continue;
         const T* ycol = y + t.col;
         auto Y = [&](int row) -> T { return __ldg(ycol + (long long)row * w); };
@@ -496,10 +501,9 @@ __global__ void __launch_bounds__(256) spline_ab_kernel(const T* __restrict__ x,
                                                         int periodic, const T* __restrict__ fac, const T* __restrict__ R,
                                                         T* __restrict__ a, T* __restrict__ b, const int32_t* __restrict__ pos = nullptr) {
     const T* k2 = fac + 4 * (size_t)n;
-    const long long chunks = (w + blockDim.x - 1) / blockDim.x;
-    const long long ntasks = chunks * ((n - 1 + kRowGroup - 1) / kRowGroup);
+    const long long ntasks = row_task_count(w, n - 1);
     for (long long task = blockIdx.x; task < ntasks; task += gridDim.x) {
-        const RowTask t = row_task(task, chunks, w);
+        const RowTask t = row_task(task, w, n - 1);
         if (!t.live) continue;
         const long long at0 = (long long)t.row * w + t.col;
         T kv[kRowGroup + 1], yv[kRowGroup + 1];
@@ -625,9 +629,8 @@ cudaError_t launch_spline_sweep(int len, int nsys, long long w, const T* fac, si
 }
 
 static int row_group_grid(long long w, long long nrows) {
-    const long long chunks = (w + 255) / 256;
     const long long cap = (long long)device_info().sm_count * 8;
-    const long long tasks = chunks * ((nrows + kRowGroup - 1) / kRowGroup);
+    const long long tasks = (((nrows + kRowGroup - 1) / kRowGroup) * w + 255) / 256;
     return (int)(tasks < cap ? tasks : cap);
 }
 
