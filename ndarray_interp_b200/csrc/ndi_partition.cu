@@ -351,50 +351,63 @@ __global__ void __launch_bounds__(256) part_corr_kernel(const PartPlan pl, int l
 // :354-365) in one pass; k is formed in registers only.  A thread takes kRowGroup consecutive intervals of one column (the
 // item layout of spline_ab_kernel) and the k of their kRowGroup + 1 rows; the separator rows it needs are read by every
 // thread of the block's eight row groups, out of L2.
-template <class T>
+template <class T, int V>
 __global__ void __launch_bounds__(256) part_ab_kernel(const PartPlan pl, T* fac, size_t fac_stride, const T* __restrict__ R,
                                                       const T* __restrict__ y, int n, long long w, T* __restrict__ a, T* __restrict__ b,
                                                       const int32_t* __restrict__ lks, const int32_t* __restrict__ rks) {
     const PartLevel L = pl.lv[0];
     const int m = pl.m, P = L.len / m;
     const T* dx = fac;
-    const long long groups = (n - 1 + kRowGroup - 1) / kRowGroup;
-    const long long ntasks = (groups * w + blockDim.x - 1) / blockDim.x;
+    const long long wv = w / V, ntasks = row_task_count(wv, n - 1, blockDim.x);
     for (long long task = blockIdx.x; task < ntasks; task += gridDim.x) {
-        const long long item = task * blockDim.x + threadIdx.x;        // consecutive threads: consecutive columns, then the next row group
-        const long long g = item / w, col = item - g * w;
-        if (g >= groups) continue;
-        const int row = (int)g * kRowGroup;
-        T* facb = fac + (lks ? (size_t)part_group(lks, rks, col) * fac_stride : 0);
+        const RowTask t = row_task(task, wv, n - 1);
+        if (!t.live) continue;
+        const long long col = t.col * V;
+        const int row = t.row;
+        T* facb = fac + (lks ? (size_t)part_group(lks, rks, col) * fac_stride : 0);     // V == 1 with Individual boundaries
         const PartArrays<T> pa(facb, L);
-        auto Rat = [&](int i) -> T { return R[(long long)i * w + col]; };
-        T kv[kRowGroup + 1], yv[kRowGroup + 1];
+        T kv[kRowGroup + 1][V], yv[kRowGroup + 1][V];
 #pragma unroll
         for (int j = 0; j <= kRowGroup; ++j) {
             const int i = min(row + j, n - 1);
-            kv[j] = Rat(i);
-            yv[j] = __ldg(y + (long long)i * w + col);
+            ld_vec<T, V>(R + (long long)i * w + col, kv[j]);
+            ld_vec<T, V>(y + (long long)i * w + col, yv[j]);
         }
         // the rows of a group lie in at most two blocks: separators of the first row's block, and the one after them
         const int c0 = row / m;
-        const T s0 = c0 > 0 ? Rat(c0 * m - 1) : (T)0, s1 = c0 < P ? Rat(c0 * m + m - 1) : (T)0,
-                s2 = c0 + 1 < P ? Rat(c0 * m + 2 * m - 1) : (T)0;
+        T s0[V], s1[V], s2[V];
+#pragma unroll
+        for (int c = 0; c < V; ++c) s0[c] = s1[c] = s2[c] = (T)0;
+        if (c0 > 0) ld_vec<T, V>(R + (long long)(c0 * m - 1) * w + col, s0);
+        if (c0 < P) ld_vec<T, V>(R + (long long)(c0 * m + m - 1) * w + col, s1);
+        if (c0 + 1 < P) ld_vec<T, V>(R + (long long)(c0 * m + 2 * m - 1) * w + col, s2);
 #pragma unroll
         for (int j = 0; j <= kRowGroup; ++j) {
             const int i = min(row + j, n - 1);
-            const int c = i / m;
-            if (!(c < P && i - c * m == m - 1)) {
-                const T kl = c == c0 ? s0 : s1, kr = c == c0 ? s1 : s2;
-                kv[j] = FMA(-__ldg(pa.q + i), kr, FMA(-__ldg(pa.p + i), kl, kv[j]));
+            const int cb = i / m;
+            if (!(cb < P && i - cb * m == m - 1)) {
+                const T pi = __ldg(pa.p + i), qi = __ldg(pa.q + i);
+#pragma unroll
+                for (int c = 0; c < V; ++c) {
+                    const T kl = cb == c0 ? s0[c] : s1[c], kr = cb == c0 ? s1[c] : s2[c];
+                    kv[j][c] = FMA(-qi, kr, FMA(-pi, kl, kv[j][c]));
+                }
             }
         }
 #pragma unroll
         for (int j = 0; j < kRowGroup; ++j) {
             const int i = row + j;
             if (i >= n - 1) break;
-            const T d = __ldg(dx + i), dy = SUB(yv[j + 1], yv[j]);
-            a[(long long)i * w + col] = SUB(MUL(kv[j], d), dy);
-            b[(long long)i * w + col] = SUB(dy, MUL(kv[j + 1], d));
+            const T d = __ldg(dx + i);
+            T av[V], bv[V];
+#pragma unroll
+            for (int c = 0; c < V; ++c) {
+                const T dy = SUB(yv[j + 1][c], yv[j][c]);
+                av[c] = SUB(MUL(kv[j][c], d), dy);
+                bv[c] = SUB(dy, MUL(kv[j + 1][c], d));
+            }
+            st_vec<T, V>(a + (long long)i * w + col, av);
+            st_vec<T, V>(b + (long long)i * w + col, bv);
         }
     }
 }
@@ -507,9 +520,11 @@ cudaError_t launch_partition_build(const T* x, int64_t n, const T* data, int64_t
         if (periodic && (e = launch_spline_periodic_close<T>(x, (int)n, (long long)w, fac, R, st)) != cudaSuccess) return e;
         return launch_spline_ab<T>(x, (int)n, data, (long long)w, periodic, fac, R, a, b, nullptr, st);
     }
-    const long long tasks = (((n - 1 + kRowGroup - 1) / kRowGroup) * (long long)w + 255) / 256;
-    const long long cap = (long long)device_info().sm_count * 8;
-    part_ab_kernel<T><<<(unsigned)(tasks < cap ? tasks : cap), 256, 0, st>>>(pl, fac, fac_stride, R, data, (int)n, (long long)w, a, b, ilk, rk);
+    constexpr int V = 16 / sizeof(T);
+    if (!ilk && vec_ok<T>(w, data, R, a, b))
+        part_ab_kernel<T, V><<<row_group_grid(w / V, n - 1), 256, 0, st>>>(pl, fac, fac_stride, R, data, (int)n, (long long)w, a, b, nullptr, nullptr);
+    else
+        part_ab_kernel<T, 1><<<row_group_grid(w, n - 1), 256, 0, st>>>(pl, fac, fac_stride, R, data, (int)n, (long long)w, a, b, ilk, rk);
     count_launch();
     return cudaGetLastError();
 }

@@ -236,43 +236,27 @@ __device__ __forceinline__ T lds_elem(unsigned smem_addr) {
     return v;
 }
 
-// a thread works on (group of kRowGroup rows, column) items, consecutive threads on consecutive columns -- wrapping
-// into the next row group, so that narrow tables keep every thread busy too (a block of 256 threads per 64 columns
-// left three quarters of them idle: 65536 x 64 f64, right-hand sides 69 us); a task is blockDim.x consecutive
-// items, `chunks` the number of tasks; grid-stride over the tasks
-struct RowTask { int row; long long col; bool live; };
-__device__ __forceinline__ long long row_task_count(long long w, long long nrows) {
-    return (((nrows + kRowGroup - 1) / kRowGroup) * w + blockDim.x - 1) / blockDim.x;
-}
-__device__ __forceinline__ RowTask row_task(long long task, long long w, long long nrows) {
-    const long long item = task * blockDim.x + threadIdx.x;
-    const long long g = item / w;
-    return RowTask{(int)g * kRowGroup, item - g * w, g * kRowGroup < nrows};
-}
-
 // launch 1: right-hand sides.  Non-periodic: R[0] = left boundary row, R[1..n-2] = interior rows (:468),
 // R[n-1] = right boundary row.  Periodic (n > 3): R[0] = condensed first row (:529-530), R[1..n-3] interior,
 // R[n-2] = the last condensed equation's right-hand side (:531-532), kept for k_m1; columns whose first
 // and last value differ are reported through err (:499-507).
-template <class T>
+template <class T, int V>
 __global__ void __launch_bounds__(256) spline_rhs_kernel(const T* __restrict__ x, int n, const T* __restrict__ y, long long w,
                                                          int periodic, Side<T> left, Side<T> right, T* __restrict__ R,
                                                          unsigned long long* err, const int32_t* __restrict__ lks = nullptr,
                                                          const T* __restrict__ lvs = nullptr, const int32_t* __restrict__ rks = nullptr,
                                                          const T* __restrict__ rvs = nullptr, const int32_t* __restrict__ pos = nullptr) {
-    Side<T> l = specialize(left), r = specialize(right);
     const T three = (T)3;
     const int rows = periodic ? n - 1 : n;
-    const long long ntasks = row_task_count(w, rows);
+    const long long wv = w / V, ntasks = row_task_count(wv, rows, blockDim.x);
     for (long long task = blockIdx.x; task < ntasks; task += gridDim.x) {
-        const RowTask t = row_task(task, w, rows);
+        const RowTask t = row_task(task, wv, rows);
         if (!t.live) continue;
-        const T* ycol = y + t.col;
-        auto Y = [&](int row) -> T { return __ldg(ycol + (long long)row * w); };
+        const long long col0 = t.col * V;
         // window y[row-1 .. row+kRowGroup] shared by the rows of the group (clamped at the ends, where it is not used)
-        T yv[kRowGroup + 2];
+        T yv[kRowGroup + 2][V];
 #pragma unroll
-        for (int j = 0; j < kRowGroup + 2; ++j) yv[j] = Y(min(max(t.row - 1 + j, 0), n - 1));
+        for (int j = 0; j < kRowGroup + 2; ++j) ld_vec<T, V>(y + (long long)min(max(t.row - 1 + j, 0), n - 1) * w + col0, yv[j]);
         // grid steps of the intervals row-1 .. row+kRowGroup-1 and their reciprocals: the two divisions of an interior
         // row are divisions by grid steps, the same for all columns -- formed once per row group, every quotient is
         // the IEEE quotient (ndi_device.cuh, Hoisted) at 3 operations instead of ~25
@@ -287,33 +271,47 @@ __global__ void __launch_bounds__(256) spline_rhs_kernel(const T* __restrict__ x
         for (int j = 0; j < kRowGroup; ++j) {
             const int i = t.row + j;
             if (i >= rows) break;
-            T v;
+            T out[V];
             const bool interior = periodic ? (i > 0 && i < n - 2) : (i > 0 && i < n - 1);
             if (interior) {
                 const T dxn = dv[j + 1], dxn_1 = dv[j];                               // x[i+1] - x[i], x[i] - x[i-1]
-                v = MUL(three, ADD(Hoisted<T>::div(MUL(dxn, SUB(yv[j + 1], yv[j])), dxn_1, rv[j]),
-                                   Hoisted<T>::div(MUL(dxn_1, SUB(yv[j + 2], yv[j + 1])), dxn, rv[j + 1])));   // :468
-            } else if (periodic) {
-                const T dx0 = SUB(x[1], x[0]), dx_1 = SUB(x[n - 1], x[n - 2]), dx_2 = SUB(x[n - 2], x[n - 3]);
-                if (i == 0) {
-                    const T y0 = Y(0), yN = Y(n - 1);
-                    if (y0 != yN) atomicMin(err, (unsigned long long)t.col);
-                    const T slope0 = DIV(SUB(Y(1), y0), dx0);                         // :521
-                    const T slope_1 = DIV(SUB(yN, Y(n - 2)), dx_1);                   // :526
-                    v = MUL(ADD(MUL(slope_1, dx0), MUL(slope0, dx_1)), three);        // :529-530
-                } else {
-                    const T yn2 = Y(n - 2);
-                    const T slope_1 = DIV(SUB(Y(n - 1), yn2), dx_1), slope_2 = DIV(SUB(yn2, Y(n - 3)), dx_2);   // :526-527
-                    v = MUL(ADD(MUL(slope_2, dx_1), MUL(slope_1, dx_2)), three);      // :531-532
-                }
-            } else if (i == 0) {
-                if (lks) l = specialize(Side<T>{lks[t.col], lvs[t.col]});             // Individual: this column's own boundary
-                v = rhs_left<T>(x, l, Y(0), Y(1), Y(2));
+#pragma unroll
+                for (int c = 0; c < V; ++c)
+                    out[c] = MUL(three, ADD(Hoisted<T>::div(MUL(dxn, SUB(yv[j + 1][c], yv[j][c])), dxn_1, rv[j]),
+                                            Hoisted<T>::div(MUL(dxn_1, SUB(yv[j + 2][c], yv[j + 1][c])), dxn, rv[j + 1])));   // :468
             } else {
-                if (rks) r = specialize(Side<T>{rks[t.col], rvs[t.col]});
-                v = rhs_right<T>(x, n, r, Y(n - 1), Y(n - 2), Y(n - 3));
+#pragma unroll 1
+                for (int c = 0; c < V; ++c) {
+                    const long long col = col0 + c;
+                    const T* ycol = y + col;
+                    auto Y = [&](int row) -> T { return __ldg(ycol + (long long)row * w); };
+                    T v;
+                    if (periodic) {
+                        const T dx0 = SUB(x[1], x[0]), dx_1 = SUB(x[n - 1], x[n - 2]), dx_2 = SUB(x[n - 2], x[n - 3]);
+                        if (i == 0) {
+                            const T y0 = Y(0), yN = Y(n - 1);
+                            if (y0 != yN) atomicMin(err, (unsigned long long)col);
+                            const T slope0 = DIV(SUB(Y(1), y0), dx0);                 // :521
+                            const T slope_1 = DIV(SUB(yN, Y(n - 2)), dx_1);           // :526
+                            v = MUL(ADD(MUL(slope_1, dx0), MUL(slope0, dx_1)), three);   // :529-530
+                        } else {
+                            const T yn2 = Y(n - 2);
+                            const T slope_1 = DIV(SUB(Y(n - 1), yn2), dx_1), slope_2 = DIV(SUB(yn2, Y(n - 3)), dx_2);   // :526-527
+                            v = MUL(ADD(MUL(slope_2, dx_1), MUL(slope_1, dx_2)), three);   // :531-532
+                        }
+                    } else if (i == 0) {
+                        // Individual: this column's own boundary
+                        const Side<T> l = specialize(lks ? Side<T>{lks[col], lvs[col]} : left);
+                        v = rhs_left<T>(x, l, Y(0), Y(1), Y(2));
+                    } else {
+                        const Side<T> r = specialize(rks ? Side<T>{rks[col], rvs[col]} : right);
+                        v = rhs_right<T>(x, n, r, Y(n - 1), Y(n - 2), Y(n - 3));
+                    }
+                    out[c] = v;
+                }
             }
-            R[(long long)i * w + (pos ? pos[t.col] : t.col)] = v;                     // Individual: columns grouped by matrix
+            if (V == 1 && pos) R[(long long)i * w + pos[col0]] = out[0];              // Individual: columns grouped by matrix
+            else st_vec<T, V>(R + (long long)i * w + col0, out);
         }
     }
 }
@@ -496,36 +494,50 @@ __global__ void __launch_bounds__(256) spline_periodic_close_kernel(const T* __r
 
 // launch 3: a[i] = k[i] dx - dy, b[i] = dy - k[i+1] dx (:354-365).  Periodic: k[i] = k1[i] + k_m1 k2[i]
 // for i < n-2 (:559-561), rows n-2 and n-1 of R already hold k.
-template <class T>
+template <class T, int V>
 __global__ void __launch_bounds__(256) spline_ab_kernel(const T* __restrict__ x, int n, const T* __restrict__ y, long long w,
                                                         int periodic, const T* __restrict__ fac, const T* __restrict__ R,
                                                         T* __restrict__ a, T* __restrict__ b, const int32_t* __restrict__ pos = nullptr) {
     const T* k2 = fac + 4 * (size_t)n;
-    const long long ntasks = row_task_count(w, n - 1);
+    const long long wv = w / V, ntasks = row_task_count(wv, n - 1, blockDim.x);
     for (long long task = blockIdx.x; task < ntasks; task += gridDim.x) {
-        const RowTask t = row_task(task, w, n - 1);
+        const RowTask t = row_task(task, wv, n - 1);
         if (!t.live) continue;
-        const long long at0 = (long long)t.row * w + t.col;
-        T kv[kRowGroup + 1], yv[kRowGroup + 1];
+        const long long col0 = t.col * V;
+        const long long at0 = (long long)t.row * w + col0;
+        const long long rcol = (V == 1 && pos) ? pos[col0] : col0;
+        T kv[kRowGroup + 1][V], yv[kRowGroup + 1][V];
 #pragma unroll
         for (int j = 0; j <= kRowGroup; ++j) {
             const int i = min(t.row + j, n - 1);
-            kv[j] = R[(long long)i * w + (pos ? pos[t.col] : t.col)];
-            yv[j] = __ldg(y + (long long)i * w + t.col);
+            ld_vec<T, V>(R + (long long)i * w + rcol, kv[j]);
+            ld_vec<T, V>(y + (long long)i * w + col0, yv[j]);
         }
         if (periodic) {
-            const T k_m1 = R[(long long)(n - 2) * w + t.col];
+            T k_m1[V];
+            ld_vec<T, V>(R + (long long)(n - 2) * w + col0, k_m1);
 #pragma unroll
             for (int j = 0; j <= kRowGroup; ++j)
-                if (t.row + j < n - 2) kv[j] = ADD(kv[j], MUL(k_m1, k2[t.row + j]));
+                if (t.row + j < n - 2) {
+                    const T k2v = k2[t.row + j];
+#pragma unroll
+                    for (int c = 0; c < V; ++c) kv[j][c] = ADD(kv[j][c], MUL(k_m1[c], k2v));
+                }
         }
 #pragma unroll
         for (int j = 0; j < kRowGroup; ++j) {
             const int i = t.row + j;
             if (i >= n - 1) break;
-            const T dx = SUB(x[i + 1], x[i]), dy = SUB(yv[j + 1], yv[j]);
-            a[at0 + (long long)j * w] = SUB(MUL(kv[j], dx), dy);
-            b[at0 + (long long)j * w] = SUB(dy, MUL(kv[j + 1], dx));
+            const T dx = SUB(x[i + 1], x[i]);
+            T av[V], bv[V];
+#pragma unroll
+            for (int c = 0; c < V; ++c) {
+                const T dy = SUB(yv[j + 1][c], yv[j][c]);
+                av[c] = SUB(MUL(kv[j][c], dx), dy);
+                bv[c] = SUB(dy, MUL(kv[j + 1][c], dx));
+            }
+            st_vec<T, V>(a + at0 + (long long)j * w, av);
+            st_vec<T, V>(b + at0 + (long long)j * w, bv);
         }
     }
 }
@@ -628,16 +640,30 @@ cudaError_t launch_spline_sweep(int len, int nsys, long long w, const T* fac, si
     return cudaGetLastError();
 }
 
-static int row_group_grid(long long w, long long nrows) {
+int row_group_grid(long long wv, long long nrows) {
     const long long cap = (long long)device_info().sm_count * 8;
-    const long long tasks = (((nrows + kRowGroup - 1) / kRowGroup) * w + 255) / 256;
+    const long long tasks = row_task_count(wv, nrows, 256);
     return (int)(tasks < cap ? tasks : cap);
 }
 
 template <class T>
 cudaError_t launch_spline_ab(const T* x, int n, const T* y, long long w, int periodic, const T* fac, const T* R, T* a, T* b,
                              const int32_t* pos, cudaStream_t st) {
-    spline_ab_kernel<T><<<row_group_grid(w, n - 1), 256, 0, st>>>(x, n, y, w, periodic, fac, R, a, b, pos);
+    constexpr int V = 16 / sizeof(T);
+    if (!pos && vec_ok<T>(w, y, R, a, b)) spline_ab_kernel<T, V><<<row_group_grid(w / V, n - 1), 256, 0, st>>>(x, n, y, w, periodic, fac, R, a, b, nullptr);
+    else spline_ab_kernel<T, 1><<<row_group_grid(w, n - 1), 256, 0, st>>>(x, n, y, w, periodic, fac, R, a, b, pos);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <class T>
+static cudaError_t launch_spline_rhs_pos(const T* x, int n, const T* y, long long w, int periodic, Side<T> left, Side<T> right, T* R,
+                                         unsigned long long* err, const int32_t* lks, const T* lvs, const int32_t* rks, const T* rvs,
+                                         const int32_t* pos, cudaStream_t st) {
+    constexpr int V = 16 / sizeof(T);
+    const int rows = periodic ? n - 1 : n;
+    if (!pos && vec_ok<T>(w, y, R, R, R)) spline_rhs_kernel<T, V><<<row_group_grid(w / V, rows), 256, 0, st>>>(x, n, y, w, periodic, left, right, R, err, lks, lvs, rks, rvs, nullptr);
+    else spline_rhs_kernel<T, 1><<<row_group_grid(w, rows), 256, 0, st>>>(x, n, y, w, periodic, left, right, R, err, lks, lvs, rks, rvs, pos);
     count_launch();
     return cudaGetLastError();
 }
@@ -646,9 +672,7 @@ template <class T>
 cudaError_t launch_spline_rhs(const T* x, int n, const T* y, long long w, int periodic, Side<T> left, Side<T> right, T* R,
                               unsigned long long* err, const int32_t* lks, const T* lvs, const int32_t* rks, const T* rvs,
                               cudaStream_t st) {
-    spline_rhs_kernel<T><<<row_group_grid(w, periodic ? n - 1 : n), 256, 0, st>>>(x, n, y, w, periodic, left, right, R, err, lks, lvs, rks, rvs, nullptr);
-    count_launch();
-    return cudaGetLastError();
+    return launch_spline_rhs_pos<T>(x, n, y, w, periodic, left, right, R, err, lks, lvs, rks, rvs, nullptr, st);
 }
 
 template <class T>
@@ -690,10 +714,7 @@ cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w,
             spline_factor_kernel<T><<<9, kFacBlock, 0, st>>>(x, (int)n, 0, 0, 0, scratch, fac_elems);
             count_launch();
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            spline_rhs_kernel<T><<<row_group_grid(w, n), 256, 0, st>>>(x, (int)n, data, (long long)w, 0, Side<T>{SB_NAK, (T)0}, Side<T>{SB_NAK, (T)0}, R, err,
-                                                                       lk, lv, rk, rv, pos);
-            count_launch();
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if ((e = launch_spline_rhs_pos<T>(x, (int)n, data, (long long)w, 0, Side<T>{SB_NAK, (T)0}, Side<T>{SB_NAK, (T)0}, R, err, lk, lv, rk, rv, pos, st)) != cudaSuccess) return e;
         }
         if ((e = launch_spline_sweep<T>((int)n, nsys, (long long)w, scratch, fac_elems, R, group_count, st)) != cudaSuccess) return e;
         return launch_spline_ab<T>(x, (int)n, data, (long long)w, 0, scratch, R, a, b, pos, st);
@@ -711,10 +732,7 @@ cudaError_t launch_spline_build(const T* x, int64_t n, const T* data, int64_t w,
             spline_factor_kernel<T><<<1, kFacBlock, 0, st>>>(x, (int)n, periodic, ls.kind, rs.kind, scratch, 0);
             count_launch();
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            const int rows = periodic ? (int)n - 1 : (int)n;
-            spline_rhs_kernel<T><<<row_group_grid(w, rows), 256, 0, st>>>(x, (int)n, data, (long long)w, periodic, l, r, R, err);
-            count_launch();
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if ((e = launch_spline_rhs<T>(x, (int)n, data, (long long)w, periodic, l, r, R, err, nullptr, nullptr, nullptr, nullptr, st)) != cudaSuccess) return e;
         }
         if ((e = launch_spline_sweep<T>(periodic ? (int)n - 2 : (int)n, nsys, (long long)w, scratch, 0, R, nullptr, st)) != cudaSuccess) return e;
         if (periodic && (e = launch_spline_periodic_close<T>(x, (int)n, (long long)w, scratch, R, st)) != cudaSuccess) return e;

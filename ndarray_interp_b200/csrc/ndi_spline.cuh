@@ -140,6 +140,47 @@ cudaError_t launch_spline_sweep(int len, int nsys, long long w, const T* fac, si
                                 const int64_t* counts, cudaStream_t st);
 
 constexpr int kRowGroup = 4;              // rhs / ab kernels: rows per thread, sharing their loads
+int row_group_grid(long long wv, long long nrows);      // grid for items of kRowGroup rows x one vector of columns
+// V consecutive columns as one 16-byte access (V == 1: a plain element)
+template <class T, int V>
+__device__ __forceinline__ void ld_vec(const T* __restrict__ p, T (&out)[V]) {
+    if constexpr (V == 1) out[0] = __ldg(p);
+    else {
+        static_assert(sizeof(T) * V == 16, "one 16-byte vector");
+        const int4 q = __ldg(reinterpret_cast<const int4*>(p));
+        memcpy(out, &q, 16);
+    }
+}
+template <class T, int V>
+__device__ __forceinline__ void st_vec(T* __restrict__ p, const T (&in)[V]) {
+    if constexpr (V == 1) *p = in[0];
+    else { int4 q; memcpy(&q, in, 16); *reinterpret_cast<int4*>(p) = q; }
+}
+template <class T>
+inline bool vec_ok(long long w, const void* p0, const void* p1, const void* p2, const void* p3) {
+    return w % (long long)(16 / sizeof(T)) == 0 &&
+           (((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)p3) & 15) == 0;
+}
+// The elementwise kernels (right-hand sides, a / b) work on items of kRowGroup rows x V columns, V columns being one
+// 16-byte vector (V = 1 when the row length or a pointer does not allow it): a thread that requests 4-byte words
+// keeps too few bytes in flight to fill the memory system (4096 x 16384 f32: 363 us for 537 MB, profiles/r02).  A
+// task is blockDim.x items: a chunk of columns of one row group, or -- tables narrower than a block -- consecutive
+// items wrapping into the next row groups, so that every thread stays busy; grid-stride over the tasks.
+struct RowTask { int row; long long col; bool live; };      // col: in vectors
+__host__ __device__ inline long long row_task_count(long long wv, long long nrows, int block) {
+    const long long groups = (nrows + kRowGroup - 1) / kRowGroup;
+    return wv >= block ? groups * ((wv + block - 1) / block) : (groups * wv + block - 1) / block;
+}
+__device__ __forceinline__ RowTask row_task(long long task, long long wv, long long nrows) {
+    if (wv >= blockDim.x) {
+        const long long chunks = (wv + blockDim.x - 1) / blockDim.x, g = task / chunks;
+        const long long col = (task - g * chunks) * blockDim.x + threadIdx.x;
+        return RowTask{(int)g * kRowGroup, col, col < wv};
+    }
+    const long long item = task * blockDim.x + threadIdx.x, g = item / wv;
+    return RowTask{(int)g * kRowGroup, item - g * wv, g * kRowGroup < nrows};
+}
+
 template <class T>
 cudaError_t launch_spline_ab(const T* x, int n, const T* y, long long w, int periodic, const T* fac, const T* R, T* a, T* b,
                              const int32_t* pos, cudaStream_t st);

@@ -1,14 +1,14 @@
 #!/bin/bash
-# round 2, call 15: partition build after the dense item layout: spline parity tests, wall times, launch lists at the
+# round 2, call 16: partition build after the dense item layout: spline parity tests, wall times, launch lists at the
 # C2, long and many-column shapes
 mkdir -p gpurun_out
-T=gpurun_out/r2c15
-timeout 900 python -m pytest tests/test_partition_gpu.py tests/test_rowsplit_gpu.py tests/test_parity_spline_gpu.py tests/test_reference_cubic_spline.py -m gpu -q --maxfail=20 -p no:cacheprovider > ${T}_pytest.log 2>&1
+T=gpurun_out/r2c16
+timeout 900 python -m pytest tests/test_partition_gpu.py tests/test_rowsplit_gpu.py tests/test_parity_spline_gpu.py tests/test_reference_cubic_spline.py tests/test_fuzz_gpu.py tests/test_fullsize_gpu.py -m gpu -q --maxfail=20 -p no:cacheprovider > ${T}_pytest.log 2>&1
 echo "pytest rc=$?"; tail -5 ${T}_pytest.log
 python scripts/bench_spline_build.py --levels 0 --blocks 0 --bc Natural,Periodic,Individual > ${T}_build.jsonl 2> ${T}_build.err || tail -c 600 ${T}_build.err
 python - <<'PY'
 import json
-for ln in open('gpurun_out/r2c15_build.jsonl'):
+for ln in open('gpurun_out/r2c16_build.jsonl'):
     d = json.loads(ln); print('%-10s %-10s %-10s %4d  %.4f ms  %.0f GB/s' % (d['shape'], d['boundary'], d['mode'], d['levels'], d['ms'], d['algorithmic_GBps']))
 PY
 python scripts/bench_spline_build.py c2 long c5b-shard wide --levels 0 --blocks 0 --bc Natural > ${T}_plain.log 2>&1 && \
@@ -16,7 +16,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ${T}_
 python - <<'PY'
 import csv
 try:
-    rows = [r for r in csv.reader(open('gpurun_out/r2c15_launches.csv')) if len(r) > 5]
+    rows = [r for r in csv.reader(open('gpurun_out/r2c16_launches.csv')) if len(r) > 5]
     h = rows[0]; ki, vi = h.index('Kernel Name'), h.index('Metric Value')
     seq = [(r[ki][:64], float(r[vi].replace(',', '')) / 1000) for r in rows[1:]]
     # last partition build of every shape: find the last 'part_ab' launches separated by shape changes (time jumps)
