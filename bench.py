@@ -262,10 +262,17 @@ def cpu_baseline_for(wl, tables, coeffs, qx, qy, budget_s, how):
 
 
 def oracle_coeffs(tables, levels):
+    """levels: ndi_interp1d_build_info's value (0 reference order, L > 0 row-split levels, -m partition blocks)"""
     from oracle import oracle_py as O
-    st, a, b = O.spline_build(tables["x"], tables["data"], {"kind": "Natural"}, rowsplit_levels=levels)
+    st, a, b = O.spline_build_as(tables["x"], tables["data"], {"kind": "Natural"}, levels)
     assert st == 0
     return a, b
+
+
+def build_spec_name(levels):
+    if levels > 0:
+        return "row-split specification with %d levels" % levels
+    return ("partition specification with blocks of %d rows" % -levels) if levels < 0 else "reference order"
 
 
 # ---- the reference arm: the reference's own CPU implementation of the path (here: its restatement) ---------------
@@ -587,7 +594,7 @@ def measure_eval(ctx, name, wl, steps, warmup, role, sampler=None):
                      "frac_of_nominal_8000": achieved / 8000.0},
     })
     if levels or wl["kind"] == "cubic":
-        res["spline_rowsplit_levels"] = levels
+        res["spline_build_info"] = levels                     # 0 reference order, L > 0 row-split levels, -m partition blocks
 
     # ---- check: sampled rows, bit for bit against the oracle, for every rank's shard (also at world > 1) ----
     nsamp = 256 if wl["w"] >= 256 else 1024
@@ -611,7 +618,7 @@ def measure_eval(ctx, name, wl, steps, warmup, role, sampler=None):
             a_dev, b_dev = ip.coeffs_to_host()
             res["check"]["coefficients_bit_exact"] = bool(np.array_equal(a_dev.reshape(coeffs[0].shape), coeffs[0]) and
                                                           np.array_equal(b_dev.reshape(coeffs[1].shape), coeffs[1]))
-            res["check"]["coefficients_vs"] = ("oracle, row-split specification with %d levels" % levels) if levels else "oracle, reference order"
+            res["check"]["coefficients_vs"] = "oracle, " + build_spec_name(levels)
 
     # ---- end to end through the host-array API (pinned host buffers, H2D + D2H in the timed region) ----
     e2e_q = int(min(nq, max(1 << 14, (1 << 31) // (wl["w"] * s)))) if role != "headline" else nq    # <= 2 GB of result rows
@@ -689,7 +696,7 @@ def measure_eval(ctx, name, wl, steps, warmup, role, sampler=None):
 
 
 def time_builds(ctx, ip, wl):
-    """K6 on its own: CubicSpline::calc_coefficients for this table in both build modes (host-synchronous calls,
+    """K6 on its own: CubicSpline::calc_coefficients for this table in the three build modes (host-synchronous calls,
     wall clock per call including allocation and the final synchronisation; kernels alone by CUDA events are in
     profiles/)"""
     from ndarray_interp_b200 import _lib as L
@@ -698,7 +705,7 @@ def time_builds(ctx, ip, wl):
     out = {"columns": wl["w"], "rows": wl["n"], "algorithmic_bytes": s * (3 * wl["n"] - 2) * wl["w"],
            "note": "ndi_interp1d_spline_build, Natural boundary, wall clock per call (allocation + launches + final sync)"}
     peak, _ = measured_peak()
-    for label, mode in (("sequential", L.BUILD_SEQUENTIAL), ("rowsplit", L.BUILD_ROWSPLIT)):
+    for label, mode in (("sequential", L.BUILD_SEQUENTIAL), ("rowsplit", L.BUILD_ROWSPLIT), ("partition", L.BUILD_PARTITION)):
         ip.set_build_mode(mode, 0)
         for _ in range(3):
             ip.spline_build(BC_NATURAL)
@@ -714,7 +721,9 @@ def time_builds(ctx, ip, wl):
     st, _ = ip.spline_build(BC_NATURAL)                       # leave the handle with the AUTO coefficients
     assert st == 0
     out["auto_levels"] = ip.build_levels()
-    out["ms"] = out["rowsplit" if out["auto_levels"] else "sequential"]["ms"]
+    out["auto"] = "partition" if out["auto_levels"] < 0 else ("rowsplit" if out["auto_levels"] else "sequential")
+    out["ms"] = out[out["auto"]]["ms"]
+    out["frac_of_hbm_peak"] = out[out["auto"]]["frac_of_hbm_peak"]
     return out
 
 
@@ -767,7 +776,7 @@ def measure_build(ctx, name, wl, steps, warmup):
     moved = s * (3 * n - 2) * w
     peak, _ = measured_peak()
     res = {"workload": f"{name}: {wl['desc']}", "dtype": "f32", "scaling": "strong", "columns_per_gpu": cw, "rows": n,
-           "rowsplit_levels": levels, "build_ms": build_ms, "value": w / (build_ms * 1e-3), "unit": "columns/s",
+           "build_info": levels, "build_ms": build_ms, "value": w / (build_ms * 1e-3), "unit": "columns/s",
            "algorithmic_bytes_per_gpu": moved // world, "algorithmic_GBps_per_gpu": moved / world / build_ms / 1e6,
            "frac_of_hbm_peak": moved / world / build_ms / 1e6 / peak,
            "allgather_ms": gather_ms, "allgather_bytes_received_per_gpu": 2 * (world - 1) * (n - 1) * cw * s,
@@ -779,7 +788,7 @@ def measure_build(ctx, name, wl, steps, warmup):
         for r in range(world):
             cols = np.sort(np.random.default_rng(r).choice(cw, 16, replace=False))
             yr = (y if r == rank else shard_data(r))[:, torch.from_numpy(cols).to(dev)].cpu().numpy()
-            st, a_ref, b_ref = O.spline_build(x_host, np.ascontiguousarray(yr), {"kind": "Natural"}, rowsplit_levels=levels)
+            st, a_ref, b_ref = O.spline_build_as(x_host, np.ascontiguousarray(yr), {"kind": "Natural"}, levels)
             src_a = a_full[r] if world > 1 else a_full
             src_b = b_full[r] if world > 1 else b_full
             ga = src_a[:, torch.from_numpy(cols).to(dev)].cpu().numpy()
@@ -788,7 +797,7 @@ def measure_build(ctx, name, wl, steps, warmup):
             ncols += len(cols)
         res["check"] = {"bit_exact": ok, "columns": ncols, "ranks": world,
                         "what": "16 columns of every rank's shard of the all-gathered a, b against the oracle "
-                                + (f"(row-split specification, {levels} levels)" if levels else "(reference order)")}
+                                + "(" + build_spec_name(levels) + ")"}
     del part, y, a_full, b_full
     torch.cuda.empty_cache()
     return res
@@ -875,7 +884,7 @@ def run_b200(args):
                        "tables": "generated on rank 0, replicated per GPU by NCCL broadcast; queries sharded, no collective in the timed region",
                        "search_mode": args.search_mode, "numa_node": numa,
                        "launches_per_step": head.get("launches_per_step"),
-                       "spline_route": head.get("spline_route"), "spline_rowsplit_levels": head.get("spline_rowsplit_levels"),
+                       "spline_route": head.get("spline_route"), "spline_build_info": head.get("spline_build_info"),
                        "timed": "every step between its own CUDA events on the launch stream; ms_per_step = (first start -> last end) / steps, "
                                 "max over ranks; per_step = median / best / worst of the same steps",
                        "kernel_source_hash": kernel_source_hash()},

@@ -333,7 +333,8 @@ class CubicSplineStrategy : public Interp1DStrategy<T> {
 public:
     CubicSplineStrategy(BoundaryCondition<T> bc, int mode, int build_mode = NDI_BUILD_AUTO, int build_levels = 0)
         : bc_(std::move(bc)), mode_(mode), build_mode_(build_mode), build_levels_(build_levels) {}
-    // depth of the row-split the coefficients were built with (0: the reference's elimination order)
+    // how the coefficients were built (ndi_interp1d_build_info): 0 the reference's elimination order, L > 0 row-split
+    // with L levels, -m < 0 partition with blocks of m rows
     int rowsplit_levels(const Interp1D<T>& ip) const;
     bool uses_device() const override { return true; }
     void bind(const Interp1D<T>& ip) const override;         // CubicSpline::calc_coefficients (:310-368) on the device
@@ -354,8 +355,8 @@ public:
     CubicSpline extrapolate(bool e) const { CubicSpline c(*this); c.extrapolate_ = e; return c; }
     CubicSpline boundary(BoundaryCondition<T> b) const { CubicSpline c(*this); c.boundary_ = std::move(b); return c; }
     // NOT in the reference (ndi_interp1d_set_build_mode): NDI_BUILD_AUTO, NDI_BUILD_SEQUENTIAL -- the reference's
-    // elimination order, coefficients bit-identical to its arithmetic -- or NDI_BUILD_ROWSPLIT with `levels` steps of
-    // cyclic reduction (0: the library's choice)
+    // elimination order, coefficients bit-identical to its arithmetic --, NDI_BUILD_ROWSPLIT with `levels` steps of
+    // cyclic reduction (0: the library's choice) or NDI_BUILD_PARTITION with blocks of `levels` rows (0: 32)
     CubicSpline solver(int mode, int levels = 0) const { CubicSpline c(*this); c.build_mode_ = mode; c.build_levels_ = levels; return c; }
     size_t MINIMUM_DATA_LENGHT() const override { return 3; }
     std::shared_ptr<const Interp1DStrategy<T>> build(const ArrayView<T>&, const ArrayView<T>& data) const override {

@@ -191,8 +191,8 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
  *                         `levels` times shorter that is treated the same way (csrc/ndi_partition.cu); different
  *                         rounding (fused multiply-adds), inside the same bars, bit-identical to the oracle's
  *                         specification of the same scheme.
- *   NDI_BUILD_AUTO        row-split for systems of 2048 rows or more with fewer than 8192 columns (where the serial
- *                         chains bind), the reference's order otherwise (default).
+ *   NDI_BUILD_AUTO        partition (blocks of 32 rows) for tables of 1024 rows or more, the reference's order
+ *                         otherwise (default).
  * ndi_interp1d_build_info reports how the current coefficients were built: 0 reference order, L > 0 row-split with L
  * levels, -m < 0 partition with blocks of m rows. */
 #define NDI_BUILD_AUTO 0

@@ -1029,13 +1029,14 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
     const int mode = env_mode >= 0 ? (int)env_mode : h->build_mode;
     const int want_levels = env_levels >= 0 ? (int)env_levels : h->build_levels;
     int levels = 0;
-    // AUTO: the row-split build where the serial chains bind -- long systems of few columns.  With many columns the
-    // reference-order sweeps already fill the machine and the extra passes of the reduction cost more than the
-    // shorter chains save (4096 x 16384 f32: 1.21 ms against 1.34 ms; profiles/r02/spline_build.jsonl).
-    if (h->n >= 4 && mode == NDI_BUILD_PARTITION)
-        levels = -partition_block_for(want_levels);           // negative: partition build with blocks of that many rows
-    else if (h->n >= 4 && mode != NDI_BUILD_SEQUENTIAL && (mode == NDI_BUILD_ROWSPLIT || h->w < kRowsplitAutoMaxColumns))
-        levels = rowsplit_levels_for(bc_kind == NDI_BC_PERIODIC ? h->n - 2 : h->n, want_levels, mode == NDI_BUILD_ROWSPLIT);
+    // AUTO: the partition build from kPartitionAutoRows rows on -- it beats the reference order (serial chains of n steps)
+    // and the row-split build at every measured shape from there on, few long columns (4096 x 1024 f64: 0.11 against 0.91
+    // and 0.20 ms) as well as many (4096 x 16384 f32: 0.54 against 1.01 and 1.40 ms); at 512 rows the three are level
+    // (profiles/r02/partition_build.md).  Shorter systems keep the reference's order and with it the reference's bits.
+    if (h->n >= 4 && (mode == NDI_BUILD_PARTITION || (mode == NDI_BUILD_AUTO && h->n >= kPartitionAutoRows)))
+        levels = -partition_block_for(mode == NDI_BUILD_PARTITION ? want_levels : 0);   // negative: partition build, blocks of that many rows
+    else if (h->n >= 4 && mode == NDI_BUILD_ROWSPLIT)
+        levels = rowsplit_levels_for(bc_kind == NDI_BC_PERIODIC ? h->n - 2 : h->n, want_levels, true);
     return dispatch_float(h->dtype, [&](auto tag) -> ndi_status {
         using T = decltype(tag);
         const size_t coef_bytes = (size_t)(h->n - 1) * h->w * sizeof(T);

@@ -147,8 +147,8 @@ size_t spline_scratch_elems(int64_t n, int64_t w, int bc_kind, int levels);
 // leaves chains of about 256 rows -- unless the system is shorter than kRowsplitAutoRows and `force` is
 // not set, where the reference's order is kept (0); 0 also when the system is too short to split at all
 constexpr int kMaxRowsplitLevels = 6;
-constexpr int64_t kRowsplitAutoRows = 2048;
-constexpr int64_t kRowsplitAutoMaxColumns = 8192;   // AUTO keeps the reference order from this many columns on
+constexpr int64_t kRowsplitAutoRows = 2048;         // depth chosen for an unforced request: systems below this keep the reference order
+constexpr int64_t kPartitionAutoRows = 1024;        // NDI_BUILD_AUTO: partition build from this many rows on
 int rowsplit_levels_for(int64_t rows, int requested, bool force);
 // partition build (ndi_partition.cu): rows per block for a request (0: the default), passed on as levels = -block
 int partition_block_for(int requested);

@@ -167,9 +167,12 @@ static void cubic_doc_example() {
     auto aut = Interp1DBuilder<double>(ylong).strategy(CubicSpline<double>()).build();
     CHECK(static_cast<const CubicSplineStrategy<double>&>(seq.strategy()).rowsplit_levels(seq) == 0);
     CHECK(static_cast<const CubicSplineStrategy<double>&>(split.strategy()).rowsplit_levels(split) == 3);
-    CHECK(static_cast<const CubicSplineStrategy<double>&>(aut.strategy()).rowsplit_levels(aut) == 4);   // AUTO: 4096 rows -> 4 levels
+    CHECK(static_cast<const CubicSplineStrategy<double>&>(aut.strategy()).rowsplit_levels(aut) == -32); // AUTO: 4096 rows -> partition, blocks of 32
+    auto part = Interp1DBuilder<double>(ylong).strategy(CubicSpline<double>().solver(NDI_BUILD_PARTITION, 16)).build();
+    CHECK(static_cast<const CubicSplineStrategy<double>&>(part.strategy()).rowsplit_levels(part) == -16);
     for (double x : {0.5, 17.25, 2047.5, 4094.75}) {
         CHECK(close(seq.interp_scalar(x), split.interp_scalar(x), 1e-12));
+        CHECK(close(seq.interp_scalar(x), part.interp_scalar(x), 1e-12));
         CHECK(close(seq.interp_scalar(x), aut.interp_scalar(x), 1e-12));
     }
     CHECK(close(split.interp_scalar(100.0), yl[100], 8 * EPS));

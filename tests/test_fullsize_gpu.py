@@ -42,14 +42,15 @@ def test_c2_cubic_natural_f64_full_size(D):
     a, b = ip.coeffs_to_host()
     st, a_seq, b_seq = O.spline_build(g, y, {"kind": "Natural"})
     assert np.array_equal(a, a_seq) and np.array_equal(b, b_seq)        # K6 at the full C2 shape, reference order
-    ip.set_build_mode(L.BUILD_AUTO)                                     # 4096 rows: AUTO takes the row-split build
-    st, _ = ip.spline_build(1)
-    assert st == 0 and ip.build_levels() == 4
-    a, b = ip.coeffs_to_host()
-    st, a_ref, b_ref = O.spline_build(g, y, {"kind": "Natural"}, rowsplit_levels=4)
-    assert np.array_equal(a, a_ref) and np.array_equal(b, b_ref)        # bit for bit against its specification
-    for got, ref in ((a, a_seq), (b, b_seq)):                           # and inside 1e-12 of the reference order
-        assert float((np.abs(got - ref) / np.maximum(np.abs(ref), np.abs(y).max(axis=0)[None, :])).max()) <= 1e-12
+    for mode, info in ((L.BUILD_ROWSPLIT, 4), (L.BUILD_AUTO, -32)):     # 4096 rows: AUTO takes the partition build
+        ip.set_build_mode(mode)
+        st, _ = ip.spline_build(1)
+        assert st == 0 and ip.build_levels() == info
+        a, b = ip.coeffs_to_host()
+        st, a_ref, b_ref = O.spline_build_as(g, y, {"kind": "Natural"}, info)
+        assert np.array_equal(a, a_ref) and np.array_equal(b, b_ref)    # bit for bit against its specification
+        for got, ref in ((a, a_seq), (b, b_seq)):                       # and inside 1e-12 of the reference order
+            assert float((np.abs(got - ref) / np.maximum(np.abs(ref), np.abs(y).max(axis=0)[None, :])).max()) <= 1e-12
     err = D.new_err_word()
     out = ip.cubic(dev(q), 0, err=err)
     assert D.err_word_value(err) == D.ERR_NONE
@@ -185,8 +186,8 @@ def test_c5b_cubic_f32_at_scale_sorted(D):
     st, _ = ip.spline_build(1)
     assert st == 0
     a, b = ip.coeffs_to_host()
-    st, a_ref, b_ref = O.spline_build(g, y, {"kind": "Natural"}, rowsplit_levels=ip.build_levels())
-    assert ip.build_levels() == 4 and np.array_equal(a, a_ref) and np.array_equal(b, b_ref)
+    st, a_ref, b_ref = O.spline_build_as(g, y, {"kind": "Natural"}, ip.build_levels())
+    assert ip.build_levels() == -32 and np.array_equal(a, a_ref) and np.array_equal(b, b_ref)
     q = torch.sort(torch.rand(nq, dtype=torch.float32, device="cuda") * float(g[-1] - g[0]) + float(g[0]))[0].clamp(float(g[0]), float(g[-1]))
     err = D.new_err_word()
     out = ip.cubic(q, 0, err=err)

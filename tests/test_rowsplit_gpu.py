@@ -99,17 +99,26 @@ def test_rowsplit_matches_its_specification_and_the_reference_order(dt, bc, n, w
     assert same(sa, a_ref) and same(sb, b_ref)
 
 
-def test_auto_keeps_the_reference_order_on_short_systems_and_splits_long_ones():
+def test_auto_keeps_the_reference_order_on_short_systems_and_partitions_long_ones():
     rng = np.random.default_rng(3)
-    for n, expect in [(100, 0), (2047, 0), (2048, 3), (4096, 4), (70000, 6)]:
+    for n, expect in [(100, 0), (1023, 0), (1024, -32), (4096, -32), (70000, -32)]:
         g = grid(rng, n, np.float64)
         y = rng.normal(size=(n, 4))
         interp = build(g, y, BoundaryCondition.Natural, "auto")
         used = interp.strategy.rowsplit_levels(interp)
         assert used == expect, (n, used)
         a, b = interp.strategy.coefficients(interp)
-        st, a_ref, b_ref = O.spline_build(g, y, {"kind": "Natural"}, rowsplit_levels=used)
+        st, a_ref, b_ref = O.spline_build_as(g, y, {"kind": "Natural"}, used)
         assert same(a, a_ref) and same(b, b_ref)
+
+
+def test_an_unforced_rowsplit_request_picks_its_depth_by_the_system_length():
+    rng = np.random.default_rng(4)
+    for n, expect in [(2048, 3), (4096, 4), (70000, 6)]:
+        g = grid(rng, n, np.float64)
+        y = rng.normal(size=(n, 4))
+        interp = build(g, y, BoundaryCondition.Natural, "rowsplit")
+        assert interp.strategy.rowsplit_levels(interp) == expect
 
 
 def test_rowsplit_periodic_mismatch_is_reported():
