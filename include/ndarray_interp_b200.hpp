@@ -24,7 +24,7 @@
 //   VectorExtensions::{monotonic_prop,get_lower_index} monotonic_prop(), get_lower_index()
 //
 // Every number comes from the CUDA library; there is no CPU fallback (a missing device is an
-// exception).  Element types: float, double, int32_t, int64_t (integers: Linear and Bilinear only).
+// exception).  Element types: float, double, int32_t, int64_t, uint32_t, uint64_t (integers: Linear and Bilinear only).
 //
 // Link with -lndi_b200 (ndarray_interp_b200/libndi_b200.so).
 #pragma once
@@ -70,6 +70,8 @@ template <> struct dtype_of<float> { static constexpr ndi_dtype value = NDI_F32;
 template <> struct dtype_of<double> { static constexpr ndi_dtype value = NDI_F64; };
 template <> struct dtype_of<int32_t> { static constexpr ndi_dtype value = NDI_I32; };
 template <> struct dtype_of<int64_t> { static constexpr ndi_dtype value = NDI_I64; };
+template <> struct dtype_of<uint32_t> { static constexpr ndi_dtype value = NDI_U32; };
+template <> struct dtype_of<uint64_t> { static constexpr ndi_dtype value = NDI_U64; };
 
 // `{:?}` of a Rust number: shortest round-trip digits, "1.0" for integral floats, "NaN", "inf"
 template <class T>

@@ -65,6 +65,8 @@ typedef int32_t ndi_dtype;
 #define NDI_F64 1
 #define NDI_I32 2 /* everything except splines (SplineNum is float-only, cubic_spline.rs:34-49) */
 #define NDI_I64 3 /* as NDI_I32: wrapping arithmetic, truncating division (Linear / Bilinear are generic over Num) */
+#define NDI_U32 4 /* unsigned: the reference's generic bound admits them (linear.rs:29-36, T: Num); arithmetic modulo 2^32 as in */
+#define NDI_U64 5 /* a release build of the reference (a debug build panics where a difference would be negative), unsigned / and < */
 
 /* enum Monotonic (src/vector_extensions.rs:24-29) */
 #define NDI_MONO_NOT_MONOTONIC 0

@@ -15,7 +15,7 @@ SO_PATH = os.environ.get("NDI_B200_LIB") or os.path.join(_HERE, "libndi_b200.so"
 OK, OUT_OF_BOUNDS, NAN_QUERY, PERIODIC_MISMATCH, INVALID_ARGUMENT, NOT_MONOTONIC, NO_SPLINE, UNSUPPORTED_DTYPE, \
     NO_DEVICE = range(9)
 CUDA_ERROR = 100
-F32, F64, I32, I64 = 0, 1, 2, 3
+F32, F64, I32, I64, U32, U64 = 0, 1, 2, 3, 4, 5
 ASSUME_VALID, DEVICE_POINTERS, BORROW = 1, 2, 4
 SEARCH_AUTO, SEARCH_BINARY_GLOBAL, SEARCH_BINARY_SMEM, SEARCH_UNIFORM_GUESS, SEARCH_BUCKET_LUT, SEARCH_MERGE = 0, 1, 2, 3, 4, 5
 EXTRAP_NO, EXTRAP_YES, EXTRAP_PERIODIC = 0, 1, 2
@@ -24,7 +24,7 @@ BUILD_AUTO, BUILD_SEQUENTIAL, BUILD_ROWSPLIT, BUILD_PARTITION = 0, 1, 2, 3
 ERR_WORD_NONE = 2 ** 64 - 1
 
 DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32,
-          np.dtype(np.int64): I64}
+          np.dtype(np.int64): I64, np.dtype(np.uint32): U32, np.dtype(np.uint64): U64}
 
 _vp, _i64, _i32, _u32, _u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_uint64
 _pi64, _pi32 = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
@@ -155,4 +155,4 @@ def dtype_code(dt):
         return DTYPES[np.dtype(dt)]
     except KeyError:
         raise TypeError(f"element type {np.dtype(dt)} is not supported on the device path "
-                        "(f32, f64, i32 and i64 are)") from None
+                        "(f32, f64, i32, i64, u32 and u64 are)") from None

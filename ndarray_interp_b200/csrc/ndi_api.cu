@@ -91,8 +91,8 @@ static long env_long(const char* name, long dflt) {
     return v && *v ? strtol(v, nullptr, 10) : dflt;
 }
 
-static size_t elem_size(ndi_dtype d) { return (d == NDI_F64 || d == NDI_I64) ? 8 : 4; }
-static bool dtype_ok(ndi_dtype d) { return d == NDI_F32 || d == NDI_F64 || d == NDI_I32 || d == NDI_I64; }
+static size_t elem_size(ndi_dtype d) { return (d == NDI_F64 || d == NDI_I64 || d == NDI_U64) ? 8 : 4; }
+static bool dtype_ok(ndi_dtype d) { return d >= NDI_F32 && d <= NDI_U64; }
 
 template <class F>
 static ndi_status dispatch(ndi_dtype d, F&& f) {
@@ -101,6 +101,8 @@ static ndi_status dispatch(ndi_dtype d, F&& f) {
     case NDI_F64: return f(double{});
     case NDI_I32: return f(int32_t{});
     case NDI_I64: return f(int64_t{});
+    case NDI_U32: return f(uint32_t{});
+    case NDI_U64: return f(uint64_t{});
     default: return fail(NDI_UNSUPPORTED_DTYPE, "unsupported dtype %d", (int)d);
     }
 }
@@ -326,6 +328,12 @@ static ndi_status build_aids(ndi_dtype dtype, const void* grid, int64_t n, cudaS
     } else if (dtype == NDI_I64) {
         int64_t a, b; memcpy(&a, ends, 8); memcpy(&b, ends + 8, 8);
         g0d = (double)a; scale = (double)nb / ((double)b - (double)a);
+    } else if (dtype == NDI_U64) {
+        uint64_t a, b; memcpy(&a, ends, 8); memcpy(&b, ends + 8, 8);
+        g0d = (double)a; scale = (double)nb / ((double)b - (double)a);
+    } else if (dtype == NDI_U32) {
+        uint32_t a, b; memcpy(&a, ends, 4); memcpy(&b, ends + 8, 4);
+        g0d = a; scale = (double)nb / ((double)b - (double)a);
     } else {
         int32_t a, b; memcpy(&a, ends, 4); memcpy(&b, ends + 8, 4);
         g0d = a; scale = (double)nb / ((double)b - (double)a);
@@ -1145,7 +1153,7 @@ ndi_status ndi_interp1d_spline_coeffs(const ndi_interp1d* h, void* a, void* b) {
 
 ndi_status ndi_interp1d_spline_set_coeffs(ndi_interp1d* h, const void* a, const void* b, uint32_t flags) {
     if (!h || !a || !b) return fail(NDI_INVALID_ARGUMENT, "null pointer");
-    if (h->dtype == NDI_I32 || h->dtype == NDI_I64) return fail(NDI_UNSUPPORTED_DTYPE, "cubic splines need a float dtype");
+    if (h->dtype != NDI_F32 && h->dtype != NDI_F64) return fail(NDI_UNSUPPORTED_DTYPE, "cubic splines need a float dtype");
     DeviceGuard g(h->device);
     const size_t bytes = (size_t)(h->n - 1) * h->w * elem_size(h->dtype);
     void *na = nullptr, *nb = nullptr; bool oa = false, ob = false;

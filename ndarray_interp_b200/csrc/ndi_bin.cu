@@ -237,5 +237,7 @@ NDI_INST_BIN(float)
 NDI_INST_BIN(double)
 NDI_INST_BIN(int32_t)
 NDI_INST_BIN(int64_t)
+NDI_INST_BIN(uint32_t)
+NDI_INST_BIN(uint64_t)
 
 }  // namespace ndi

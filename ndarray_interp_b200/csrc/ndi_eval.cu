@@ -945,6 +945,8 @@ NDI_INST_COMMON(float)
 NDI_INST_COMMON(double)
 NDI_INST_COMMON(int32_t)
 NDI_INST_COMMON(int64_t)
+NDI_INST_COMMON(uint32_t)
+NDI_INST_COMMON(uint64_t)
 template cudaError_t launch_interp1d_cubic<float>(const float*, int64_t, SearchCfg, const float*, const float*,
                                                   const float*, int64_t, const float*, int64_t, int, float*,
                                                   unsigned long long*, cudaStream_t);

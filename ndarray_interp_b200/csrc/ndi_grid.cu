@@ -196,11 +196,15 @@ template cudaError_t launch_build_lut<float>(const float*, int64_t, double, doub
 template cudaError_t launch_build_lut<double>(const double*, int64_t, double, double, int, void*, cudaStream_t);
 template cudaError_t launch_build_lut<int32_t>(const int32_t*, int64_t, double, double, int, void*, cudaStream_t);
 template cudaError_t launch_build_lut<int64_t>(const int64_t*, int64_t, double, double, int, void*, cudaStream_t);
+template cudaError_t launch_build_lut<uint32_t>(const uint32_t*, int64_t, double, double, int, void*, cudaStream_t);
+template cudaError_t launch_build_lut<uint64_t>(const uint64_t*, int64_t, double, double, int, void*, cudaStream_t);
 
 template cudaError_t launch_grid_classify<float>(const float*, int64_t, int32_t*, uint32_t*, cudaStream_t);
 template cudaError_t launch_grid_classify<double>(const double*, int64_t, int32_t*, uint32_t*, cudaStream_t);
 template cudaError_t launch_grid_classify<int32_t>(const int32_t*, int64_t, int32_t*, uint32_t*, cudaStream_t);
 template cudaError_t launch_grid_classify<int64_t>(const int64_t*, int64_t, int32_t*, uint32_t*, cudaStream_t);
+template cudaError_t launch_grid_classify<uint32_t>(const uint32_t*, int64_t, int32_t*, uint32_t*, cudaStream_t);
+template cudaError_t launch_grid_classify<uint64_t>(const uint64_t*, int64_t, int32_t*, uint32_t*, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
 // Dense copy of a strided view (ndi_interp*_create_strided): one thread per destination element,

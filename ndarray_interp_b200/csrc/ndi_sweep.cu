@@ -336,5 +336,7 @@ NDI_INST_SWEEP(float)
 NDI_INST_SWEEP(double)
 NDI_INST_SWEEP(int32_t)
 NDI_INST_SWEEP(int64_t)
+NDI_INST_SWEEP(uint32_t)
+NDI_INST_SWEEP(uint64_t)
 
 }  // namespace ndi

@@ -14,6 +14,9 @@ import torch
 from . import _lib as L
 
 _TORCH_DT = {torch.float32: L.F32, torch.float64: L.F64, torch.int32: L.I32, torch.int64: L.I64}
+for _name, _code_ in (("uint32", L.U32), ("uint64", L.U64)):      # torch >= 2.3 has the (storage-only) unsigned types
+    if hasattr(torch, _name):
+        _TORCH_DT[getattr(torch, _name)] = _code_
 ERR_NONE = L.ERR_WORD_NONE
 
 
@@ -21,7 +24,7 @@ def _code(t):
     try:
         return _TORCH_DT[t.dtype]
     except KeyError:
-        raise TypeError(f"dtype {t.dtype} is not supported (f32, f64, i32, i64)") from None
+        raise TypeError(f"dtype {t.dtype} is not supported (f32, f64, i32, i64, u32, u64)") from None
 
 
 def _p(t):

@@ -61,6 +61,8 @@ inline bool is_nan(T v) {
 }
 
 // wrapping integer arithmetic / plain float arithmetic --------------------------------------
+// (integers: what a release build of the reference computes; a debug build panics on overflow -- for the unsigned
+// types that includes every negative difference y2 - y1 or x - x1)
 template <class T> inline T t_add(T a, T b) {
     if constexpr (std::is_integral_v<T>) { using U = std::make_unsigned_t<T>; return (T)((U)a + (U)b); } else return a + b;
 }
@@ -73,8 +75,8 @@ template <class T> inline T t_mul(T a, T b) {
 template <class T> inline T t_div(T a, T b) {
     if constexpr (std::is_integral_v<T>) {
         if (b == 0) return 0;              // Rust panics; unreachable on a strictly rising grid
-        if (a == std::numeric_limits<T>::min() && b == -1) return a;
-        return a / b;                      // truncating, like Rust
+        if constexpr (std::is_signed_v<T>) { if (a == std::numeric_limits<T>::min() && b == (T)-1) return a; }
+        return a / b;                      // truncating, like Rust (unsigned types: unsigned division)
     } else return a / b;
 }
 
@@ -135,7 +137,7 @@ int64_t get_lower_index(const T* g, int64_t n, T x, int32_t* status) {
     if (is_nan(mid)) { *status = ST_NAN_QUERY; return 0; }        // :83-84
     int64_t mid_idx;                                              // truncation, NumCast
     if (!(mid < (T)(n - 1))) mid_idx = n - 1;                     // (Rust would panic past n-1;
-    else if (mid < (T)0) mid_idx = 0;                             //  unreachable for g[0] < x < g[n-1])
+    else if (std::is_signed_v<T> && mid < (T)0) mid_idx = 0;      //  unreachable for g[0] < x < g[n-1])
     else mid_idx = (int64_t)mid;
     T mid_x = g[mid_idx];                                         // :86
     if (mid_x <= x && x < g[mid_idx + 1]) return mid_idx;         // :88-90 (&& short-circuits)
@@ -728,6 +730,8 @@ ORA_COMMON(f32, float)
 ORA_COMMON(f64, double)
 ORA_COMMON(i32, int32_t)
 ORA_COMMON(i64, int64_t)
+ORA_COMMON(u32, uint32_t)
+ORA_COMMON(u64, uint64_t)
 ORA_SPLINE(f32, float)
 ORA_SPLINE(f64, double)
 

@@ -18,8 +18,8 @@ BC = {"NotAKnot": 0, "Natural": 1, "Clamped": 2, "Periodic": 3, "Individual": 4}
 SB = {"NotAKnot": 0, "Natural": 1, "Clamped": 2, "FirstDeriv": 3, "SecondDeriv": 4}
 
 _SFX = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.int32): "i32",
-        np.dtype(np.int64): "i64"}
-_CT = {"f32": C.c_float, "f64": C.c_double, "i32": C.c_int32, "i64": C.c_int64}
+        np.dtype(np.int64): "i64", np.dtype(np.uint32): "u32", np.dtype(np.uint64): "u64"}
+_CT = {"f32": C.c_float, "f64": C.c_double, "i32": C.c_int32, "i64": C.c_int64, "u32": C.c_uint32, "u64": C.c_uint64}
 
 
 def build(force=False):

@@ -13,6 +13,8 @@ pub const NDI_F32: i32 = 0;
 pub const NDI_F64: i32 = 1;
 pub const NDI_I32: i32 = 2;
 pub const NDI_I64: i32 = 3;
+pub const NDI_U32: i32 = 4;
+pub const NDI_U64: i32 = 5;
 
 pub const NDI_ASSUME_VALID: u32 = 1;
 

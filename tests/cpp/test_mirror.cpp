@@ -104,6 +104,14 @@ static void linear_errors() {
     auto i8 = Interp1D<int64_t>::builder(I8{big, big + 20, big + 50}).x(I8{0, 10, 40}).build();
     CHECK(i8.interp_array(I8{0, 5, 10, 25, 40}) == (I8{big, big + 10, big + 20, big + 35, big + 50}));
     CHECK(throws<InterpolateError>([&] { i8.interp_scalar(41); }));
+    // unsigned: values with the top bit set compare and divide as unsigned; falling data wraps like a release build
+    using U4 = Array<uint32_t>;
+    const uint32_t top = 0x80000000u;
+    auto u4 = Interp1D<uint32_t>::builder(U4{top - 10, top + 10, top + 40}).x(U4{top - 5, top + 5, top + 35}).build();
+    CHECK(u4.interp_array(U4{top - 5, top, top + 5, top + 20, top + 35}) == (U4{top - 10, top, top + 10, top + 25, top + 40}));
+    CHECK(throws<InterpolateError>([&] { u4.interp_scalar(top + 36); }));
+    auto fall = Interp1D<uint32_t>::builder(U4{30, 10}).x(U4{0, 10}).build();
+    CHECK(fall.interp_scalar(5) == (uint32_t)(((uint32_t)(10 - 30) / 10u) * 5u + 30u));   // (y2 - y1) wraps, unsigned division
 }
 
 // src/vector_extensions.rs unit tests: borders, exact hits, +-inf, NaN panic, monotonic classification

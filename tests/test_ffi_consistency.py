@@ -67,7 +67,7 @@ def test_rust_constants_carry_the_header_values():
     _, c = _header()
     _, r = _rust()
     assert {"NDI_OK", "NDI_OUT_OF_BOUNDS", "NDI_NAN_QUERY", "NDI_PERIODIC_MISMATCH", "NDI_NOT_MONOTONIC", "NDI_F32",
-            "NDI_F64", "NDI_I32", "NDI_I64", "NDI_ASSUME_VALID"} <= set(r)
+            "NDI_F64", "NDI_I32", "NDI_I64", "NDI_U32", "NDI_U64", "NDI_ASSUME_VALID"} <= set(r)
     for k, v in r.items():
         assert c.get(k) == v, (k, v, c.get(k))
 

@@ -18,10 +18,10 @@ EDGE_W = [1, 2, 3, 4, 5, 7, 8, 12, 16, 31, 32, 33, 63, 64, 100, 127, 128, 129, 2
 EDGE_Q = [1, 2, 31, 32, 33, 63, 64, 65, 255, 1000, 2047, 2048, 2049, 4097, 10000]
 
 
-@pytest.mark.parametrize("seed", range(32))
+@pytest.mark.parametrize("seed", range(44))
 def test_fuzz_linear_and_bilinear(seed):
     rng = np.random.default_rng(9000 + seed)
-    dt = [np.float32, np.float64, np.int32][seed % 3] if seed < 24 else np.int64
+    dt = [np.float32, np.float64, np.int32][seed % 3] if seed < 24 else (np.int64 if seed < 32 else [np.uint32, np.uint64][seed % 2])
     n, m = int(rng.choice(EDGE_N)), int(rng.choice(EDGE_N[:14]))
     w, nq = int(rng.choice(EDGE_W)), int(rng.choice(EDGE_Q))
     extrap = bool(seed & 1)

@@ -280,3 +280,58 @@ def test_partition_specification_stays_inside_the_bars():
                 if dt is np.float64 and bc["kind"] == "Natural":
                     sci = SciSpline(x, yy, bc_type="natural")(q)
                     assert float((np.abs(par - sci) / sc).max()) < 1e-12
+
+
+def _wrap(v, bits, signed):
+    v &= (1 << bits) - 1
+    return v - (1 << bits) if signed and v >> (bits - 1) else v
+
+
+def _int_calc_frac(x1, y1, x2, y2, x, bits, signed):
+    """Linear::calc_frac (linear.rs:29-36) as a release build of the reference evaluates it for an integer type:
+    every operation modulo 2^bits, division truncating (signed) / flooring (unsigned), on Python's big integers"""
+    num, den = _wrap(y2 - y1, bits, signed), _wrap(x2 - x1, bits, signed)
+    if signed and num == -(1 << (bits - 1)) and den == -1:
+        m = num
+    else:
+        m = abs(num) // abs(den) * (1 if (num < 0) == (den < 0) else -1) if signed else num // den
+    return _wrap(_wrap(m * _wrap(x - x1, bits, signed), bits, signed) + y1, bits, signed)
+
+
+@pytest.mark.parametrize("dt", [np.int32, np.int64, np.uint32, np.uint64], ids=["i32", "i64", "u32", "u64"])
+def test_integer_arithmetic_of_the_oracle_is_the_wrapping_arithmetic_of_a_release_build(dt):
+    """the oracle's integer Linear / Bilinear against big-integer arithmetic modulo 2^bits: large values whose
+    products wrap, falling data (differences that are negative, i.e. wrap for the unsigned types), queries outside the
+    grid on both sides"""
+    bits, signed = np.dtype(dt).itemsize * 8, np.issubdtype(dt, np.signedinteger)
+    rng = np.random.default_rng(bits + signed)
+    top = (1 << (bits - 2))
+    n, m, w = 40, 7, 3
+    base = top if not signed else -top // 2
+    g = (base + np.cumsum(rng.integers(1, 1000, n))).astype(dt)
+    gy = (5 + np.cumsum(rng.integers(1, 9, m))).astype(dt)
+    lo, hi = (0, 1 << (bits - 1)) if not signed else (-top, top)
+    d1 = rng.integers(lo, hi, (n, w), dtype=np.int64 if bits == 32 else None).astype(dt) if bits == 32 else \
+        (rng.integers(0, 1 << 62, (n, w)).astype(np.uint64) * 2).astype(dt)
+    d2 = rng.integers(0, 1 << 20, (n, m, w)).astype(dt)
+    q = (int(g[0]) - 30 + rng.integers(0, int(g[-1]) - int(g[0]) + 60, 500)).astype(dt)
+    qy = (max(0, int(gy[0]) - 3) + rng.integers(0, int(gy[-1]) - int(gy[0]) + 6, 500)).astype(dt)
+    st, out, _ = O.interp1d_linear(g, d1, q, True)
+    assert st == O.ST_OK
+    st, idx, _ = O.lower_index(g, q)
+    for k in range(len(q)):
+        i = int(idx[k])
+        assert i == min(max(int(np.searchsorted(g, q[k], side="right")) - 1, 0), n - 2)
+        for c in range(w):
+            exp = _int_calc_frac(int(g[i]), int(d1[i, c]), int(g[i + 1]), int(d1[i + 1, c]), int(q[k]), bits, signed)
+            assert int(out[k, c]) == exp, (k, c)
+    st, out2, _, _ = O.interp2d_bilinear(g, gy, d2, q, qy, True)
+    assert st == O.ST_OK
+    st, jdx, _ = O.lower_index(gy, qy)
+    for k in range(0, len(q), 7):
+        i, j = int(idx[k]), int(jdx[k])
+        for c in range(w):
+            z1 = _int_calc_frac(int(g[i]), int(d2[i, j, c]), int(g[i + 1]), int(d2[i + 1, j, c]), int(q[k]), bits, signed)
+            z2 = _int_calc_frac(int(g[i]), int(d2[i, j + 1, c]), int(g[i + 1]), int(d2[i + 1, j + 1, c]), int(q[k]), bits, signed)
+            exp = _int_calc_frac(int(gy[j]), z1, int(gy[j + 1]), z2, int(qy[k]), bits, signed)
+            assert int(out2[k, c]) == exp, (k, c)

@@ -17,7 +17,7 @@ from oracle import oracle_py as O
 
 pytestmark = pytest.mark.gpu
 
-DTS = [np.float32, np.float64, np.int32, np.int64]
+DTS = [np.float32, np.float64, np.int32, np.int64, np.uint32, np.uint64]
 
 
 def same(a, b):
@@ -62,6 +62,8 @@ def make_queries(rng, g, nq, dt, outside):
         q = np.round(q)
         if not outside:
             q = np.clip(q, g[0], g[-1])
+        if np.issubdtype(dt, np.unsignedinteger):
+            q = np.maximum(q, 0.0)                    # below the grid, but not below zero
         return q.astype(dt)
     q = q.astype(dt)
     if not outside:
@@ -75,6 +77,8 @@ def make_queries(rng, g, nq, dt, outside):
 
 
 def make_data(rng, shape, dt):
+    if np.issubdtype(dt, np.unsignedinteger):
+        return rng.integers(0, 2000, shape).astype(dt)   # falling data: y2 - y1 wraps, as in a release build of the reference
     if np.issubdtype(dt, np.integer):
         return rng.integers(-1000, 1000, shape).astype(dt)
     return rng.normal(size=shape).astype(dt)
@@ -581,6 +585,57 @@ def test_i64_values_beyond_2_pow_53_and_wrapping(mode):
     L.check(L.load().ndi_interp2d_set_search_mode(ip._handle(), mode))
     st, ref, _, _ = O.interp2d_bilinear(gx, gy, d2, qx, qy, False)
     assert st == O.ST_OK and same(ip.interp_array(qx, qy), ref)
+
+
+# ---- u32 / u64 (the reference's generic bound admits them: linear.rs:29-36, T: Num) --------------------------------
+@pytest.mark.parametrize("dt", [np.uint32, np.uint64], ids=["u32", "u64"])
+@pytest.mark.parametrize("mode", [L.SEARCH_AUTO, L.SEARCH_BINARY_GLOBAL, L.SEARCH_BINARY_SMEM, L.SEARCH_UNIFORM_GUESS,
+                                  L.SEARCH_BUCKET_LUT, L.SEARCH_MERGE])
+def test_unsigned_values_in_the_upper_half_and_wrapping(dt, mode):
+    """grid and data values with the top bit set (a signed comparison or division would get them wrong), falling data
+    and queries left of the grid (differences that wrap, as in a release build of the reference), products that wrap"""
+    bits = np.dtype(dt).itemsize * 8
+    rng = np.random.default_rng(bits)
+    top = 1 << (bits - 1)
+    for n, w in ((2, 1), (50, 3), (5000, 8), (70001, 2)):
+        g = (top - 40000 + np.cumsum(rng.integers(1, 9, n))).astype(dt)        # crosses 2^(bits-1)
+        data = (rng.integers(0, 1 << 32, (n, w)).astype(np.uint64) << np.uint64(bits - 32)).astype(dt)
+        q = (int(g[0]) - 50 + rng.integers(0, int(g[-1]) - int(g[0]) + 100, 20000)).astype(dt)
+        q[:4] = [g[0], g[-1], g[0] - dt(1), g[-1] + dt(1)]
+        st, ref_idx, _ = O.lower_index(g, q)
+        assert st == O.ST_OK and np.array_equal(get_lower_index(g, q), ref_idx)
+        interp = Interp1D.new_unchecked(g, data, Linear.new().extrapolate(True))
+        L.check(L.load().ndi_interp1d_set_search_mode(interp._handle(), mode))
+        st, ref, _ = O.interp1d_linear(g, data, q, True)
+        assert st == O.ST_OK
+        got = interp.interp_array(q)
+        assert got.dtype == np.dtype(dt) and same(got, ref)
+    gx = (top + np.cumsum(rng.integers(1, 1000, 300))).astype(dt)
+    gy = (np.arange(40) * 7 + 3).astype(dt)
+    d2 = rng.integers(0, 1 << 30, (300, 40, 5)).astype(dt)
+    qx = (int(gx[0]) + rng.integers(0, int(gx[-1]) - int(gx[0]) + 1, 30000)).astype(dt)
+    qy = rng.integers(int(gy[0]), int(gy[-1]) + 1, 30000).astype(dt)
+    ip = Interp2D.new_unchecked(gx, gy, d2, Bilinear.new())
+    L.check(L.load().ndi_interp2d_set_search_mode(ip._handle(), mode))
+    st, ref, _, _ = O.interp2d_bilinear(gx, gy, d2, qx, qy, False)
+    assert st == O.ST_OK and same(ip.interp_array(qx, qy), ref)
+
+
+@pytest.mark.parametrize("dt", [np.uint32, np.uint64], ids=["u32", "u64"])
+def test_unsigned_builder_checks_and_errors(dt):
+    """the same builder / OutOfBounds behaviour as i32 (tests/interp1d.rs:93-127); no splines on integers"""
+    u = dt
+    with pytest.raises(BuilderError.Monotonic):
+        Interp1D.builder(np.array([1, 2, 3], u)).x(np.array([1, 2, 2], u)).build()
+    interp = Interp1D.builder(np.array([10, 20, 40], u)).build()
+    assert interp.interp_scalar(u(1)) == 20 and interp.interp_scalar(u(2)).dtype == np.dtype(dt)
+    with pytest.raises(InterpolateError.OutOfBounds):
+        interp.interp_scalar(u(3))
+    big = 1 << (np.dtype(dt).itemsize * 8 - 1)
+    assert monotonic_prop(np.array([big - 1, big, big], u)) == Monotonic.Rising(False)
+    assert monotonic_prop(np.array([big + 5, big, 3], u)) == Monotonic.Falling(True)
+    rising = Interp1D.builder(np.array([5, 9, 10], u)).x(np.array([big - 1, big, big + 7], u)).build()
+    assert rising.interp_scalar(u(big + 7)) == 10 and rising.interp_scalar(u(big - 1)) == 5
 
 
 def test_i64_builder_checks_and_errors():
