@@ -600,7 +600,7 @@ def test_unsigned_values_in_the_upper_half_and_wrapping(dt, mode):
     for n, w in ((2, 1), (50, 3), (5000, 8), (70001, 2)):
         g = (top - 40000 + np.cumsum(rng.integers(1, 9, n))).astype(dt)        # crosses 2^(bits-1)
         data = (rng.integers(0, 1 << 32, (n, w)).astype(np.uint64) << np.uint64(bits - 32)).astype(dt)
-        q = (int(g[0]) - 50 + rng.integers(0, int(g[-1]) - int(g[0]) + 100, 20000)).astype(dt)
+        q = (np.uint64(int(g[0]) - 50) + rng.integers(0, int(g[-1]) - int(g[0]) + 100, 20000).astype(np.uint64)).astype(dt)
         q[:4] = [g[0], g[-1], g[0] - dt(1), g[-1] + dt(1)]
         st, ref_idx, _ = O.lower_index(g, q)
         assert st == O.ST_OK and np.array_equal(get_lower_index(g, q), ref_idx)
@@ -610,10 +610,10 @@ def test_unsigned_values_in_the_upper_half_and_wrapping(dt, mode):
         assert st == O.ST_OK
         got = interp.interp_array(q)
         assert got.dtype == np.dtype(dt) and same(got, ref)
-    gx = (top + np.cumsum(rng.integers(1, 1000, 300))).astype(dt)
+    gx = (np.uint64(top) + np.cumsum(rng.integers(1, 1000, 300)).astype(np.uint64)).astype(dt)
     gy = (np.arange(40) * 7 + 3).astype(dt)
     d2 = rng.integers(0, 1 << 30, (300, 40, 5)).astype(dt)
-    qx = (int(gx[0]) + rng.integers(0, int(gx[-1]) - int(gx[0]) + 1, 30000)).astype(dt)
+    qx = (np.uint64(int(gx[0])) + rng.integers(0, int(gx[-1]) - int(gx[0]) + 1, 30000).astype(np.uint64)).astype(dt)
     qy = rng.integers(int(gy[0]), int(gy[-1]) + 1, 30000).astype(dt)
     ip = Interp2D.new_unchecked(gx, gy, d2, Bilinear.new())
     L.check(L.load().ndi_interp2d_set_search_mode(ip._handle(), mode))
@@ -634,8 +634,8 @@ def test_unsigned_builder_checks_and_errors(dt):
     big = 1 << (np.dtype(dt).itemsize * 8 - 1)
     assert monotonic_prop(np.array([big - 1, big, big], u)) == Monotonic.Rising(False)
     assert monotonic_prop(np.array([big + 5, big, 3], u)) == Monotonic.Falling(True)
-    rising = Interp1D.builder(np.array([5, 9, 10], u)).x(np.array([big - 1, big, big + 7], u)).build()
-    assert rising.interp_scalar(u(big + 7)) == 10 and rising.interp_scalar(u(big - 1)) == 5
+    rising = Interp1D.builder(np.array([5, 9, 16], u)).x(np.array([big - 1, big, big + 7], u)).build()
+    assert rising.interp_scalar(u(big + 7)) == 16 and rising.interp_scalar(u(big - 1)) == 5 and rising.interp_scalar(u(big + 3)) == 12
 
 
 def test_i64_builder_checks_and_errors():
