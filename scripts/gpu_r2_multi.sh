@@ -19,7 +19,7 @@ try:
     print('E2E', {k: (round(v, 2) if isinstance(v, float) else v) for k, v in d['e2e'].items() if 'GBps' in k or 'frac' in k}, 'numa', d['config']['numa_node'])
     for k, v in d['workloads'].items():
         if 'error' in v: print(k, 'ERROR', v['error'], v.get('trace')); continue
-        print(k, {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk in ('ms_per_step', 'value', 'build_ms', 'allgather_ms', 'allgather_GBps_per_gpu', 'rowsplit_levels', 'scaling', 'queries_per_gpu')},
+        print(k, {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk in ('ms_per_step', 'value', 'build_ms', 'allgather_ms', 'allgather_GBps_per_gpu', 'build_info', 'scaling', 'queries_per_gpu')},
               'frac=%s' % (v.get('roofline') or {}).get('frac'), 'check=%s' % (v.get('check') or {}), 'e2e=%s' % (v.get('e2e') or {}).get('value'))
 except Exception as e:
     print('bench FAILED', e)
