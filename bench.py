@@ -96,6 +96,22 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def l2_note(wl, nq):
+    """how the timed steps stand to the 126 MB L2 (the contract wants it said in `config`)"""
+    ab = algorithmic_bytes(wl, nq)
+    if ab < (512 << 20):
+        return "flushed between timed steps (512 MB overwrite); ms_per_step = mean of the K individually timed steps"
+    return "working set per step (%.2f GB, output streamed once) exceeds the 126 MB L2; no explicit flush" % (ab / 1e9)
+
+
+def workload_config(name, wl, world):
+    """`config` of the JSON line: names the workload -- the same dictionary in both arms (`--impl reference` measures the
+    reference's CPU path on this arm's config); what is specific to a GPU run goes to the line's `run` object"""
+    nq = queries_per_gpu(wl, world)
+    return {"workload": f"{name}: {wl['desc']}", "queries_per_gpu": nq, "columns": wl["w"],
+            "l2": l2_note(wl, nq) if wl["kind"] != "build" else None}
+
+
 def kernel_source_hash():
     """sha256 over the kernel sources (csrc without the host-only ndi_api.cu): ties a recorded ncu capture to the
     kernels it was taken from"""
@@ -326,9 +342,9 @@ def run_reference(args):
         "impl": "reference", "metric": "queries/s", "value": head["value"], "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
-        "config": {"workload": f"{name}: {wl['desc']}",
-                   "note": "CPU restatement of the reference algorithm (oracle/ndi_oracle.cpp, g++ -O2 -ffp-contract=off); "
-                           "the Rust crate itself cannot be built in this image (no cargo/rustc)"},
+        "config": workload_config(name, wl, max(1, args.gpus)),
+        "note": "CPU restatement of the reference algorithm (oracle/ndi_oracle.cpp, g++ -O2 -ffp-contract=off); "
+                "the Rust crate itself cannot be built in this image (no cargo/rustc)",
         "cpu_baseline": {"value": head["value"], "unit": "queries/s", "cores": head["cores"], "kind": "port", "sample": head["sample"]},
         "e2e": {"value": head["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "workloads": others,
@@ -587,8 +603,7 @@ def measure_eval(ctx, name, wl, steps, warmup, role, sampler=None):
         "per_step": {"median_ms": per[len(per) // 2], "best_ms": per[0], "worst_ms": per[-1], "n": len(per),
                      "note": "the same K steps as ms_per_step, each between its own CUDA events (this rank)"},
         "launches_per_step": int(launches) // max(steps, 1),
-        "l2": ("flushed between timed steps (512 MB overwrite); ms_per_step = mean of the K individually timed steps" if flush_l2 else
-               "working set per step (%.2f GB, output streamed once) exceeds the 126 MB L2; no explicit flush" % (abytes / 1e9)),
+        "l2": l2_note(wl, nq),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_capture": stamp, "algorithmic_bytes": abytes, "peak_source": peak_src,
                      "frac_of_nominal_8000": achieved / 8000.0},
@@ -879,15 +894,14 @@ def run_b200(args):
             "metric": "queries/s", "value": head.get("value"), "unit": head.get("unit", "queries/s"), "n_gpus": ctx.world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": head["scaling"], "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
-            "config": {"workload": head["workload"], "queries_per_gpu": head.get("queries_per_gpu"), "columns": wl["w"],
-                       "l2": head.get("l2"),
-                       "tables": "generated on rank 0, replicated per GPU by NCCL broadcast; queries sharded, no collective in the timed region",
-                       "search_mode": args.search_mode, "numa_node": numa,
-                       "launches_per_step": head.get("launches_per_step"),
-                       "spline_route": head.get("spline_route"), "spline_build_info": head.get("spline_build_info"),
-                       "timed": "every step between its own CUDA events on the launch stream; ms_per_step = (first start -> last end) / steps, "
-                                "max over ranks; per_step = median / best / worst of the same steps",
-                       "kernel_source_hash": kernel_source_hash()},
+            "config": workload_config(name, wl, ctx.world),
+            "run": {"tables": "generated on rank 0, replicated per GPU by NCCL broadcast; queries sharded, no collective in the timed region",
+                    "search_mode": args.search_mode, "numa_node": numa,
+                    "launches_per_step": head.get("launches_per_step"),
+                    "spline_route": head.get("spline_route"), "spline_build_info": head.get("spline_build_info"),
+                    "timed": "every step between its own CUDA events on the launch stream; ms_per_step = (first start -> last end) / steps, "
+                             "max over ranks; per_step = median / best / worst of the same steps",
+                    "kernel_source_hash": kernel_source_hash()},
             "roofline": head.get("roofline"),
             "per_step": head.get("per_step"),
             "check": head.get("check"),

@@ -15,8 +15,8 @@ python - <<PY
 import json
 try:
     d = json.load(open('${T}_bench.json'))
-    print('HEAD n_gpus=%d' % d['n_gpus'], d['config']['workload'][:30], 'value=%.4g ms=%.4f frac=%.3f e2e=%.4g check=%s route=%s' % (d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d.get('check'), d['config'].get('spline_route')))
-    print('E2E', {k: (round(v, 2) if isinstance(v, float) else v) for k, v in d['e2e'].items() if 'GBps' in k or 'frac' in k}, 'numa', d['config']['numa_node'])
+    print('HEAD n_gpus=%d' % d['n_gpus'], d['config']['workload'][:30], 'value=%.4g ms=%.4f frac=%.3f e2e=%.4g check=%s route=%s' % (d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d.get('check'), d['run'].get('spline_route')))
+    print('E2E', {k: (round(v, 2) if isinstance(v, float) else v) for k, v in d['e2e'].items() if 'GBps' in k or 'frac' in k}, 'numa', d['run']['numa_node'])
     for k, v in d['workloads'].items():
         if 'error' in v: print(k, 'ERROR', v['error'], v.get('trace')); continue
         print(k, {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk in ('ms_per_step', 'value', 'build_ms', 'allgather_ms', 'allgather_GBps_per_gpu', 'build_info', 'scaling', 'queries_per_gpu')},

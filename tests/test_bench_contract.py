@@ -25,6 +25,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("c1") and d["gpu_launches"] == 0 and d["vs_baseline"] is None
+    # `config` is the dictionary the GPU arm prints for the same workload and GPU count (bench.workload_config)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config("c1", bench.WORKLOADS["c1"], 1)
+    assert set(d["config"]) == {"workload", "queries_per_gpu", "columns", "l2"}
 
 
 def test_reference_arm_other_ranks_exit_silently():
