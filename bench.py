@@ -112,15 +112,19 @@ def workload_config(name, wl, world):
             "l2": l2_note(wl, nq) if wl["kind"] != "build" else None}
 
 
-def kernel_source_hash():
-    """sha256 over the kernel sources (csrc without the host-only ndi_api.cu): ties a recorded ncu capture to the
-    kernels it was taken from"""
+EVAL_SOURCES = ("ndi_bin.cu", "ndi_device.cuh", "ndi_eval.cu", "ndi_grid.cu", "ndi_internal.h", "ndi_sweep.cu")
+BUILD_SOURCES = ("ndi_device.cuh", "ndi_internal.h", "ndi_partition.cu", "ndi_rowsplit.cu", "ndi_spline.cu", "ndi_spline.cuh")
+
+
+def kernel_source_hash(files=EVAL_SOURCES):
+    """sha256 over kernel sources: ties a recorded ncu capture to the kernels it was taken from.  The DRAM-traffic stamps
+    (profiles/roofline_traffic.json) belong to the EVALUATION workloads, so they carry the hash of the sources the
+    evaluation kernels are compiled from; the spline-build sources have a hash of their own (`run.build_source_hash`)"""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "ndarray_interp_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h")) and f != "ndi_api.cu":
-            h.update(f.encode())
-            h.update(open(os.path.join(d, f), "rb").read())
+    for f in sorted(files):
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 
 
@@ -901,7 +905,7 @@ def run_b200(args):
                     "spline_route": head.get("spline_route"), "spline_build_info": head.get("spline_build_info"),
                     "timed": "every step between its own CUDA events on the launch stream; ms_per_step = (first start -> last end) / steps, "
                              "max over ranks; per_step = median / best / worst of the same steps",
-                    "kernel_source_hash": kernel_source_hash()},
+                    "kernel_source_hash": kernel_source_hash(), "build_source_hash": kernel_source_hash(BUILD_SOURCES)},
             "roofline": head.get("roofline"),
             "per_step": head.get("per_step"),
             "check": head.get("check"),

@@ -11,8 +11,8 @@
 //      q = A_block^-1 up[last] e_last) depends on x only and is formed once per block (part_factor_kernel);
 //   3. the separators' equations  -low[s] p[s-1] k[s-m] + (mid[s] - low[s] q[s-1] - up[s] p[s+1]) k[s]
 //      - up[s] q[s+1] k[s+m] = rhs[s] - low[s] g[s-1] - up[s] g[s+1]  are again a tridiagonal system with a matrix
-//      shared by all columns, m times shorter: the same three steps are applied to it until at most 4 m rows are
-//      left, which one lane per column solves directly out of shared memory (part_top_kernel);
+//      shared by all columns, m times shorter: the same three steps are applied to it until at most min(4 m, 128)
+//      rows are left, which one lane per column solves directly out of shared memory (part_top_kernel);
 //   4. k = g - p k_left - q k_right, elementwise, from the top level down (part_corr_kernel); on level 0 that
 //      correction is part of the kernel that writes a and b (part_ab_kernel), so k itself is never stored.
 // Every chain is m - 1 steps of one fused multiply-add (+ one multiplication by a reciprocal formed once per row); no

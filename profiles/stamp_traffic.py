@@ -36,10 +36,9 @@ def main():
     d, commit = sys.argv[1], sys.argv[2]
     import bench
     out = {"_note": "dram__bytes_read.sum + dram__bytes_write.sum per STEP (all launches of the step) from `ncu --set full` "
-                    "captures summarised under profiles/; each entry names the commit and the hash of the kernel sources "
-                    "(ndarray_interp_b200/csrc without the host-only ndi_api.cu) it was taken from (bench.py: "
-                    "kernel_source_hash) -- bench.py reports `current: false` when the kernels have changed since; written "
-                    "by profiles/stamp_traffic.py"}
+                    "captures summarised under profiles/; each entry names the commit and the hash of the evaluation-kernel "
+                    "sources (bench.py: EVAL_SOURCES, kernel_source_hash) it was taken from -- bench.py reports "
+                    "`current: false` when those sources have changed since; written by profiles/stamp_traffic.py"}
     for wl, (files, nq) in STEPS.items():
         paths = [os.path.join(d, f) for f in files]
         if not all(os.path.exists(p) for p in paths):
