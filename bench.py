@@ -112,20 +112,26 @@ def workload_config(name, wl, world):
             "l2": l2_note(wl, nq) if wl["kind"] != "build" else None}
 
 
-EVAL_SOURCES = ("ndi_bin.cu", "ndi_device.cuh", "ndi_eval.cu", "ndi_grid.cu", "ndi_internal.h", "ndi_sweep.cu")
+EVAL_SOURCES_1D = ("ndi_device.cuh", "ndi_eval.cu", "ndi_grid.cu", "ndi_internal.h")
+EVAL_SOURCES = EVAL_SOURCES_1D + ("ndi_bin.cu", "ndi_sweep.cu")          # bilinear: binning and band sweeps as well
 BUILD_SOURCES = ("ndi_device.cuh", "ndi_internal.h", "ndi_partition.cu", "ndi_rowsplit.cu", "ndi_spline.cu", "ndi_spline.cuh")
 
 
 def kernel_source_hash(files=EVAL_SOURCES):
     """sha256 over kernel sources: ties a recorded ncu capture to the kernels it was taken from.  The DRAM-traffic stamps
     (profiles/roofline_traffic.json) belong to the EVALUATION workloads, so they carry the hash of the sources the
-    evaluation kernels are compiled from; the spline-build sources have a hash of their own (`run.build_source_hash`)"""
+    evaluation kernels of that workload are compiled from (workload_sources); the spline-build sources have a hash of
+    their own (`run.build_source_hash`)"""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "ndarray_interp_b200", "csrc")
     for f in sorted(files):
         h.update(f.encode())
         h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
+
+
+def workload_sources(name):
+    return EVAL_SOURCES if WORKLOADS[name]["kind"] == "bilinear" else EVAL_SOURCES_1D
 
 
 def recorded_traffic(name, nq):
@@ -140,7 +146,7 @@ def recorded_traffic(name, nq):
     if not isinstance(e, dict) or e.get("bytes") is None:
         return None, None
     stamp = {k: e.get(k) for k in ("commit", "source_hash", "capture", "per")}
-    stamp["current"] = e.get("source_hash") == kernel_source_hash()
+    stamp["current"] = e.get("source_hash") == kernel_source_hash(workload_sources(name))
     if e.get("queries") not in (None, nq):
         stamp["bytes_at_capture_size"] = e["bytes"]
         return None, stamp

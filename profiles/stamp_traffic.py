@@ -37,14 +37,21 @@ def main():
     import bench
     out = {"_note": "dram__bytes_read.sum + dram__bytes_write.sum per STEP (all launches of the step) from `ncu --set full` "
                     "captures summarised under profiles/; each entry names the commit and the hash of the evaluation-kernel "
-                    "sources (bench.py: EVAL_SOURCES, kernel_source_hash) it was taken from -- bench.py reports "
-                    "`current: false` when those sources have changed since; written by profiles/stamp_traffic.py"}
+                    "sources of its workload (bench.py: workload_sources, kernel_source_hash) it was taken from -- "
+                    "bench.py reports `current: false` when those sources have changed since; written by "
+                    "profiles/stamp_traffic.py"}
+    try:                                             # entries whose summaries are not in `d` keep their capture
+        for k, v in json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).items():
+            if k != "_note":
+                out[k] = v
+    except Exception:
+        pass
     for wl, (files, nq) in STEPS.items():
         paths = [os.path.join(d, f) for f in files]
         if not all(os.path.exists(p) for p in paths):
             continue
         out[wl] = {"bytes": sum(dram_bytes(p) for p in paths), "per": f"step of {nq} queries", "queries": nq, "commit": commit,
-                   "source_hash": bench.kernel_source_hash(),
+                   "source_hash": bench.kernel_source_hash(bench.workload_sources(wl)),
                    "capture": " + ".join(os.path.relpath(p, ROOT) for p in paths)}
     json.dump(out, open(os.path.join(ROOT, "profiles", "roofline_traffic.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
