@@ -80,23 +80,14 @@ __global__ void __launch_bounds__(kBinBlock) bin_totals_kernel(const BinArgs<T> 
     const GridView<T> g = make_grid_view<T>(p.gx, p.n, p.scx, smem_raw, &bar);
     for (int i = threadIdx.x; i <= kMaxBands; i += kBinBlock) hist[i] = 0;
     __syncthreads();
-    // the next chunk's queries are requested before this chunk's are used: a block that waits for its loads at the
-    // top of every chunk spends a fifth of its time there (profiles/r02/ncu_c5a_bin_scatter.txt)
-    T xn[kBinPerThread];
-    auto request = [&](long long chunk) {
-#pragma unroll
-        for (int k = 0; k < kBinPerThread; ++k) {
-            const long long i = chunk * kBinChunk + k * kBinBlock + threadIdx.x;
-            xn[k] = (chunk < p.nchunks && i < p.nq) ? __ldg(p.qx + i) : g.g0;
-        }
-    };
-    request(blockIdx.x);
     for (long long chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x) {
         const long long base = chunk * kBinChunk;
         T x[kBinPerThread]; int band[kBinPerThread];
 #pragma unroll
-        for (int k = 0; k < kBinPerThread; ++k) x[k] = xn[k];
-        request(chunk + gridDim.x);
+        for (int k = 0; k < kBinPerThread; ++k) {
+            const long long i = base + k * kBinBlock + threadIdx.x;
+            x[k] = i < p.nq ? __ldg(p.qx + i) : g.g0;
+        }
         bands_of<T, kBinPerThread>(g, x, p.band_shift, band);
 #pragma unroll
         for (int k = 0; k < kBinPerThread; ++k)
@@ -141,24 +132,16 @@ __global__ void __launch_bounds__(kBinBlock) bin_scatter_kernel(const BinArgs<T>
         if (threadIdx.x < kMaxBands) { band_base[threadIdx.x] = e; hist[threadIdx.x] = 0; }
     }
     __syncthreads();
-    // queries of the next chunk requested one chunk ahead (see bin_totals_kernel)
-    T xn[kBinPerThread], yn[kBinPerThread];
-    auto request = [&](long long chunk) {
-#pragma unroll
-        for (int k = 0; k < kBinPerThread; ++k) {
-            const long long i = chunk * kBinChunk + k * kBinBlock + threadIdx.x;
-            const bool live = chunk < p.nchunks && i < p.nq;
-            xn[k] = live ? ld_query(p.qx + i) : g.g0;
-            yn[k] = live ? ld_query(p.qy + i) : g.g0;
-        }
-    };
-    request(blockIdx.x);
     for (long long chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x) {
         const long long base = chunk * kBinChunk;
         T x[kBinPerThread], y[kBinPerThread]; int band[kBinPerThread]; unsigned rank[kBinPerThread];
 #pragma unroll
-        for (int k = 0; k < kBinPerThread; ++k) { x[k] = xn[k]; y[k] = yn[k]; }
-        request(chunk + gridDim.x);
+        for (int k = 0; k < kBinPerThread; ++k) {
+            const long long i = base + k * kBinBlock + threadIdx.x;
+            const bool live = i < p.nq;
+            x[k] = live ? ld_query(p.qx + i) : g.g0;
+            y[k] = live ? ld_query(p.qy + i) : g.g0;
+        }
         bands_of<T, kBinPerThread>(g, x, p.band_shift, band);
 #pragma unroll
         for (int k = 0; k < kBinPerThread; ++k)
