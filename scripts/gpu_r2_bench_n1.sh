@@ -2,6 +2,7 @@
 # the default bench line and the reference arm at one GPU (what the driver runs at round end)
 mkdir -p gpurun_out/final
 T=gpurun_out/final
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 ( time timeout 1200 python bench.py > ${T}/bench_n1.json 2> ${T}/bench_n1.err ) 2> ${T}/bench_n1.time; echo "bench rc=$?"; tail -3 ${T}/bench_n1.time; tail -c 300 ${T}/bench_n1.err
 ( time timeout 600 python bench.py --impl reference > ${T}/bench_reference.json 2> ${T}/bench_reference.err ) 2> ${T}/bench_reference.time; echo "reference arm rc=$?"
 python - <<'PY'
