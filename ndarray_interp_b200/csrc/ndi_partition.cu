@@ -33,10 +33,6 @@ namespace ndi {
 #define FMA A<T>::fma
 
 constexpr int kPartLevelsMax = 16;
-#ifndef NDI_PART_FUSE_RHS
-#define NDI_PART_FUSE_RHS 1
-#endif
-constexpr bool kPartFuseRhs = NDI_PART_FUSE_RHS != 0;    // level 0 forms its right-hand sides itself (part_local_y_kernel)
 constexpr int kPartTopMax = 128;                     // rows of the directly solved system: min(kPartTopMax, 4 m)
 
 // Level l: a tridiagonal system of `len` rows; its row j lives in row (j + 1) * stride - 1 of the scratch matrix R
@@ -279,106 +275,6 @@ __global__ void __launch_bounds__(128) part_local_kernel(const PartPlan pl, int 
     }
 }
 
-// what part_local_y_kernel needs to form the right-hand sides of level 0 itself
-template <class T>
-struct PartData {
-    const T* x; const T* y; int n, periodic; Side<T> left, right; const T* lvs; const T* rvs; unsigned long long* err;
-};
-
-// Level 0 with the right-hand sides formed in the same pass (solve_for_k :456-471 interior rows, :599-669 boundary rows,
-// :521-532 periodic; the two divisions of an interior row by grid steps go through the reciprocals the factor kernel
-// left in fac -- ndi_device.cuh, Hoisted: the IEEE quotients): one thread per (block, column) as in part_local_kernel,
-// but the thread's window of y and its swept right-hand sides live in a shared-memory column of its own
-// (tile[row][thread], conflict-free) instead of registers.  (The register version of this fusion needed 192 registers
-// and lost to the two separate kernels, profiles/r02/partition_build.md; this one needs 40.)  y is read once, g written
-// once; the separator's right-hand side is left in R for the level above.
-constexpr int kPlyThreads = 128;
-template <class T>
-__global__ void __launch_bounds__(kPlyThreads) part_local_y_kernel(const PartPlan pl, T* fac, size_t fac_stride, T* __restrict__ R,
-                                                                  long long w, const int32_t* __restrict__ lks,
-                                                                  const int32_t* __restrict__ rks, const PartData<T> dt) {
-    extern __shared__ __align__(16) unsigned char ply_smem[];
-    T* S = reinterpret_cast<T*>(ply_smem) + threadIdx.x;              // slot j of this thread: S[j * kPlyThreads]
-    const PartLevel L = pl.lv[0];
-    const int m = pl.m, P = L.len / m, tail = L.len - P * m, nblk = P + (tail > 0 ? 1 : 0);
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long c64 = gid / w, col = gid - c64 * w;
-    if (c64 >= nblk) return;
-    const int c = (int)c64, n = dt.n;
-    T* facb = fac + (lks ? (size_t)part_group(lks, rks, col) * fac_stride : 0);
-    const int first = c * m, cnt = c < P ? m - 1 : tail, rows = c < P ? m : tail;   // rows: with the separator
-    const FacRow<T>* fr = PartArrays<T>(facb, L).fr + first;
-    const T* ycol = dt.y + col;
-    auto Y = [&](int row) -> T { return __ldg(ycol + (long long)row * w); };
-    // slots 0 .. rows + 1 = y[first - 1 .. first + rows] (rows outside the table: 0 -- they only reach right-hand sides
-    // that are replaced below)
-#pragma unroll 8
-    for (int j = 0; j <= rows + 1; ++j) {
-        const int gi = first - 1 + j;
-        S[j * kPlyThreads] = (gi >= 0 && gi < n) ? Y(gi) : (T)0;
-    }
-    // boundary rows of the system, where this thread owns them
-    Side<T> sl = specialize(dt.left), sr = specialize(dt.right);
-    if (lks) { sl = specialize(Side<T>{lks[col], dt.lvs[col]}); sr = specialize(Side<T>{rks[col], dt.rvs[col]}); }
-    const T three = (T)3;
-    T first_rhs = (T)0, last_rhs = (T)0;
-    const bool own_last = !dt.periodic && first + rows == n;
-    if (c == 0) {
-        if (dt.periodic) {
-            const T* x = dt.x;
-            const T dx0 = SUB(x[1], x[0]), dx_1 = SUB(x[n - 1], x[n - 2]);
-            const T y0 = Y(0), yN = Y(n - 1);
-            if (y0 != yN) atomicMin(dt.err, (unsigned long long)col);                             // :499-507
-            const T slope0 = DIV(SUB(Y(1), y0), dx0);                                             // :521
-            const T slope_1 = DIV(SUB(yN, Y(n - 2)), dx_1);                                       // :526
-            first_rhs = MUL(ADD(MUL(slope_1, dx0), MUL(slope0, dx_1)), three);                    // :529-530
-        } else {
-            first_rhs = rhs_left<T>(dt.x, sl, Y(0), Y(1), Y(2));
-        }
-    }
-    if (own_last) last_rhs = rhs_right<T>(dt.x, n, sr, Y(n - 1), Y(n - 2), Y(n - 3));
-    if (dt.periodic && c == nblk - 1) {                                                           // :531-532, kept for k_m1
-        const T* x = dt.x;
-        const T dx_1 = SUB(x[n - 1], x[n - 2]), dx_2 = SUB(x[n - 2], x[n - 3]);
-        const T yn2 = Y(n - 2);
-        const T slope_1 = DIV(SUB(Y(n - 1), yn2), dx_1), slope_2 = DIV(SUB(yn2, Y(n - 3)), dx_2);
-        R[(long long)(n - 2) * w + col] = MUL(ADD(MUL(slope_2, dx_1), MUL(slope_1, dx_2)), three);
-    }
-    // interior rows: 3 (d_i e_{i-1} / d_{i-1} + d_{i-1} e_i / d_i), e_i = y[i+1] - y[i], d_i = x[i+1] - x[i]   (:468),
-    // swept forward as they are formed (:698); the swept value of row t takes the slot of y[first - 1 + t], which no
-    // later row reads
-    const T* dx = fac;
-    const T* rdx = fac + (size_t)n;
-    T dp = first > 0 ? __ldg(dx + first - 1) : (T)1, rp = first > 0 ? __ldg(rdx + first - 1) : (T)0;
-    T e_prev = SUB(S[kPlyThreads], S[0]), f_prev = (T)0;
-    for (int t = 0; t < rows; ++t) {
-        const int i = first + t;
-        const bool has = i + 1 < n;
-        const T di = has ? __ldg(dx + i) : (T)1, ri = has ? __ldg(rdx + i) : (T)0;
-        const T e_cur = SUB(S[(t + 2) * kPlyThreads], S[(t + 1) * kPlyThreads]);
-        T val = MUL(three, ADD(Hoisted<T>::div(MUL(di, e_prev), dp, rp), Hoisted<T>::div(MUL(dp, e_cur), di, ri)));
-        if (t == 0 && c == 0) val = first_rhs;
-        if (own_last && t == rows - 1) val = last_rhs;
-        if (t < cnt) {
-            if (t > 0) val = FMA(-ld_fac<T>(fr + t).wl, f_prev, val);
-            S[t * kPlyThreads] = val;
-            f_prev = val;
-        } else {
-            R[(long long)i * w + col] = val;                           // the separator's right-hand side, for the level above
-        }
-        dp = di; rp = ri; e_prev = e_cur;
-    }
-    // backward (:704-720)
-    T nxt = (T)0;
-    for (int t = cnt - 1; t >= 0; --t) {
-        const FacRow<T> f = ld_fac<T>(fr + t);
-        const T v = S[t * kPlyThreads];
-        const T val = MUL(t == cnt - 1 ? v : FMA(-f.up, nxt, v), f.rmid);
-        R[(long long)(first + t) * w + col] = val;
-        nxt = val;
-    }
-}
-
 // The last level: a block takes kTopCols columns (few, so that many SMs take part: the kernel is a chain of 2 len
 // dependent steps per column whatever the block does); all its threads form the right-hand sides into shared memory,
 // one lane per column runs the two recurrences there (factors staged in shared memory unless the columns have
@@ -524,12 +420,12 @@ static void part_launch_local(const PartPlan& pl, int l, T* fac, size_t fac_stri
     count_launch();
 }
 
-// the solve on R, whose level-0 rows hold the right-hand sides (dt: they are formed from dt->y by the first kernel).
+// the solve on R, whose level-0 rows hold the right-hand sides.
 // final0: 0 leaves level 0 uncorrected (g in the block rows, k in the separator rows) for part_ab_kernel.
 // ev0 / join: waited for before the first kernel that needs the factorisation of level 0 / of the levels above it.
 template <class T>
 static cudaError_t part_solve(const PartPlan& pl, T* fac, size_t fac_stride, T* R, long long w, const int32_t* lk, const int32_t* rk,
-                              const PartData<T>* dt, bool final0, cudaEvent_t ev0, cudaEvent_t join, cudaStream_t st) {
+                              bool final0, cudaEvent_t ev0, cudaEvent_t join, cudaStream_t st) {
     cudaError_t e;
     if (ev0 && (e = cudaStreamWaitEvent(st, ev0, 0)) != cudaSuccess) return e;
     for (int l = 0; l < pl.nsplit; ++l) {
@@ -538,14 +434,7 @@ static cudaError_t part_solve(const PartPlan& pl, T* fac, size_t fac_stride, T* 
         const long long blocks = (nblk * w + 127) / 128;
         if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
         if (l == 1 && join && (e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
-        if (l == 0 && dt) {
-            const size_t smem = (size_t)(pl.m + 2) * kPlyThreads * sizeof(T);
-            if (smem > 48 * 1024 &&
-                (e = cudaFuncSetAttribute(part_local_y_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
-                return e;
-            part_local_y_kernel<T><<<(unsigned)((nblk * w + kPlyThreads - 1) / kPlyThreads), kPlyThreads, smem, st>>>(pl, fac, fac_stride, R, w, lk, rk, *dt);
-            count_launch();
-        } else if (l == 0) part_launch_local<T, PART_SRC_R>(pl, l, fac, fac_stride, R, w, lk, rk, (unsigned)blocks, st);
+        if (l == 0) part_launch_local<T, PART_SRC_R>(pl, l, fac, fac_stride, R, w, lk, rk, (unsigned)blocks, st);
         else part_launch_local<T, PART_SRC_LOWER>(pl, l, fac, fac_stride, R, w, lk, rk, (unsigned)blocks, st);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -621,16 +510,12 @@ cudaError_t launch_partition_build(const T* x, int64_t n, const T* data, int64_t
         if (lvl == 0 && forked && (e = cudaEventRecord(side.lvl0, ms)) != cudaSuccess) return e;
     }
     if ((e = top_factor(ms)) != cudaSuccess) return e;
-    if (periodic && (e = part_solve<T>(pl, fac, fac_stride, fac + 4 * (size_t)n, 1, nullptr, nullptr, nullptr, true, nullptr, nullptr, ms)) != cudaSuccess) return e;
+    if (periodic && (e = part_solve<T>(pl, fac, fac_stride, fac + 4 * (size_t)n, 1, nullptr, nullptr, true, nullptr, nullptr, ms)) != cudaSuccess) return e;
     if (forked && (e = cudaEventRecord(side.join, ms)) != cudaSuccess) return e;
-    // right-hand sides: formed by the block solve of level 0 itself; a system short enough to be solved directly
-    // takes them from the kernel of the other modes
-    const PartData<T> dt{x, data, (int)n, periodic, l, r, lv, rv, err};
-    const bool fused_rhs = pl.nsplit > 0 && kPartFuseRhs;
-    if (!fused_rhs && (e = launch_spline_rhs<T>(x, (int)n, data, (long long)w, periodic, l, r, R, err, ilk, lv, rk, rv, st)) != cudaSuccess) return e;
+    if ((e = launch_spline_rhs<T>(x, (int)n, data, (long long)w, periodic, l, r, R, err, ilk, lv, rk, rv, st)) != cudaSuccess) return e;
     const bool fused_ab = !periodic && pl.nsplit > 0 && pl.m >= 5;   // part_ab_kernel: a row group lies in at most two blocks
-    if ((e = part_solve<T>(pl, fac, fac_stride, R, (long long)w, ilk, rk, fused_rhs ? &dt : nullptr, !fused_ab,
-                           (forked && pl.nsplit > 0) ? side.lvl0 : nullptr, forked ? side.join : nullptr, st)) != cudaSuccess) return e;
+    if ((e = part_solve<T>(pl, fac, fac_stride, R, (long long)w, ilk, rk, !fused_ab, (forked && pl.nsplit > 0) ? side.lvl0 : nullptr,
+                           forked ? side.join : nullptr, st)) != cudaSuccess) return e;
     if (!fused_ab) {
         if (periodic && (e = launch_spline_periodic_close<T>(x, (int)n, (long long)w, fac, R, st)) != cudaSuccess) return e;
         return launch_spline_ab<T>(x, (int)n, data, (long long)w, periodic, fac, R, a, b, nullptr, st);
