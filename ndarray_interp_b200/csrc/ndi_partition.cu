@@ -275,14 +275,18 @@ __global__ void __launch_bounds__(128) part_local_kernel(const PartPlan pl, int 
     }
 }
 
-// The last level: a block takes kTopCols columns (few, so that many SMs take part: the kernel is a chain of 2 len
+// The last level: a block takes kTopCols columns (few -- kTopColsNarrow -- so that many SMs take part: the kernel is a chain of 2 len
 // dependent steps per column whatever the block does); all its threads form the right-hand sides into shared memory,
 // one lane per column runs the two recurrences there (factors staged in shared memory unless the columns have
 // matrices of their own), all threads write k back.
-constexpr int kTopCols = 8, kTopThreads = 256, kTopRowLanes = kTopThreads / kTopCols;
-template <class T>
+// (With enough columns to fill the machine at 32 per block -- kTopColsWide -- the wider block stages the factors a
+// quarter as often and needs a quarter of the blocks: 4096 x 16384 f32 build 0.544 -> 0.530 ms, 512 x 262144 1.126 ->
+// 1.066 ms; profiles/r02/partition_build.md.)
+constexpr int kTopColsNarrow = 8, kTopColsWide = 32, kTopThreads = 256;
+template <class T, int kTopCols>
 __global__ void __launch_bounds__(kTopThreads) part_top_kernel(const PartPlan pl, T* fac, size_t fac_stride, T* __restrict__ R, long long w,
                                                                const int32_t* __restrict__ lks, const int32_t* __restrict__ rks) {
+    constexpr int kTopRowLanes = kTopThreads / kTopCols;
     __shared__ T tile[kPartTopMax][kTopCols + 1];
     __shared__ T s_wl[kPartTopMax], s_up[kPartTopMax], s_rm[kPartTopMax];
     const int l = pl.nsplit;
@@ -439,7 +443,10 @@ static cudaError_t part_solve(const PartPlan& pl, T* fac, size_t fac_stride, T* 
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (pl.nsplit <= 1 && join && (e = cudaStreamWaitEvent(st, join, 0)) != cudaSuccess) return e;
-    part_top_kernel<T><<<(unsigned)((w + kTopCols - 1) / kTopCols), kTopThreads, 0, st>>>(pl, fac, fac_stride, R, w, lk, rk);
+    if (w >= (long long)kTopColsWide * device_info().sm_count)
+        part_top_kernel<T, kTopColsWide><<<(unsigned)((w + kTopColsWide - 1) / kTopColsWide), kTopThreads, 0, st>>>(pl, fac, fac_stride, R, w, lk, rk);
+    else
+        part_top_kernel<T, kTopColsNarrow><<<(unsigned)((w + kTopColsNarrow - 1) / kTopColsNarrow), kTopThreads, 0, st>>>(pl, fac, fac_stride, R, w, lk, rk);
     count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     for (int l = pl.nsplit - 1; l >= (final0 ? 0 : 1); --l) {
@@ -513,7 +520,7 @@ cudaError_t launch_partition_build(const T* x, int64_t n, const T* data, int64_t
     if (periodic && (e = part_solve<T>(pl, fac, fac_stride, fac + 4 * (size_t)n, 1, nullptr, nullptr, true, nullptr, nullptr, ms)) != cudaSuccess) return e;
     if (forked && (e = cudaEventRecord(side.join, ms)) != cudaSuccess) return e;
     if ((e = launch_spline_rhs<T>(x, (int)n, data, (long long)w, periodic, l, r, R, err, ilk, lv, rk, rv, st)) != cudaSuccess) return e;
-    const bool fused_ab = !periodic && pl.nsplit > 0 && pl.m >= 5;   // part_ab_kernel: a row group lies in at most two blocks
+    const bool fused_ab = !periodic && pl.nsplit > 0 && pl.m >= kRowGroup + 1;   // part_ab_kernel: a row group (kRowGroup + 1 rows from a multiple of kRowGroup) lies in at most two blocks
     if ((e = part_solve<T>(pl, fac, fac_stride, R, (long long)w, ilk, rk, !fused_ab, (forked && pl.nsplit > 0) ? side.lvl0 : nullptr,
                            forked ? side.join : nullptr, st)) != cudaSuccess) return e;
     if (!fused_ab) {

@@ -139,7 +139,10 @@ template <class T>
 cudaError_t launch_spline_sweep(int len, int nsys, long long w, const T* fac, size_t fac_stride, T* R,
                                 const int64_t* counts, cudaStream_t st);
 
-constexpr int kRowGroup = 4;              // rhs / ab kernels: rows per thread, sharing their loads
+#ifndef NDI_ROW_GROUP
+#define NDI_ROW_GROUP 4
+#endif
+constexpr int kRowGroup = NDI_ROW_GROUP;  // rhs / ab kernels: rows per thread, sharing their loads
 int row_group_grid(long long wv, long long nrows);      // grid for items of kRowGroup rows x one vector of columns
 // V consecutive columns as one 16-byte access (V == 1: a plain element)
 template <class T, int V>
