@@ -85,9 +85,10 @@ def test_first_error_across_two_ranks(bad_positions):
         assert gathered == list(map(float, range(6)))
 
 
-def _data_worker(rank, world, port, results):
+def _data_worker(rank, world, port, results, info):
     """the multi-GPU data flow of bench.py on CPU, the oracle standing in for the kernels: spline built on a column
-    shard, coefficients all-gathered, queries evaluated per contiguous block, blocks gathered"""
+    shard (info: the build the kernels would report -- 0 reference order, -m partition blocks), coefficients
+    all-gathered, queries evaluated per contiguous block, blocks gathered"""
     from oracle import oracle_py as O
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -100,7 +101,7 @@ def _data_worker(rank, world, port, results):
         q = np.sort(rng.uniform(x[0], x[-1], nq))
         q[700] = x[-1] + 1.0                                    # a failing query in the second block
         c_lo, c_hi = P.column_shards(w, world)[rank]
-        st, a_sh, b_sh = O.spline_build(x, np.ascontiguousarray(y[:, c_lo:c_hi]), {"kind": "Natural"})
+        st, a_sh, b_sh = O.spline_build_as(x, np.ascontiguousarray(y[:, c_lo:c_hi]), {"kind": "Natural"}, info)
         assert st == 0
         ga = [torch.empty((n - 1, c_hi - c_lo), dtype=torch.float64) for _ in range(world)]
         gb = [torch.empty((n - 1, c_hi - c_lo), dtype=torch.float64) for _ in range(world)]
@@ -119,19 +120,20 @@ def _data_worker(rank, world, port, results):
         dist.destroy_process_group()
 
 
-def test_sharded_build_allgather_and_sharded_evaluation_equal_the_single_process_result():
+@pytest.mark.parametrize("info", [0, -8], ids=["reference-order", "partition"])
+def test_sharded_build_allgather_and_sharded_evaluation_equal_the_single_process_result(info):
     from oracle import oracle_py as O
     world = 2
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_data_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    mp.spawn(_data_worker, args=(world, _free_port(), results, info), nprocs=world, join=True)
     rng = np.random.default_rng(11)
     n, w, nq = 200, 8, 1001
     x = np.cumsum(rng.uniform(0.5, 1.5, n))
     y = rng.normal(size=(n, w))
     q = np.sort(rng.uniform(x[0], x[-1], nq))
     q[700] = x[-1] + 1.0
-    st, a, b = O.spline_build(x, y, {"kind": "Natural"})
+    st, a, b = O.spline_build_as(x, y, {"kind": "Natural"}, info)
     st, ref, bad = O.interp1d_cubic(x, y, a, b, q, 0, out=np.full((nq, w), -1.0))
     assert bad == 700
     for r in range(world):
