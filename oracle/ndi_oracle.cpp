@@ -19,13 +19,17 @@
 //
 // Reference citations are relative to /root/reference/.
 //
-// One function here is NOT a restatement of the reference: rowsplit_thomas (ora_spline_build_rowsplit_*), the
-// operation-by-operation specification of a row-split (PCR + Thomas) solve that is not built yet (DESIGN.md section
-// 7); it is checked against the sequential solve at north_star's tolerances and never used for parity of shipped code.
+// Two functions here are NOT restatements of the reference: rowsplit_thomas (ora_spline_build_rowsplit_*) and
+// partition_thomas (ora_spline_build_partition_*), the operation-by-operation specifications of the two other solves the
+// product offers for the spline build (csrc/ndi_rowsplit.cu: cyclic reduction + Thomas; csrc/ndi_partition.cu: block
+// partition).  Each is checked against the sequential solve above at north_star's tolerances
+// (tests/test_oracle_golden.py) and is what those kernels are compared with bit for bit; the reference-order functions
+// remain the statement of the reference's own arithmetic, and parity with the reference is claimed through them only.
 //
-// Element types: f32, f64 (all entry points) and i32 / i64 (everything except splines, which
+// Element types: f32, f64 (all entry points) and i32 / i64 / u32 / u64 (everything except splines, which
 // the reference restricts to float types through SplineNum, cubic_spline.rs:34-49).
-// Integer arithmetic wraps on overflow like a Rust release build.
+// Integer arithmetic wraps on overflow like a Rust release build (pinned against big-integer arithmetic modulo 2^bits,
+// tests/test_oracle_golden.py::test_integer_arithmetic_*).
 
 #include <cmath>
 #include <cstdint>
