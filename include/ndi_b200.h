@@ -194,7 +194,9 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
  *                         rounding (fused multiply-adds), inside the same bars, bit-identical to the oracle's
  *                         specification of the same scheme.
  *   NDI_BUILD_AUTO        partition (blocks of 32 rows) for tables of 1024 rows or more, the reference's order
- *                         otherwise (default).
+ *                         otherwise (default) -- and also where a NotAKnot row on the right meets a grid whose last
+ *                         step is about 0.55 of the one before it: the reference's system (cubic_spline.rs:635) is
+ *                         then nearly singular and only its own order of operations reproduces its result.
  * ndi_interp1d_build_info reports how the current coefficients were built: 0 reference order, L > 0 row-split with L
  * levels, -m < 0 partition with blocks of m rows. */
 #define NDI_BUILD_AUTO 0

@@ -367,6 +367,7 @@ struct ndi_interp1d {
     void* pair = nullptr;            // pair table for thin-row Linear (ndi_eval.cu: rows i, i+1 interleaved), owned
     int build_mode = NDI_BUILD_AUTO, build_levels = 0;   // spline solve: reference order or row-split (ndi_rowsplit.cu)
     int built_levels = kNotBuilt;    // how the current coefficients were built: 0 reference order, L > 0 row-split levels, -m partition blocks
+    double nak_pivot = -1.0;         // last eliminated pivot of the NotAKnot system relative to its diagonal entry (< 0: not formed yet)
     GridAids aids;
     GridMeta meta() const { return aids.meta(x, n, elem_size(dtype), uniform_hint); }
 };
@@ -1018,6 +1019,38 @@ ndi_status ndi_interp1d_linear(const ndi_interp1d* h, const void* q, int64_t nq,
 }
 
 // ---- cubic spline ---------------------------------------------------------------------------------------------
+// The reference's NotAKnot system takes x[n-1] - x[n-2] for the last diagonal entry (cubic_spline.rs:635, the quirk kept
+// on purpose).  With that entry the last pivot of the elimination,
+//     mid'[n-1] = (x[n-1] - x[n-2]) - (x[n-1] - x[n-3]) / mid'[n-2] * (x[n-2] - x[n-3]),
+// vanishes when the last grid step is about 0.55 of the one before it: the reference's own result is then the quotient of
+// two rounding errors, and any other order of operations moves it by as much (partition against reference order, f32:
+// up to 6e-5 of the column's scale inside |pivot| < 0.03 of the entry, 3e-6 up to 0.1, 1e-6 beyond; profiles/r02/
+// partition_build.md).  NDI_BUILD_AUTO therefore keeps the reference's order -- and with it the reference's bits --
+// whenever a right NotAKnot row meets such a grid.  The pivot ratio is formed once per handle from the last grid points
+// (the elimination forgets its start at a rate of ~0.07 per row; 64 rows are exact to double precision).
+constexpr double kNakPivotFloor = 0.1;
+static ndi_status nak_pivot_ratio(ndi_interp1d* h, cudaStream_t st, double* ratio) {
+    if (h->nak_pivot >= 0.0) { *ratio = h->nak_pivot; return NDI_OK; }
+    const int64_t n = h->n, cnt = n < 67 ? n : 67;
+    const size_t es = elem_size(h->dtype);
+    unsigned char raw[67 * 8];
+    CK(cudaMemcpyAsync(raw, (const unsigned char*)h->x + (size_t)(n - cnt) * es, (size_t)cnt * es, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    double x[67];
+    for (int64_t i = 0; i < cnt; ++i) {
+        if (h->dtype == NDI_F32) { float v; memcpy(&v, raw + i * 4, 4); x[i] = v; }
+        else { double v; memcpy(&v, raw + i * 8, 8); x[i] = v; }
+    }
+    // rows 1 .. cnt-2 of the window are interior rows (:440-451); the first one starts from its own diagonal entry
+    double mp = 2.0 * (x[2] - x[0]);
+    for (int64_t i = 2; i + 1 < cnt; ++i) mp = 2.0 * (x[i + 1] - x[i - 1]) - (x[i + 1] - x[i]) / mp * (x[i - 1] - x[i - 2]);
+    const double mid = x[cnt - 1] - x[cnt - 2], low = x[cnt - 1] - x[cnt - 3], up = x[cnt - 2] - x[cnt - 3];
+    double r = fabs(mid - low / mp * up) / fabs(mid);
+    if (!(r == r)) r = 0.0;
+    h->nak_pivot = r; *ratio = r;
+    return NDI_OK;
+}
+
 ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int32_t* left_kind, const void* left_val,
                                      const int32_t* right_kind, const void* right_val, int64_t* bad_column) {
     if (bad_column) *bad_column = -1;
@@ -1041,7 +1074,19 @@ ndi_status ndi_interp1d_spline_build(ndi_interp1d* h, int32_t bc_kind, const int
     // and the row-split build at every measured shape from there on, few long columns (4096 x 1024 f64: 0.11 against 0.91
     // and 0.20 ms) as well as many (4096 x 16384 f32: 0.54 against 1.01 and 1.40 ms); at 512 rows the three are level
     // (profiles/r02/partition_build.md).  Shorter systems keep the reference's order and with it the reference's bits.
-    if (h->n >= 4 && (mode == NDI_BUILD_PARTITION || (mode == NDI_BUILD_AUTO && h->n >= kPartitionAutoRows)))
+    bool auto_partition = mode == NDI_BUILD_AUTO && h->n >= kPartitionAutoRows;
+    if (auto_partition) {                                     // a NotAKnot row on the right over a grid that makes the reference's system singular?
+        bool right_nak = bc_kind == NDI_BC_NOT_A_KNOT;
+        if (bc_kind == NDI_BC_INDIVIDUAL)
+            for (int64_t c = 0; c < h->w && !right_nak; ++c) right_nak = right_kind[c] == NDI_SB_NOT_A_KNOT;
+        if (right_nak && (h->dtype == NDI_F32 || h->dtype == NDI_F64)) {
+            double ratio = 1.0;
+            ndi_status ps = nak_pivot_ratio(h, ws->s[0], &ratio);
+            if (ps != NDI_OK) return ps;
+            if (ratio < kNakPivotFloor) auto_partition = false;
+        }
+    }
+    if (h->n >= 4 && (mode == NDI_BUILD_PARTITION || auto_partition))
         levels = -partition_block_for(mode == NDI_BUILD_PARTITION ? want_levels : 0);   // negative: partition build, blocks of that many rows
     else if (h->n >= 4 && mode == NDI_BUILD_ROWSPLIT)
         levels = rowsplit_levels_for(bc_kind == NDI_BC_PERIODIC ? h->n - 2 : h->n, want_levels, true);

@@ -58,7 +58,9 @@ def test_fuzz_spline_build_and_eval(seed):
     strat = CubicSpline.new().extrapolate(extrap).boundary(getattr(BoundaryCondition, bc))
     ip = Interp1DBuilder.new(y).x(g).strategy(strat).build()
     info = ip.strategy.rowsplit_levels(ip)
-    assert info == (-32 if n >= 1024 else 0)                  # AUTO: the reference's order below 1024 rows, partition from there on
+    # AUTO: the reference's order below 1024 rows, partition from there on (NotAKnot: unless the grid makes the
+    # reference's system nearly singular, test_partition_gpu.py::test_auto_keeps_the_reference_order_on_a_singular_*)
+    assert info == (-32 if n >= 1024 else 0) or (bc == "NotAKnot" and info == 0)
     st, a_ref, b_ref = O.spline_build_as(g, y, {"kind": bc}, info)
     assert st == O.ST_OK
     a, b = ip.strategy.coefficients(ip)

@@ -86,3 +86,34 @@ def test_partition_long_columns_f64_and_many_columns_f32():
         ok, err = eval_close(g, y, a, b, a_ref, b_ref, rng)
         assert ok, err
         assert same(interp.interp_array(g[:-1]), y[:-1])
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64], ids=["f32", "f64"])
+def test_auto_keeps_the_reference_order_on_a_singular_not_a_knot_system(dt):
+    """the reference's NotAKnot system takes x[n-1] - x[n-2] for its last diagonal entry (cubic_spline.rs:635); its last
+    pivot vanishes when the last grid step is about 0.55 of the one before it, and the reference's result is then only
+    reproduced by its own order of operations: AUTO keeps that order there (bit-identical coefficients), takes the
+    partition build for the same grid under another boundary, and for NotAKnot on a grid without that property"""
+    rng = np.random.default_rng(5)
+    n, w = 2000, 6
+    g = np.cumsum(rng.uniform(0.5, 1.5, n))
+    y = rng.normal(size=(n, w)).astype(dt)
+    for last_over_prev, expect in ((0.5359, 0), (1.0, -32), (0.2, -32)):
+        gg = g.copy()
+        gg[-1] = gg[-2] + last_over_prev * (gg[-2] - gg[-3])
+        gg = gg.astype(dt)
+        interp = build(gg, y, BoundaryCondition.NotAKnot, "auto")
+        info = interp.strategy.rowsplit_levels(interp)
+        a, b = interp.strategy.coefficients(interp)
+        st, a_ref, b_ref = O.spline_build_as(gg, y, {"kind": "NotAKnot"}, info)
+        assert st == O.ST_OK and same(a, a_ref) and same(b, b_ref)
+        if expect == 0:
+            assert info == 0, (last_over_prev, info)
+        nat = build(gg, y, BoundaryCondition.Natural, "auto")
+        assert nat.strategy.rowsplit_levels(nat) == -32
+        # per-column boundaries: one NotAKnot on the right is enough
+        rows, spec = individual(rng, w)
+        ind = build(gg, y, BoundaryCondition.Individual([rows]), "auto")
+        has_right_nak = any(s.get("kind") == "NotAKnot" or (s.get("kind") == "Mixed" and s["right"]["kind"] == "NotAKnot") for s in spec)
+        if expect == 0 and has_right_nak:
+            assert ind.strategy.rowsplit_levels(ind) == 0
