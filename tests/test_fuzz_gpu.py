@@ -21,7 +21,10 @@ EDGE_Q = [1, 2, 31, 32, 33, 63, 64, 65, 255, 1000, 2047, 2048, 2049, 4097, 10000
 @pytest.mark.parametrize("seed", range(44))
 def test_fuzz_linear_and_bilinear(seed):
     rng = np.random.default_rng(9000 + seed)
-    dt = [np.float32, np.float64, np.int32][seed % 3] if seed < 24 else (np.int64 if seed < 32 else [np.uint32, np.uint64][seed % 2])
+    if seed < 44:
+        dt = [np.float32, np.float64, np.int32][seed % 3] if seed < 24 else (np.int64 if seed < 32 else [np.uint32, np.uint64][seed % 2])
+    else:                                                          # scripts/fuzz_eval.py: further seeds cycle through every element type
+        dt = [np.float32, np.float64, np.int32, np.int64, np.uint32, np.uint64][seed % 6]
     n, m = int(rng.choice(EDGE_N)), int(rng.choice(EDGE_N[:14]))
     w, nq = int(rng.choice(EDGE_W)), int(rng.choice(EDGE_Q))
     extrap = bool(seed & 1)
