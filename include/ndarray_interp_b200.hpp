@@ -338,6 +338,7 @@ public:
     // how the coefficients were built (ndi_interp1d_build_info): 0 the reference's elimination order, L > 0 row-split
     // with L levels, -m < 0 partition with blocks of m rows
     int rowsplit_levels(const Interp1D<T>& ip) const;
+    int build_info(const Interp1D<T>& ip) const { return rowsplit_levels(ip); }
     bool uses_device() const override { return true; }
     void bind(const Interp1D<T>& ip) const override;         // CubicSpline::calc_coefficients (:310-368) on the device
     void interp_batch_into(const Interp1D<T>& ip, const T* xs, size_t nq, T* out_rows) const override;

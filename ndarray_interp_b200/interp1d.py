@@ -267,6 +267,8 @@ class CubicSplineStrategy(Interp1DStrategy):
         L.check(L.load().ndi_interp1d_build_info(interpolator._handle(), C.byref(lv)))
         return lv.value
 
+    build_info = rowsplit_levels          # the name says what it returns since the partition build exists
+
     def coefficients(self, interpolator):
         """(a, b) copied back from the device: shape (n-1, ...data.shape[1:])"""
         d = interpolator.data
