@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(32 * kPfWarps) part_factor_kernel(const T* __r
         a.fr[first + t] = FacRow<T>{uu[t], mi[t], wl[t], r};
     }
     __syncwarp();
-    if (lane == 0) {                                                  // p = A^-1 (low[first] e_first); wl[] becomes its forward sweep
+    if (lane == 0) {                                                  // p = A^-1 (low[first] e_first); lo[] becomes its forward sweep
         T f = lo[0];
         T* fw = s_lo[wi];
         fw[0] = f;
