@@ -35,3 +35,20 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 def test_reference_arm_other_ranks_exit_silently():
     r = run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2")
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_traffic_stamps_name_committed_captures_of_the_current_kernel_sources():
+    """profiles/roofline_traffic.json: every entry points at ncu summaries that are in the tree, carries the commit of
+    its capture, and -- as long as nobody has edited the evaluation kernels since -- the hash bench.py compares with"""
+    sys.path.insert(0, ROOT)
+    import bench
+    d = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    entries = {k: v for k, v in d.items() if k != "_note"}
+    assert set(entries) == {"c2", "c3", "c4", "c5a", "c5b"}
+    for name, e in entries.items():
+        assert e["bytes"] > 0 and e["commit"] and len(e["source_hash"]) == 16
+        for cap in e["capture"].split(" + "):
+            assert os.path.exists(os.path.join(ROOT, cap.split(" (")[0])), cap
+        traffic, stamp = bench.recorded_traffic(name, e["queries"])
+        assert traffic == e["bytes"] and stamp["commit"] == e["commit"]
+        assert stamp["current"] == (e["source_hash"] == bench.kernel_source_hash(bench.workload_sources(name)))
